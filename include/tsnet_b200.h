@@ -1,0 +1,176 @@
+/*
+ * libtsnet_sm100.so -- C ABI of the B200-native TS-Net forward hot path.
+ *
+ * The reference (nihaomiao/WACV23_TSNet) has no FFI: its hot path is the body of
+ * TSNet.forward() (model/TSNet.py:309-407, model/TSNet_pose.py:325-417) expressed as stock torch ops.
+ * Each entry point below replaces a group of those ops; the reference lines are cited per function.
+ * The Python class wacv23_tsnet_b200.model.TSNet.TSNet (same surface as the reference class) binds
+ * these through ctypes (wacv23_tsnet_b200/lib.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer (the caller -- PyTorch -- owns the memory and keeps
+ *     it alive until the stream has drained); descriptors (`*_desc`) are host structs;
+ *   - functions only ENQUEUE work on `stream` (a cudaStream_t passed as void*); they never
+ *     synchronise and never allocate: all workspaces are caller-provided;
+ *   - return 0 on success, <0 for argument errors, >0 = cudaError_t; the message is available from
+ *     tsnet_last_error() (thread-local);
+ *   - there is NO CPU fallback: without an sm_100a device the launch fails and the error is returned.
+ *
+ * Data layouts in HBM
+ *   activation ("act")   fp32 NHWC  [B, H, W, C]
+ *   tap source ("taps")  16-bit hi and lo planes, NHWC with padding already applied:
+ *                        [B * planes, Hp, Wp, Cp], Cp % 64 == 0; value = hi + lo (3-term split operand)
+ *   packed weight        16-bit hi and lo, K-major [Cout_pad, num_taps * Cp]
+ *   instance statistics  partial  [B * H*W/32, C, 2] = (sum, centred M2) per 32-pixel run
+ *                        reduced  [B, C, 2]          = (mean, 1/sqrt(var + eps))
+ */
+#ifndef TSNET_B200_H_
+#define TSNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSNET_ABI_VERSION 1
+
+/* 16-bit operand format of the tensor-core path */
+#define TSNET_FMT_FP16 0
+#define TSNET_FMT_BF16 1
+
+/* tap-source builder modes (tsnet_build_taps) */
+#define TSNET_TAPS_SAME 0     /* no padding: 1x1 convs, channel-concat targets                       */
+#define TSNET_TAPS_REFLECT1 1 /* nn.ReflectionPad2d(1) for 3x3 stride-1 convs                       */
+#define TSNET_TAPS_S2ZERO 2   /* zero pad 1 + parity split into 4 planes for 3x3 stride-2 convs      */
+#define TSNET_TAPS_UP2REFLECT1 3 /* nn.Upsample(x2, bilinear, align_corners=False) + ReflectionPad2d(1) */
+
+#define TSNET_MAX_TAPS 49
+
+int tsnet_abi_version(void);
+const char* tsnet_last_error(void);
+/* 1 if the current device is compute capability 10.x, else 0 */
+int tsnet_device_ok(void);
+
+/* ---- weights --------------------------------------------------------------------------------
+ * nn.Conv2d weight [Cout, Cin, KH, KW] fp32 (state_dict layout) -> packed K-major hi/lo.
+ * fold_kw = 0: taps = KH*KW (row-major r,s), K per tap = Cp >= Cin, channel c at column tap*Cp + c.
+ * fold_kw = 1: taps = KH, K per tap = Cp >= KW*Cin, column tap*Cp + s*Cin + c  (7x7 stems, see
+ *              tsnet_stem_taps).  Rows >= Cout and unused columns are zero.
+ * scale: weights are multiplied by `scale` (power of two; FP16 mode range management) before the split. */
+int tsnet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, int fold_kw, int Cp,
+                           int Cout_pad, float scale, int fmt, uint16_t* w_hi, uint16_t* w_lo, void* stream);
+
+/* ---- implicit-GEMM convolution on tcgen05 ---------------------------------------------------
+ * Replaces nn.Conv2d (+ the preceding pad / upsample, which tsnet_build_taps folded into the tap
+ * source): model/TSNet.py:27,42 (ResnetBlock 3x3), :70 (stride-2), :66 (7x7 stem, kw-folded),
+ * :139 (map_conv 1x1), :147 (decoder up-convs), :193 (FuseNet 1x1).
+ * y_raw [B,H,W,Cout] fp32 = conv + bias (pre-norm); stats_partial as above (may be NULL). */
+typedef struct {
+  int B, H, W;      /* output geometry */
+  int Cout;         /* real output channels (multiple of 32) */
+  int Cout_pad;     /* rows of the packed weight, multiple of block_n */
+  int Cp;           /* K per tap = channels per pixel of the tap source (multiple of 64) */
+  int Hp, Wp, planes; /* tap source geometry */
+  int num_taps;
+  int8_t tap_dy[TSNET_MAX_TAPS], tap_dx[TSNET_MAX_TAPS], tap_plane[TSNET_MAX_TAPS];
+  int block_n;      /* 64, 128 or 256 */
+  int split;        /* 1: hi*hi + hi*lo + lo*hi (fp32-faithful); 0: hi*hi only (fast, non-parity) */
+  int fmt;          /* TSNET_FMT_* */
+  float out_scale;  /* accumulators are multiplied by this before bias (undo operand pre-scaling) */
+} tsnet_conv_desc;
+
+int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,
+                        const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
+                        float* stats_partial, void* stream);
+
+/* ---- InstanceNorm statistics -----------------------------------------------------------------
+ * nn.InstanceNorm2d(affine=False, eps=1e-5, biased variance): model/TSNet.py:28,43,66,71,149.
+ * partial [B*HW/32, C, 2] -> mean_rstd [B, C, 2]; fixed-order (deterministic) Chan merge in fp64. */
+int tsnet_instnorm_reduce(const float* stats_partial, int B, int HW, int C, float eps, float* mean_rstd,
+                          void* stream);
+
+/* ---- normalise / activate / residual / pad / split --------------------------------------------
+ * One pass over a raw conv output that produces what the NEXT layer needs:
+ *   v = raw; if mean_rstd: v = (v - mean) * rstd; if relu: v = max(v, 0); if residual: v += residual
+ *   act_out (optional) <- v (fp32 NHWC)      taps (optional) <- pad/upsample(mode)(v) split into hi/lo
+ * Replaces InstanceNorm + ReLU + residual add + ReflectionPad2d / Upsample / torch.cat of
+ * model/TSNet.py:19-48, 145-150, 163, 196 (cat = two producers writing channel ranges c_off of a
+ * wider tap source of Cp_total channels). */
+typedef struct {
+  int B, H, W, C;   /* source geometry */
+  int mode;         /* TSNET_TAPS_* */
+  int relu;
+  int Cp_total;     /* channels per pixel of the destination tap source */
+  int c_off;        /* first destination channel */
+  int fmt;
+  float scale;      /* activations are multiplied by `scale` before the split (power of two) */
+} tsnet_taps_desc;
+
+int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* mean_rstd, const float* residual,
+                     float* act_out, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
+
+/* ---- encoder stem input ------------------------------------------------------------------------
+ * Builds the kw-folded tap source of the 7x7 stem conv directly from the NCHW network inputs:
+ * torch.cat([img, lbl]) (model/TSNet.py:312), Encoder.coord_conv (:107-125, channels x, y, r generated
+ * analytically) and ReflectionPad2d(3) (:66).  Destination [B, H+6, W, Cp]: pixel (yp, x) holds, for
+ * s = 0..6, the Cin = Cimg + Clbl + 3 channels of source pixel (reflect(yp-3), reflect(x+s-3)).
+ * img may be NULL (label encoder).  img_scale multiplies the image (the /255 of set_*_input, :268-286). */
+int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_scale, const float* lbl_nchw, int Clbl, int B,
+                    int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
+
+/* ---- correlation operands ------------------------------------------------------------------------
+ * F.normalize(fea, p=2, dim=1) (model/TSNet.py:319, :339; eps = 1e-12) of an fp32 NHWC feature map
+ * [B, HW, C], written as 16-bit hi/lo K-major operands [B*HW, C] (scaled by `scale`). */
+int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, uint16_t* out_hi,
+                       uint16_t* out_lo, void* stream);
+
+/* ---- fused mask-aware correlation -> softmax -> coordinate expectation -> warp -> source mean ---
+ * model/TSNet.py:322-323 (target mask), :347-366 (per source: mask, two masked bmm, softmax(100 x),
+ * expected coordinate, grid_sample) and :392 (mean over sources).  The HW x HW matrix is never
+ * materialised.  bbox pointers are the FULL-RESOLUTION masks [B, bbox_h, bbox_w] (uint8 or fp32);
+ * nearest down-sampling to (h, w) is done by integer indexing inside the kernel.
+ *   tar_hi/lo        [B*hw, C]   normalised target operands (tsnet_l2norm_split)
+ *   src_hi/lo        ONE buffer [n_src, B*hw, C]: normalised operands of all sources, source-major
+ *   src_fea          n_src pointers (host array) to fp32 NHWC un-normalised source features (sampled)
+ *   coord_table      h + w floats: torch.linspace(-1,1,h) then torch.linspace(-1,1,w) (:301-302)
+ *   out_mean         fp32 NHWC [B, hw, C]  = mean_i grid_sample(src_fea_i, G_i)
+ *   out_grids        NULL or [n_src, B, h, w, 2] (x, y) -- the reference's warp_grid2d_list (:369-370)
+ *   operand_scale    product of the two operand pre-scales (accumulators are divided by it)          */
+typedef struct {
+  int B, n_src, C, h, w;
+  int bbox_h, bbox_w, bbox_dtype; /* 0 = uint8, 1 = fp32 */
+  float temperature;              /* 100 (model/TSNet.py:359) */
+  int split, fmt;
+  float operand_scale;
+} tsnet_corr_desc;
+
+int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
+                        const uint16_t* src_hi, const uint16_t* src_lo,
+                        const float* const* src_fea, const void* tar_bbox, const void* const* src_bbox,
+                        const float* coord_table, float* out_mean, float* out_grids, void* workspace,
+                        size_t workspace_bytes, void* stream);
+size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc* d);
+
+/* ---- output head ---------------------------------------------------------------------------------
+ * ReflectionPad2d(3) + Conv2d(64 -> 3, 7x7) + Tanh (model/TSNet.py:151-152) on the fp32 NHWC
+ * activation, written as NCHW [B, 3, H, W]; optional pose compositing
+ * out = out * fore + fill_c * (1 - fore), fore = columns [fore_x0, fore_x1) (model/TSNet_pose.py:276-280,
+ * :416-417; fill = -mean/255).  Pass fore_x1 <= fore_x0 to disable.  SIMT fp32 (Cout = 3 is not a
+ * tensor-core shape). */
+int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
+                         const float* bias, int fore_x0, int fore_x1, const float* fill3, float* out_nchw,
+                         void* stream);
+
+/* ---- reference-style direct convolution (validation kernel, fp32 SIMT) ----------------------------
+ * Plain NHWC direct convolution with zero or reflect padding; used by the tests to cross-check the
+ * tensor-core path on device and by nothing on the hot path. */
+int tsnet_direct_conv_fp32(const float* x_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
+                           const float* bias, int Cout, int K, int stride, int pad, int reflect, float* y_nhwc,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSNET_B200_H_ */

@@ -1,0 +1,323 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   y_raw[b, y, x, co] = bias[co] + out_scale * sum_{tap, c} taps[b*planes + plane(tap), y + dy(tap), x + dx(tap), c]
+//                                                            * w[co, tap*Cp + c]
+//
+// A operand  = 128 output pixels x 64 channels of one tap, fetched by ONE 4-D TMA box from the padded
+//              NHWC "tap source" (padding / upsampling / parity split were applied by its producer);
+// B operand  = BLOCK_N x 64 slice of the K-major packed weight, 2-D TMA box;
+// both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
+// fp32-faithful mode: operands are stored as 16-bit (hi, lo) pairs and every K step issues
+//   D += Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi      (fp32 accumulation in TMEM).
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> bias -> global store + InstanceNorm partial statistics).
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "sm100_prims.cuh"
+#include "host_util.h"
+#include "../../include/tsnet_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace tsnet {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;          // 64 x 16-bit = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct alignas(64) ConvGemmArgs {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  const float* bias;
+  float* y;
+  float* stats;
+  float out_scale;
+  int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
+  int Cout, num_taps, kc_per_tap, planes, split, fmt;
+  int8_t tap_dy[TSNET_MAX_TAPS + 7], tap_dx[TSNET_MAX_TAPS + 7], tap_plane[TSNET_MAX_TAPS + 7];
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 6 ? 6 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Lane j of the warp ends with sum over the 32 lanes of v[j] (transpose-reduce butterfly, 31 shuffles).
+__device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? v[i] : v[i + o];
+      const float keep = upper ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs args) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int num_kb = args.num_taps * args.kc_per_tap;
+  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&args.a_hi);
+    tma_prefetch_desc(&args.b_hi);
+    if (args.split) {
+      tma_prefetch_desc(&args.a_lo);
+      tma_prefetch_desc(&args.b_lo);
+    }
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane_id() == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = args.split ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / args.num_n_tiles;
+        const int n_tile = tile - m_tile * args.num_n_tiles;
+        const int img = m_tile / args.tiles_per_img;
+        const int t = m_tile - img * args.tiles_per_img;
+        const int ty = t / args.wtiles_per_row;
+        const int tx = t - ty * args.wtiles_per_row;
+        const int y0 = ty * args.rows_per_tile;
+        const int x0 = tx * args.Wt;
+        for (int tap = 0; tap < args.num_taps; ++tap) {
+          const int cy = y0 + args.tap_dy[tap];
+          const int cx = x0 + args.tap_dx[tap];
+          const int cn = img * args.planes + args.tap_plane[tap];
+          for (int kc = 0; kc < args.kc_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            const int kb = tap * args.kc_per_tap + kc;
+            tma_load_4d(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+            tma_load_2d(st + 2 * Cfg::kABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+            if (args.split) {
+              tma_load_4d(st + Cfg::kABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+              tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &args.b_lo, &full_bar[stage], kb * kBlockK,
+                          n_tile * BLOCK_N);
+            }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane_id() == 0) {
+      const uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, args.fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = make_desc_kmajor_sw128(st);
+          const uint64_t a_lo = make_desc_kmajor_sw128(st + Cfg::kABytes);
+          const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes);
+          const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint32_t off = k * kUmmaK * 2;
+            umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, (kb | k) != 0);
+            if (args.split) {
+              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+              umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane_id();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / args.num_n_tiles;
+      const int n_tile = tile - m_tile * args.num_n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
+      float* yrow = args.y + gm * args.Cout;
+      float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int n0 = n_tile * BLOCK_N + c0;
+        if (n0 >= args.Cout) break;  // padded output channels (warp-uniform)
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (srow) {
+          // per-column (sum, centred M2) over this warp's 32 pixels
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = v[j];
+          const float colsum = warp_col_sums(t);  // lane j: sum of column j
+          const float mean_l = colsum * (1.f / 32.f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float mj = __shfl_sync(0xffffffffu, mean_l, j);
+            const float dlt = v[j] - mj;
+            t[j] = dlt * dlt;
+          }
+          const float m2 = warp_col_sums(t);
+          *reinterpret_cast<float2*>(srow + (n0 + lane_id()) * 2) = make_float2(colsum, m2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_gemm_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tsnet
+
+using namespace tsnet;
+
+extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,
+                                   const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
+                                   float* stats_partial, void* stream) {
+  TSNET_ARG_CHECK(d && taps_hi && w_hi && y_raw, "conv_gemm: null argument");
+  TSNET_ARG_CHECK(!d->split || (taps_lo && w_lo), "conv_gemm: split mode needs the lo operands");
+  TSNET_ARG_CHECK(d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "conv_gemm: block_n %d", d->block_n);
+  TSNET_ARG_CHECK(d->Cp > 0 && d->Cp % 64 == 0, "conv_gemm: Cp %d must be a multiple of 64", d->Cp);
+  TSNET_ARG_CHECK(d->Cout > 0 && d->Cout % 32 == 0, "conv_gemm: Cout %d must be a multiple of 32", d->Cout);
+  TSNET_ARG_CHECK(d->Cout_pad % d->block_n == 0 && d->Cout_pad >= d->Cout, "conv_gemm: Cout_pad %d", d->Cout_pad);
+  TSNET_ARG_CHECK(d->num_taps >= 1 && d->num_taps <= TSNET_MAX_TAPS, "conv_gemm: num_taps %d", d->num_taps);
+  TSNET_ARG_CHECK((d->H * d->W) % kBlockM == 0, "conv_gemm: H*W = %d must be a multiple of 128", d->H * d->W);
+  const int Wt = d->W < kBlockM ? d->W : kBlockM;
+  TSNET_ARG_CHECK(kBlockM % Wt == 0 && d->W % Wt == 0, "conv_gemm: unsupported width %d", d->W);
+  const int rows = kBlockM / Wt;
+  TSNET_ARG_CHECK(d->H % rows == 0, "conv_gemm: H %d not a multiple of tile rows %d", d->H, rows);
+  for (int t = 0; t < d->num_taps; ++t) {
+    TSNET_ARG_CHECK(d->tap_plane[t] >= 0 && d->tap_plane[t] < d->planes, "conv_gemm: tap %d plane", t);
+    TSNET_ARG_CHECK(d->tap_dy[t] >= 0 && d->tap_dy[t] + d->H <= d->Hp, "conv_gemm: tap %d dy out of range", t);
+    TSNET_ARG_CHECK(d->tap_dx[t] >= 0 && d->tap_dx[t] + d->W <= d->Wp, "conv_gemm: tap %d dx out of range", t);
+  }
+
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Cp, (uint64_t)d->Wp, (uint64_t)d->Hp, (uint64_t)d->B * d->planes};
+    const uint64_t str[3] = {(uint64_t)d->Cp * 2, (uint64_t)d->Wp * d->Cp * 2, (uint64_t)d->Hp * d->Wp * d->Cp * 2};
+    const uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)rows, 1};
+    int r = encode_tmap_u16_sw128(&a.a_hi, taps_hi, 4, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, taps_lo, 4, dims, str, box))) return r;
+  }
+  {
+    const uint64_t K = (uint64_t)d->num_taps * d->Cp;
+    const uint64_t dims[2] = {K, (uint64_t)d->Cout_pad};
+    const uint64_t str[1] = {K * 2};
+    const uint32_t box[2] = {64, (uint32_t)d->block_n};
+    int r = encode_tmap_u16_sw128(&a.b_hi, w_hi, 2, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.b_lo, w_lo, 2, dims, str, box))) return r;
+  }
+  a.bias = bias;
+  a.y = y_raw;
+  a.stats = stats_partial;
+  a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  a.tiles_per_img = d->H * d->W / kBlockM;
+  a.num_m_tiles = d->B * a.tiles_per_img;
+  a.num_n_tiles = d->Cout_pad / d->block_n;
+  a.Wt = Wt;
+  a.rows_per_tile = rows;
+  a.wtiles_per_row = d->W / Wt;
+  a.Cout = d->Cout;
+  a.num_taps = d->num_taps;
+  a.kc_per_tap = d->Cp / 64;
+  a.planes = d->planes;
+  a.split = d->split;
+  a.fmt = d->fmt;
+  for (int t = 0; t < d->num_taps; ++t) {
+    a.tap_dy[t] = d->tap_dy[t];
+    a.tap_dx[t] = d->tap_dx[t];
+    a.tap_plane[t] = d->tap_plane[t];
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (d->block_n) {
+    case 64: return launch_conv_gemm<64>(a, s);
+    case 128: return launch_conv_gemm<128>(a, s);
+    default: return launch_conv_gemm<256>(a, s);
+  }
+}

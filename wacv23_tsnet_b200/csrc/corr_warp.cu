@@ -1,0 +1,366 @@
+// Fused mask-aware correlation -> softmax(100 x) -> expected source coordinate -> bilinear warp -> mean over sources.
+// (model/TSNet.py:319-366, :392 of the reference.)  The hw x hw similarity matrix lives only in TMEM.
+//
+// Work item = (sample b, tile of 128 target positions).  For every source i and every chunk of 256 source
+// positions the tensor cores compute S = T_hat[128 x C] . S_hat_i[256 x C]^T into one of two TMEM accumulators
+// (3-term hi/lo split, fp32 accumulate) while the four epilogue warps run an online softmax with a 2-channel
+// "V" (the source coordinates) over the previous chunk: one thread owns one target row.
+// After the last source the epilogue warps gather the 4 bilinear taps per (row, source) from the
+// UN-normalised fp32 source features and write the source mean.
+//
+// warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = softmax + gather.
+#include "sm100_prims.cuh"
+#include "host_util.h"
+#include "../../include/tsnet_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace tsnet {
+
+constexpr int kCorrM = 128;      // target rows per work item
+constexpr int kCorrN = 256;      // source columns per accumulator
+constexpr int kCorrK = 64;       // K block (one 128 B swizzle row)
+constexpr int kCorrThreads = 256;
+constexpr int kCorrMaxSrc = 16;
+constexpr int kCorrABytes = kCorrM * kCorrK * 2;  // 16 KB
+constexpr int kCorrBBytes = kCorrN * kCorrK * 2;  // 32 KB
+constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 96 KB
+constexpr int kCorrStages = 2;
+constexpr int kCorrMaxHW = 2048;
+
+struct alignas(64) CorrArgs {
+  CUtensorMap t_hi, t_lo, s_hi, s_lo;  // [B*hw, C] and [n_src*B*hw, C], box {64, 128} / {64, 256}
+  const float* src_fea[kCorrMaxSrc];
+  const void* src_bbox[kCorrMaxSrc];
+  const void* tar_bbox;
+  const float* coord_table;  // h values (y) then w values (x)
+  float* out_mean;
+  float* out_grids;
+  int B, n_src, C, h, w, hw, tiles_per_img, num_items;
+  int bbox_h, bbox_w, bbox_dtype;
+  int split, fmt;
+  float temperature, inv_operand_scale;
+};
+
+__device__ __forceinline__ float read_mask(const void* bbox, int dtype, int b, int bh, int bw, int h, int w, int pos) {
+  // F.interpolate(mode='nearest'): src = min(floor(dst * (in / out)), in - 1), float scale (ATen)
+  const int y = pos / w, x = pos - y * w;
+  const int sy = min(static_cast<int>(floorf(y * (static_cast<float>(bh) / h))), bh - 1);
+  const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(bw) / w))), bw - 1);
+  const size_t off = (static_cast<size_t>(b) * bh + sy) * bw + sx;
+  return dtype == 0 ? static_cast<float>(static_cast<const uint8_t*>(bbox)[off])
+                    : static_cast<const float*>(bbox)[off];
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid_constant__ CorrArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + kCorrStages * kCorrStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kCorrStages;
+  uint64_t* tmem_full = empty_bar + kCorrStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_mask = reinterpret_cast<float*>(tail + 128);                 // [hw] source mask of the current source
+  float* s_cx = s_mask + kCorrMaxHW;                                    // [w]
+  float* s_cy = s_cx + 128;                                             // [h]
+  float2* s_grid = reinterpret_cast<float2*>(s_cy + 128);               // [n_src][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int num_kb = args.C / kCorrK;
+  const int chunks = args.hw / kCorrN;
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&args.t_hi);
+    tma_prefetch_desc(&args.s_hi);
+    if (args.split) {
+      tma_prefetch_desc(&args.t_lo);
+      tma_prefetch_desc(&args.s_lo);
+    }
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int s = 0; s < kCorrStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, 2 * kCorrN);
+  for (int i = threadIdx.x; i < args.w; i += blockDim.x) s_cx[i] = args.coord_table[args.h + i];
+  for (int i = threadIdx.x; i < args.h; i += blockDim.x) s_cy[i] = args.coord_table[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane_id() == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = args.split ? kCorrStageBytes : (kCorrABytes + kCorrBBytes);
+      for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
+        const int b = item / args.tiles_per_img;
+        const int mt = item - b * args.tiles_per_img;
+        const int trow = b * args.hw + mt * kCorrM;
+        for (int i = 0; i < args.n_src; ++i) {
+          for (int ch = 0; ch < chunks; ++ch) {
+            const int srow = (i * args.B + b) * args.hw + ch * kCorrN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + stage * kCorrStageBytes;
+              mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              tma_load_2d(st, &args.t_hi, &full_bar[stage], kb * kCorrK, trow);
+              tma_load_2d(st + 2 * kCorrABytes, &args.s_hi, &full_bar[stage], kb * kCorrK, srow);
+              if (args.split) {
+                tma_load_2d(st + kCorrABytes, &args.t_lo, &full_bar[stage], kb * kCorrK, trow);
+                tma_load_2d(st + 2 * kCorrABytes + kCorrBBytes, &args.s_lo, &full_bar[stage], kb * kCorrK, srow);
+              }
+              if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane_id() == 0) {
+      const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;  // accumulator use counter
+      for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
+        for (int ic = 0; ic < args.n_src * chunks; ++ic, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kCorrN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * kCorrStageBytes);
+            const uint64_t a_hi = make_desc_kmajor_sw128(st);
+            const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
+            const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
+            const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
+#pragma unroll
+            for (int k = 0; k < kCorrK / 16; ++k) {
+              const uint32_t off = k * 32;
+              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, (kb | k) != 0);
+              if (args.split) {
+                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + gather =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane_id();
+    const int et = threadIdx.x - 128;  // 0..127 among epilogue threads
+    constexpr float kLog2e = 1.4426950408889634f;
+    int it = 0;
+    for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
+      const int b = item / args.tiles_per_img;
+      const int mt = item - b * args.tiles_per_img;
+      const int tpos = mt * kCorrM + row;  // target position inside the image
+      const float m_t = read_mask(args.tar_bbox, args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, tpos);
+      for (int i = 0; i < args.n_src; ++i) {
+        epi_bar_sync();  // previous source's mask no longer in use
+        for (int p = et; p < args.hw; p += 128)
+          s_mask[p] = read_mask(args.src_bbox[i], args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, p);
+        epi_bar_sync();
+        float run_max = -INFINITY, run_sum = 0.f, gx = 0.f, gy = 0.f;
+        for (int ch = 0; ch < chunks; ++ch, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCorrN; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kCorrN + c0, v);
+            const int s0 = ch * kCorrN + c0;
+            float gmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float m_s = s_mask[s0 + j];
+              // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)); exact for binary masks
+              const float wgt = m_t * m_s + (1.f - m_t) * (1.f - m_s);
+              v[j] = args.temperature * ((v[j] * args.inv_operand_scale) * wgt);
+              gmax = fmaxf(gmax, v[j]);
+            }
+            const float new_max = fmaxf(run_max, gmax);
+            const float corr = exp2f((run_max - new_max) * kLog2e);  // exp2f(-inf) = 0 on the first group
+            run_sum *= corr; gx *= corr; gy *= corr;
+            run_max = new_max;
+            const float mb = new_max * kLog2e;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float p = exp2f(fmaf(v[j], kLog2e, -mb));
+              const int s = s0 + j;
+              const int sy = s / args.w, sx = s - sy * args.w;
+              run_sum += p;
+              gx = fmaf(p, s_cx[sx], gx);
+              gy = fmaf(p, s_cy[sy], gy);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const float2 g = make_float2(gx / run_sum, gy / run_sum);
+        s_grid[i * kCorrM + row] = g;
+        if (args.out_grids)
+          *reinterpret_cast<float2*>(args.out_grids + ((static_cast<size_t>(i) * args.B + b) * args.hw + tpos) * 2) = g;
+      }
+      epi_bar_sync();  // all grids of this item visible
+      // ---- gather: warp q handles rows q*32 .. q*32+31; lane owns channels {128 k + 4 lane .. +3} ----
+      const int nk = args.C / 128;
+      const float n_srcf = static_cast<float>(args.n_src);
+      for (int r = 0; r < 32; ++r) {
+        const int grow = q * 32 + r;
+        const int pos = mt * kCorrM + grow;
+        float4 accv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < args.n_src; ++i) {
+          const float2 g = s_grid[i * kCorrM + grow];
+          // F.grid_sample(bilinear, zeros, align_corners=False): ix = ((x + 1) * W - 1) / 2
+          const float ix = ((g.x + 1.f) * args.w - 1.f) * 0.5f;
+          const float iy = ((g.y + 1.f) * args.h - 1.f) * 0.5f;
+          const float fx = floorf(ix), fy = floorf(iy);
+          const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+          const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+          const float wts[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
+          const float* base = args.src_fea[i] + static_cast<size_t>(b) * args.hw * args.C;
+          float4 res[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap) {
+            const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+            if (xx >= 0 && xx < args.w && yy >= 0 && yy < args.h) {
+              const float* p = base + static_cast<size_t>(yy * args.w + xx) * args.C + lane_id() * 4;
+              const float wt = wts[tap];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < nk) {
+                  const float4 f = __ldg(reinterpret_cast<const float4*>(p + k * 128));
+                  res[k].x = fmaf(f.x, wt, res[k].x); res[k].y = fmaf(f.y, wt, res[k].y);
+                  res[k].z = fmaf(f.z, wt, res[k].z); res[k].w = fmaf(f.w, wt, res[k].w);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            accv[k].x += res[k].x; accv[k].y += res[k].y; accv[k].z += res[k].z; accv[k].w += res[k].w;
+          }
+        }
+        float* o = args.out_mean + (static_cast<size_t>(b) * args.hw + pos) * args.C + lane_id() * 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < nk)
+            *reinterpret_cast<float4*>(o + k * 128) =
+                make_float4(accv[k].x / n_srcf, accv[k].y / n_srcf, accv[k].z / n_srcf, accv[k].w / n_srcf);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kCorrN);
+  }
+}
+
+constexpr int kCorrSmemBytes =
+    kCorrStages * kCorrStageBytes + 1024 + 128 + (kCorrMaxHW + 256) * 4 + kCorrMaxSrc * kCorrM * 8;
+
+}  // namespace tsnet
+
+using namespace tsnet;
+
+extern "C" size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc*) { return 0; }
+
+extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
+                                   const uint16_t* src_hi, const uint16_t* src_lo, const float* const* src_fea,
+                                   const void* tar_bbox, const void* const* src_bbox, const float* coord_table,
+                                   float* out_mean, float* out_grids, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  TSNET_ARG_CHECK(d && tar_hi && src_hi && src_fea && tar_bbox && src_bbox && coord_table && out_mean,
+                  "corr_warp: null argument");
+  TSNET_ARG_CHECK(!d->split || (tar_lo && src_lo), "corr_warp: split mode needs the lo operands");
+  TSNET_ARG_CHECK(d->n_src >= 1 && d->n_src <= kCorrMaxSrc, "corr_warp: n_src %d (max %d)", d->n_src, kCorrMaxSrc);
+  const int hw = d->h * d->w;
+  TSNET_ARG_CHECK(hw % kCorrN == 0 && hw <= kCorrMaxHW, "corr_warp: h*w = %d must be a multiple of 256, <= %d", hw,
+                  kCorrMaxHW);
+  TSNET_ARG_CHECK(d->h <= 128 && d->w <= 128, "corr_warp: h, w <= 128");
+  TSNET_ARG_CHECK(d->C % 128 == 0 && d->C <= 1024, "corr_warp: C %d must be a multiple of 128, <= 1024", d->C);
+  TSNET_ARG_CHECK(d->bbox_dtype == 0 || d->bbox_dtype == 1, "corr_warp: bbox_dtype %d", d->bbox_dtype);
+
+  CorrArgs a;
+  memset(&a, 0, sizeof(a));
+  {
+    const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->B * hw};
+    const uint64_t str[1] = {(uint64_t)d->C * 2};
+    const uint32_t box[2] = {64, kCorrM};
+    int r = encode_tmap_u16_sw128(&a.t_hi, tar_hi, 2, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.t_lo, tar_lo, 2, dims, str, box))) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->n_src * d->B * hw};
+    const uint64_t str[1] = {(uint64_t)d->C * 2};
+    const uint32_t box[2] = {64, kCorrN};
+    int r = encode_tmap_u16_sw128(&a.s_hi, src_hi, 2, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.s_lo, src_lo, 2, dims, str, box))) return r;
+  }
+  for (int i = 0; i < d->n_src; ++i) {
+    TSNET_ARG_CHECK(src_fea[i] && src_bbox[i], "corr_warp: null source %d", i);
+    a.src_fea[i] = src_fea[i];
+    a.src_bbox[i] = src_bbox[i];
+  }
+  a.tar_bbox = tar_bbox;
+  a.coord_table = coord_table;
+  a.out_mean = out_mean;
+  a.out_grids = out_grids;
+  a.B = d->B; a.n_src = d->n_src; a.C = d->C; a.h = d->h; a.w = d->w; a.hw = hw;
+  a.tiles_per_img = hw / kCorrM;
+  a.num_items = d->B * a.tiles_per_img;
+  a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
+  a.split = d->split; a.fmt = d->fmt;
+  a.temperature = d->temperature;
+  a.inv_operand_scale = 1.f / (d->operand_scale == 0.f ? 1.f : d->operand_scale);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(corr_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kCorrSmemBytes));
+    attr_set = true;
+  }
+  const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
+  corr_warp_kernel<<<grid, kCorrThreads, kCorrSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,537 @@
+// HBM-bound helper kernels of the TS-Net forward: weight packing, InstanceNorm statistics reduction,
+// tap-source construction (normalise + ReLU + residual + pad / upsample / parity split + hi/lo split),
+// encoder stem input construction, L2 normalisation for the correlation, output head, and a plain
+// fp32 direct convolution used for on-device validation.
+#include "sm100_prims.cuh"
+#include "host_util.h"
+#include "../../include/tsnet_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace tsnet {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * n - 2 - i : i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int fold_kw,
+                                   int Cp, int Cout_pad, float scale, int fmt, uint16_t* __restrict__ hi,
+                                   uint16_t* __restrict__ lo) {
+  const int taps = fold_kw ? KH : KH * KW;
+  const size_t K = static_cast<size_t>(taps) * Cp;
+  const size_t total = static_cast<size_t>(Cout_pad) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i / K);
+    const int kcol = static_cast<int>(i - static_cast<size_t>(o) * K);
+    const int tap = kcol / Cp;
+    const int j = kcol - tap * Cp;
+    int r, s, c;
+    bool valid;
+    if (fold_kw) {
+      r = tap; s = j / Cin; c = j - s * Cin; valid = s < KW;
+    } else {
+      r = tap / KW; s = tap - r * KW; c = j; valid = c < Cin;
+    }
+    float v = 0.f;
+    if (valid && o < Cout) v = w[((static_cast<size_t>(o) * Cin + c) * KH + r) * KW + s] * scale;
+    uint16_t h, l;
+    split16(v, fmt, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm statistics: [B*nsub, C, 2] (sum, M2 of 32 pixels) -> [B, C, 2] (mean, rstd)
+// block = (32 channels) x (8 segments); fixed merge order => bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+__global__ void instnorm_reduce_kernel(const float* __restrict__ part, int nsub, int C, float eps,
+                                       float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int seg = threadIdx.y;
+  __shared__ double s_n[8][32], s_mean[8][32], s_m2[8][32];
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  if (c < C) {
+    const int per = (nsub + 7) / 8;
+    const int k0 = seg * per, k1 = min(nsub, k0 + per);
+    const float* p = part + (static_cast<size_t>(b) * nsub) * C * 2 + static_cast<size_t>(c) * 2;
+    for (int k = k0; k < k1; ++k) {
+      const float2 sm = *reinterpret_cast<const float2*>(p + static_cast<size_t>(k) * C * 2);
+      const double nb = 32.0, mb = static_cast<double>(sm.x) / 32.0, m2b = sm.y;
+      const double nn = n + nb, delta = mb - mean;
+      mean += delta * nb / nn;
+      m2 += m2b + delta * delta * n * nb / nn;
+      n = nn;
+    }
+  }
+  s_n[seg][threadIdx.x] = n;
+  s_mean[seg][threadIdx.x] = mean;
+  s_m2[seg][threadIdx.x] = m2;
+  __syncthreads();
+  if (seg == 0 && c < C) {
+    for (int s = 1; s < 8; ++s) {
+      const double nb = s_n[s][threadIdx.x];
+      if (nb == 0.0) continue;
+      const double mb = s_mean[s][threadIdx.x], m2b = s_m2[s][threadIdx.x];
+      const double nn = n + nb, delta = mb - mean;
+      mean += delta * nb / nn;
+      m2 += m2b + delta * delta * n * nb / nn;
+      n = nn;
+    }
+    const double var = m2 / n;  // biased, as nn.InstanceNorm2d
+    float2 r;
+    r.x = static_cast<float>(mean);
+    r.y = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    *reinterpret_cast<float2*>(out + (static_cast<size_t>(b) * C + c) * 2) = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tap-source builder.  One thread = one destination pixel x 8 channels.
+// ------------------------------------------------------------------------------------------------
+struct TapsArgs {
+  const float* raw;
+  const float* mean_rstd;
+  const float* residual;
+  float* act_out;
+  uint16_t* hi;
+  uint16_t* lo;
+  int B, H, W, C, mode, relu, Cp_total, c_off, fmt;
+  float scale;
+  int Hd, Wd, planes;  // destination geometry
+};
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__device__ __forceinline__ void fetch_act8(const TapsArgs& a, int b, int y, int x, int c, const float (&mean)[8],
+                                           const float (&rstd)[8], float (&v)[8]) {
+  const size_t off = ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.C + c;
+  load8(a.raw + off, v);
+  if (a.mean_rstd) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean[j]) * rstd[j];
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.residual) {
+    float r[8];
+    load8(a.residual + off, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += r[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
+  const int cg = a.C / 8;
+  const size_t total = static_cast<size_t>(a.B) * a.planes * a.Hd * a.Wd * cg;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cg) * 8;
+    size_t pix = i / cg;
+    const int xd = static_cast<int>(pix % a.Wd);
+    pix /= a.Wd;
+    const int yd = static_cast<int>(pix % a.Hd);
+    pix /= a.Hd;
+    const int plane = static_cast<int>(pix % a.planes);
+    const int b = static_cast<int>(pix / a.planes);
+
+    float mean[8], rstd[8];
+    if (a.mean_rstd) {
+      const float* mr = a.mean_rstd + (static_cast<size_t>(b) * a.C + c) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float4 t = *reinterpret_cast<const float4*>(mr + j * 2);
+        mean[j] = t.x; rstd[j] = t.y; mean[j + 1] = t.z; rstd[j + 1] = t.w;
+      }
+    }
+    float v[8];
+    bool interior = false;  // destination pixel that owns the (unique) act_out write of its source pixel
+    if (a.mode == TSNET_TAPS_SAME) {
+      fetch_act8(a, b, yd, xd, c, mean, rstd, v);
+      interior = true;
+    } else if (a.mode == TSNET_TAPS_REFLECT1) {
+      const int y = reflect_idx(yd - 1, a.H), x = reflect_idx(xd - 1, a.W);
+      fetch_act8(a, b, y, x, c, mean, rstd, v);
+      interior = (yd >= 1 && yd <= a.H && xd >= 1 && xd <= a.W);
+    } else if (a.mode == TSNET_TAPS_S2ZERO) {
+      const int y = 2 * yd + (plane >> 1) - 1, x = 2 * xd + (plane & 1) - 1;
+      if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+        fetch_act8(a, b, y, x, c, mean, rstd, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+    } else {  // TSNET_TAPS_UP2REFLECT1
+      const int uy = reflect_idx(yd - 1, 2 * a.H), ux = reflect_idx(xd - 1, 2 * a.W);
+      // ATen area_pixel_compute_source_index(scale = 0.5, align_corners = false): max(0.5*(d+0.5)-0.5, 0)
+      const float sy = fmaxf(0.5f * (uy + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (ux + 0.5f) - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+      const int y1 = min(y0 + 1, a.H - 1), x1 = min(x0 + 1, a.W - 1);
+      const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      float v00[8], v01[8], v10[8], v11[8];
+      fetch_act8(a, b, y0, x0, c, mean, rstd, v00);
+      fetch_act8(a, b, y0, x1, c, mean, rstd, v01);
+      fetch_act8(a, b, y1, x0, c, mean, rstd, v10);
+      fetch_act8(a, b, y1, x1, c, mean, rstd, v11);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t0 = __fadd_rn(__fmul_rn(hx, v00[j]), __fmul_rn(lx, v01[j]));
+        const float t1 = __fadd_rn(__fmul_rn(hx, v10[j]), __fmul_rn(lx, v11[j]));
+        v[j] = __fadd_rn(__fmul_rn(hy, t0), __fmul_rn(ly, t1));
+      }
+    }
+    if (a.act_out && interior) {
+      const int y = a.mode == TSNET_TAPS_SAME ? yd : yd - 1, x = a.mode == TSNET_TAPS_SAME ? xd : xd - 1;
+      float* o = a.act_out + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.C + c;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (a.hi) {
+      uint16_t h[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split16(v[j] * a.scale, a.fmt, h[j], l[j]);
+      const size_t d = (((static_cast<size_t>(b) * a.planes + plane) * a.Hd + yd) * a.Wd + xd) * a.Cp_total +
+                       a.c_off + c;
+      uint4 ph, pl;
+      ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+      ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+      pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+      pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+      *reinterpret_cast<uint4*>(a.hi + d) = ph;
+      *reinterpret_cast<uint4*>(a.lo + d) = pl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem tap source: [B, H+6, W, Cp], kw folded into channels.  One thread = one destination pixel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_scale,
+                                                        const float* __restrict__ lbl, int Clbl, int B, int H, int W,
+                                                        int Cp, int fmt, float scale, uint16_t* __restrict__ hi,
+                                                        uint16_t* __restrict__ lo) {
+  const int Cin = Cimg + Clbl + 3;
+  const int Hd = H + 6;
+  const size_t total = static_cast<size_t>(B) * Hd * W;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  const int yd = static_cast<int>((i / W) % Hd);
+  const int b = static_cast<int>(i / (static_cast<size_t>(W) * Hd));
+  const int ys = reflect_idx(yd - 3, H);
+  // Encoder.coord_conv (model/TSNet.py:117-122): t = idx / (n-1); 2*t - 1; r = sqrt(x^2 + y^2), separate roundings
+  const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
+  uint16_t* dh = hi + i * Cp;
+  uint16_t* dl = lo + i * Cp;
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (int j0 = 0; j0 < Cp; j0 += 8) {
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = j0 + jj;
+      const int s = j / Cin;
+      const int c = j - s * Cin;
+      float v = 0.f;
+      if (s < 7) {
+        const int xs = reflect_idx(x + s - 3, W);
+        if (c < Cimg) {
+          v = img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs] * img_scale;
+        } else if (c < Cimg + Clbl) {
+          v = lbl[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane + static_cast<size_t>(ys) * W + xs];
+        } else {
+          const float xx =
+              __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
+          const int k = c - Cimg - Clbl;
+          v = k == 0 ? xx : (k == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
+        }
+      }
+      split16(v * scale, fmt, h[jj], l[jj]);
+    }
+    uint4 ph, pl;
+    ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+    ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+    pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+    pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+    *reinterpret_cast<uint4*>(dh + j0) = ph;
+    *reinterpret_cast<uint4*>(dl + j0) = pl;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// F.normalize(dim = channel) + hi/lo split. One warp = one pixel; C % 128 == 0, C <= 1024.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restrict__ fea, size_t npix, int C, int fmt,
+                                                           float scale, uint16_t* __restrict__ hi,
+                                                           uint16_t* __restrict__ lo) {
+  const size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x / 32) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = fea + pix * C;
+  float4 v[8];
+  float ss = 0.f;
+  const int nk = C / 128;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < nk) {
+      v[k] = *reinterpret_cast<const float4*>(p + k * 128 + lane * 4);
+      ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(__fsqrt_rn(ss), 1e-12f);  // F.normalize eps
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < nk) {
+      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split16(__fdiv_rn(e[j], denom) * scale, fmt, h[j], l[j]);
+      const size_t d = pix * C + k * 128 + lane * 4;
+      *reinterpret_cast<uint2*>(hi + d) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+      *reinterpret_cast<uint2*>(lo + d) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// output head: reflect-pad 3, 7x7 conv Cin -> 3, tanh, optional pose compositing, NCHW store.
+// block = 32 x 8 output pixels; channels processed in chunks of 16 through shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadTW = 32, kHeadTH = 8, kHeadCC = 8, kHeadPS = 12;  // pixel stride 12 floats: conflict-free LDS.128
+
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ act, int B, int H, int W, int Cin,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int fore_x0, int fore_x1, float fill0, float fill1,
+                                                        float fill2, float* __restrict__ out) {
+  __shared__ __align__(16) float s_in[(kHeadTH + 6) * (kHeadTW + 6) * kHeadPS];
+  __shared__ __align__(16) float s_w[49 * kHeadCC * 4];  // [tap][c][4] (3 outputs + pad)
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
+  const int tx = threadIdx.x % kHeadTW, ty = threadIdx.x / kHeadTW;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  for (int cc = 0; cc < Cin; cc += kHeadCC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kHeadTH + 6) * (kHeadTW + 6) * (kHeadCC / 4); i += blockDim.x) {
+      const int c4 = i % (kHeadCC / 4);
+      const int p = i / (kHeadCC / 4);
+      const int px = p % (kHeadTW + 6), py = p / (kHeadTW + 6);
+      const int ys = reflect_idx(y0 + py - 3, H), xs = reflect_idx(x0 + px - 3, W);
+      const float4 v =
+          *reinterpret_cast<const float4*>(act + ((static_cast<size_t>(b) * H + ys) * W + xs) * Cin + cc + c4 * 4);
+      *reinterpret_cast<float4*>(&s_in[p * kHeadPS + c4 * 4]) = v;
+    }
+    for (int i = threadIdx.x; i < 49 * kHeadCC; i += blockDim.x) {
+      const int c = i % kHeadCC, tap = i / kHeadCC;
+      float4 wv;
+      wv.x = w[(static_cast<size_t>(0) * Cin + cc + c) * 49 + tap];
+      wv.y = w[(static_cast<size_t>(1) * Cin + cc + c) * 49 + tap];
+      wv.z = w[(static_cast<size_t>(2) * Cin + cc + c) * 49 + tap];
+      wv.w = 0.f;
+      *reinterpret_cast<float4*>(&s_w[i * 4]) = wv;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float* ip = &s_in[((ty + r) * (kHeadTW + 6) + tx + s) * kHeadPS];
+        const float* wp = &s_w[(r * 7 + s) * kHeadCC * 4];
+#pragma unroll
+        for (int c4 = 0; c4 < kHeadCC / 4; ++c4) {
+          const float4 v = *reinterpret_cast<const float4*>(ip + c4 * 4);
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + (c4 * 4 + j) * 4);
+            acc0 = fmaf(e[j], wv.x, acc0);
+            acc1 = fmaf(e[j], wv.y, acc1);
+            acc2 = fmaf(e[j], wv.z, acc2);
+          }
+        }
+      }
+    }
+  }
+  const int x = x0 + tx, y = y0 + ty;
+  if (x < W && y < H) {
+    float o[3] = {tanhf(acc0 + bias[0]), tanhf(acc1 + bias[1]), tanhf(acc2 + bias[2])};
+    if (fore_x1 > fore_x0) {
+      const float fore = (x >= fore_x0 && x < fore_x1) ? 1.f : 0.f;
+      const float fill[3] = {fill0, fill1, fill2};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[k] = __fadd_rn(__fmul_rn(o[k], fore), __fmul_rn(fill[k], 1.f - fore));
+    }
+    const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[(static_cast<size_t>(b) * 3 + k) * plane + static_cast<size_t>(y) * W + x] = o[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation-only direct convolution, fp32 FMA, NHWC. One thread = one output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void direct_conv_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
+                                   const float* __restrict__ w, const float* __restrict__ bias, int Cout, int K,
+                                   int stride, int pad, int reflect, int Ho, int Wo, float* __restrict__ y) {
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * Cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);
+    size_t p = i / Cout;
+    const int xo = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int yo = static_cast<int>(p % Ho);
+    const int b = static_cast<int>(p / Ho);
+    float acc = 0.f;
+    for (int r = 0; r < K; ++r) {
+      int yi = yo * stride + r - pad;
+      if (reflect) yi = reflect_idx(yi, H);
+      if (yi < 0 || yi >= H) continue;
+      for (int s = 0; s < K; ++s) {
+        int xi = xo * stride + s - pad;
+        if (reflect) xi = reflect_idx(xi, W);
+        if (xi < 0 || xi >= W) continue;
+        const float* xp = x + ((static_cast<size_t>(b) * H + yi) * W + xi) * Cin;
+        const float* wp = w + static_cast<size_t>(co) * Cin * K * K + r * K + s;
+        for (int c = 0; c < Cin; ++c) acc = fmaf(xp[c], wp[static_cast<size_t>(c) * K * K], acc);
+      }
+    }
+    y[i] = acc + (bias ? bias[co] : 0.f);
+  }
+}
+
+static inline int grid_for(size_t total, int block, int max_blocks = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  return static_cast<int>(g < static_cast<size_t>(max_blocks) ? (g ? g : 1) : max_blocks);
+}
+
+}  // namespace tsnet
+
+using namespace tsnet;
+
+extern "C" int tsnet_abi_version(void) { return TSNET_ABI_VERSION; }
+extern "C" const char* tsnet_last_error(void) { return last_error_buf(); }
+extern "C" int tsnet_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int tsnet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, int fold_kw, int Cp,
+                                      int Cout_pad, float scale, int fmt, uint16_t* w_hi, uint16_t* w_lo,
+                                      void* stream) {
+  TSNET_ARG_CHECK(w_oihw && w_hi && w_lo, "pack_conv_weight: null argument");
+  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= (fold_kw ? KW * Cin : Cin), "pack_conv_weight: Cp %d too small", Cp);
+  TSNET_ARG_CHECK(Cout_pad >= Cout, "pack_conv_weight: Cout_pad");
+  const size_t total = static_cast<size_t>(Cout_pad) * (fold_kw ? KH : KH * KW) * Cp;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_oihw, Cout, Cin, KH, KW, fold_kw, Cp, Cout_pad, scale, fmt, w_hi, w_lo);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_instnorm_reduce(const float* stats_partial, int B, int HW, int C, float eps, float* mean_rstd,
+                                     void* stream) {
+  TSNET_ARG_CHECK(stats_partial && mean_rstd, "instnorm_reduce: null argument");
+  TSNET_ARG_CHECK(HW % 32 == 0, "instnorm_reduce: HW %d", HW);
+  dim3 grid((C + 31) / 32, B), block(32, 8);
+  instnorm_reduce_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(stats_partial, HW / 32, C, eps,
+                                                                                mean_rstd);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* mean_rstd,
+                                const float* residual, float* act_out, uint16_t* taps_hi, uint16_t* taps_lo,
+                                void* stream) {
+  TSNET_ARG_CHECK(d && raw, "build_taps: null argument");
+  TSNET_ARG_CHECK(d->C % 8 == 0, "build_taps: C %d must be a multiple of 8", d->C);
+  TSNET_ARG_CHECK((taps_hi == nullptr) == (taps_lo == nullptr), "build_taps: hi/lo must both be given or both NULL");
+  TSNET_ARG_CHECK(!taps_hi || (d->Cp_total % 8 == 0 && d->c_off % 8 == 0 && d->c_off + d->C <= d->Cp_total),
+                  "build_taps: channel window [%d, %d) does not fit Cp_total %d", d->c_off, d->c_off + d->C,
+                  d->Cp_total);
+  TSNET_ARG_CHECK(!(act_out && (d->mode == TSNET_TAPS_S2ZERO || d->mode == TSNET_TAPS_UP2REFLECT1)),
+                  "build_taps: act_out is not available in mode %d", d->mode);
+  TapsArgs a;
+  a.raw = raw; a.mean_rstd = mean_rstd; a.residual = residual; a.act_out = act_out; a.hi = taps_hi; a.lo = taps_lo;
+  a.B = d->B; a.H = d->H; a.W = d->W; a.C = d->C; a.mode = d->mode; a.relu = d->relu; a.Cp_total = d->Cp_total;
+  a.c_off = d->c_off; a.fmt = d->fmt; a.scale = d->scale == 0.f ? 1.f : d->scale;
+  a.planes = 1;
+  switch (d->mode) {
+    case TSNET_TAPS_SAME: a.Hd = d->H; a.Wd = d->W; break;
+    case TSNET_TAPS_REFLECT1: a.Hd = d->H + 2; a.Wd = d->W + 2; break;
+    case TSNET_TAPS_S2ZERO:
+      TSNET_ARG_CHECK(d->H % 2 == 0 && d->W % 2 == 0, "build_taps: stride-2 needs even H, W");
+      a.Hd = d->H / 2 + 1; a.Wd = d->W / 2 + 1; a.planes = 4; break;
+    case TSNET_TAPS_UP2REFLECT1: a.Hd = 2 * d->H + 2; a.Wd = 2 * d->W + 2; break;
+    default: return set_error(-1, "build_taps: unknown mode %d", d->mode);
+  }
+  const size_t total = static_cast<size_t>(a.B) * a.planes * a.Hd * a.Wd * (a.C / 8);
+  build_taps_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_scale, const float* lbl_nchw, int Clbl,
+                               int B, int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi,
+                               uint16_t* taps_lo, void* stream) {
+  TSNET_ARG_CHECK(lbl_nchw && taps_hi && taps_lo, "stem_taps: null argument");
+  TSNET_ARG_CHECK((img_nchw != nullptr) == (Cimg > 0), "stem_taps: img pointer / Cimg mismatch");
+  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3), "stem_taps: Cp %d too small", Cp);
+  const size_t total = static_cast<size_t>(B) * (H + 6) * W;
+  stem_taps_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      img_nchw, Cimg, img_scale, lbl_nchw, Clbl, B, H, W, Cp, fmt, scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, uint16_t* out_hi,
+                                  uint16_t* out_lo, void* stream) {
+  TSNET_ARG_CHECK(fea && out_hi && out_lo, "l2norm_split: null argument");
+  TSNET_ARG_CHECK(C % 128 == 0 && C <= 1024, "l2norm_split: C %d must be a multiple of 128, <= 1024", C);
+  const size_t npix = static_cast<size_t>(B) * HW;
+  l2norm_split_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fea, npix, C, fmt, scale == 0.f ? 1.f : scale, out_hi, out_lo);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
+                                    const float* bias, int fore_x0, int fore_x1, const float* fill3, float* out_nchw,
+                                    void* stream) {
+  TSNET_ARG_CHECK(act_nhwc && w_oihw && bias && out_nchw, "head_conv: null argument");
+  TSNET_ARG_CHECK(Cin % kHeadCC == 0, "head_conv: Cin %d must be a multiple of %d", Cin, kHeadCC);
+  TSNET_ARG_CHECK(H >= 4 && W >= 4, "head_conv: image too small for reflect pad 3");
+  TSNET_ARG_CHECK(fore_x1 <= fore_x0 || fill3, "head_conv: compositing needs fill3 (host pointer to 3 floats)");
+  dim3 grid((W + kHeadTW - 1) / kHeadTW, (H + kHeadTH - 1) / kHeadTH, B);
+  const float f0 = fill3 ? fill3[0] : 0.f, f1 = fill3 ? fill3[1] : 0.f, f2 = fill3 ? fill3[2] : 0.f;
+  head_conv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, B, H, W, Cin, w_oihw, bias, fore_x0,
+                                                                          fore_x1, f0, f1, f2, out_nchw);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_direct_conv_fp32(const float* x_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
+                                      const float* bias, int Cout, int K, int stride, int pad, int reflect,
+                                      float* y_nhwc, void* stream) {
+  TSNET_ARG_CHECK(x_nhwc && w_oihw && y_nhwc, "direct_conv: null argument");
+  const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * Cout;
+  direct_conv_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nhwc, B, H, W, Cin, w_oihw, bias, Cout, K, stride, pad, reflect, Ho, Wo, y_nhwc);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
