@@ -106,6 +106,10 @@ typedef struct {
   int c_off;        /* first destination channel */
   int fmt;
   float scale;      /* activations are multiplied by `scale` before the split (power of two) */
+  int act_C_total;  /* channels per pixel of act_out (0 = C) */
+  int act_c_off;    /* first act_out channel */
+  int avg_n;        /* > 1 (mode SAME only): v = mean over i < avg_n of f(raw[i*B + b]) -- torch.stack().mean(1)
+                       of model/TSNet.py:400; raw / mean_rstd / residual then hold avg_n*B samples */
 } tsnet_taps_desc;
 
 int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* mean_rstd, const float* residual,
@@ -116,8 +120,9 @@ int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* me
  * torch.cat([img, lbl]) (model/TSNet.py:312), Encoder.coord_conv (:107-125, channels x, y, r generated
  * analytically) and ReflectionPad2d(3) (:66).  Destination [B, H+6, W, Cp]: pixel (yp, x) holds, for
  * s = 0..6, the Cin = Cimg + Clbl + 3 channels of source pixel (reflect(yp-3), reflect(x+s-3)).
- * img may be NULL (label encoder).  img_scale multiplies the image (the /255 of set_*_input, :268-286). */
-int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_scale, const float* lbl_nchw, int Clbl, int B,
+ * img may be NULL (label encoder).  The image is DIVIDED by img_div (the /255.0 of set_*_input, :268-286;
+ * a true division so the rounding matches the reference). */
+int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const float* lbl_nchw, int Clbl, int B,
                     int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
 
 /* ---- correlation operands ------------------------------------------------------------------------

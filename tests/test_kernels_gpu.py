@@ -1,0 +1,259 @@
+"""GPU suite, part 1: every kernel of libtsnet_sm100.so through the C ABI against a plain fp32 torch reference of
+the same op (cuDNN / cuBLAS with TF32 disabled), plus edge cases of the correlation kernel against the oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from wacv23_tsnet_b200 import lib
+    lib.require_device()  # fail loudly if the CUDA extension / device is missing
+    yield
+
+
+def _recon(hi, lo, fmt):
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    return hi.view(dt).float() + lo.view(dt).float()
+
+
+def _relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# conv tolerance per math mode: relative to max|ref|.  fp16x3 / bf16x3 carry 22 / 16 operand bits; what remains
+# is the fp32 accumulation inside the tensor core (see DESIGN.md "precision").
+CONV_TOL = {"fp16x3": 4e-6, "bf16x3": 6e-5, "fp16": 3e-3, "bf16": 3e-2}
+
+
+def _conv_case(B, H, W, Cin, Cout, kind, mode_name, block_n=None, seed=0):
+    from wacv23_tsnet_b200 import lib as L, ops
+    torch.manual_seed(seed)
+    m = ops.MathMode(mode_name)
+    x = torch.randn(B, H, W, Cin, device="cuda")
+    xn = x.permute(0, 3, 1, 2)
+    k = 1 if kind == "1x1" else 3
+    w = torch.randn(Cout, Cin, k, k, device="cuda") * 0.05
+    b = torch.randn(Cout, device="cuda")
+    if kind == "1x1":
+        tm, Ho, Wo, ref = L.TAPS_SAME, H, W, F.conv2d(xn, w, b)
+    elif kind == "3x3":
+        tm, Ho, Wo, ref = L.TAPS_REFLECT1, H, W, F.conv2d(F.pad(xn, (1, 1, 1, 1), mode="reflect"), w, b)
+    elif kind == "3x3s2":
+        tm, Ho, Wo, ref = L.TAPS_S2ZERO, H // 2, W // 2, F.conv2d(xn, w, b, stride=2, padding=1)
+    else:  # up3x3
+        up = F.interpolate(xn, scale_factor=2, mode="bilinear", align_corners=False)
+        tm, Ho, Wo, ref = L.TAPS_UP2REFLECT1, 2 * H, 2 * W, F.conv2d(F.pad(up, (1, 1, 1, 1), mode="reflect"), w, b)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    pc = ops.PackedConv(w, b, m, block_n=block_n)
+    hi, lo, g = ops.build_taps(x, m, tm)
+    y, stats = ops.conv_gemm(hi, lo, g, pc, "3x3" if kind == "up3x3" else kind, B, Ho, Wo, m, m.act_scale)
+    mr = ops.instnorm_reduce(stats, B, Ho * Wo, Cout)
+    torch.cuda.synchronize()
+    return y, mr, ref
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kind,bn", [
+    (1, 32, 32, 64, 64, "1x1", None),
+    (2, 32, 32, 1024, 512, "1x1", None),       # FuseNet.conv / Decoder.map_conv shape
+    (2, 32, 32, 128, 128, "3x3", None),
+    (2, 64, 64, 64, 128, "3x3s2", None),
+    (1, 32, 32, 512, 256, "up3x3", None),       # decoder up-conv 1
+])
+def test_conv_gemm_vs_torch(B, H, W, Cin, Cout, kind, bn, mode):
+    y, mr, ref = _conv_case(B, H, W, Cin, Cout, kind, mode, bn)
+    assert _relerr(y, ref) < CONV_TOL[mode] * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
+    if mode.endswith("x3"):
+        assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
+        assert _relerr(mr[..., 1], 1.0 / torch.sqrt(ref.var((1, 2), unbiased=False) + 1e-5)) < 5e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kind,bn", [
+    (3, 32, 32, 512, 512, "3x3", 256),           # the dominant layer: ResnetBlock(512)
+    (3, 32, 32, 512, 512, "3x3", 128),
+    (1, 32, 32, 1024, 1024, "3x3", 256),         # FuseNet ResnetBlock(1024)
+    (2, 256, 256, 64, 128, "3x3s2", None),       # first down-sampling conv (W = 256 > tile width)
+    (1, 128, 128, 128, 64, "up3x3", None),       # last up-conv, Cout = 64
+    (150, 32, 32, 64, 64, "1x1", None),          # more tiles than SMs: persistent loop + TMEM double buffering
+])
+def test_conv_gemm_network_shapes(B, H, W, Cin, Cout, kind, bn):
+    y, mr, ref = _conv_case(B, H, W, Cin, Cout, kind, "fp16x3", bn)
+    assert _relerr(y, ref) < 4e-6 * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
+    assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
+
+
+def test_conv_gemm_is_deterministic_and_batch_invariant():
+    """Same sample -> same bits, whatever the batch it rides in (required for shard == single-GPU equality)."""
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(1)
+    x = torch.randn(5, 32, 32, 256, device="cuda")
+    w = torch.randn(256, 256, 3, 3, device="cuda") * 0.05
+    pc = ops.PackedConv(w, torch.zeros(256, device="cuda"), m)
+    outs = []
+    for xb in (x, x[2:3].contiguous(), x):
+        hi, lo, g = ops.build_taps(xb, m, L.TAPS_REFLECT1)
+        y, st = ops.conv_gemm(hi, lo, g, pc, "3x3", xb.shape[0], 32, 32, m, m.act_scale)
+        outs.append((y, ops.instnorm_reduce(st, xb.shape[0], 1024, 256)))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    assert torch.equal(outs[0][0][2:3], outs[1][0]) and torch.equal(outs[0][1][2:3], outs[1][1])
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3"])
+def test_build_taps_modes(mode):
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode(mode)
+    tol = 2e-6 if m.fmt == 0 else 1e-4
+    torch.manual_seed(2)
+    x = torch.randn(2, 16, 16, 64, device="cuda") * 2
+    xn = x.permute(0, 3, 1, 2)
+    hi, lo, _ = ops.build_taps(x, m, L.TAPS_REFLECT1)
+    assert _relerr(_recon(hi, lo, m.fmt), F.pad(xn, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1) * m.act_scale) < tol
+    hi, lo, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)
+    up = F.pad(F.interpolate(xn, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
+    assert _relerr(_recon(hi, lo, m.fmt), up.permute(0, 2, 3, 1) * m.act_scale) < tol
+    hi, lo, _ = ops.build_taps(x, m, L.TAPS_S2ZERO)
+    xp = F.pad(xn, (1, 1, 1, 1)).permute(0, 2, 3, 1)
+    got = _recon(hi, lo, m.fmt).view(2, 4, 9, 9, 64)
+    for k, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+        assert _relerr(got[:, k], xp[:, py::2, px::2] * m.act_scale) < tol
+    # InstanceNorm + ReLU + residual (ResnetBlock tail) and channel-offset concat
+    mr = torch.stack([x.mean((1, 2)), 1.0 / torch.sqrt(x.var((1, 2), unbiased=False) + 1e-5)], -1).contiguous()
+    res = torch.randn_like(x)
+    act = torch.zeros(2, 16, 16, 128, device="cuda")
+    cat_hi = torch.zeros(2, 18, 18, 128, dtype=torch.int16, device="cuda")
+    cat_lo = torch.zeros_like(cat_hi)
+    ops.build_taps(x, m, L.TAPS_REFLECT1, mean_rstd=mr, relu=True, residual=res, act_out=act, act_c_off=64,
+                   taps=(cat_hi, cat_lo), c_off=64)
+    ref = F.relu(F.instance_norm(xn, eps=1e-5)).permute(0, 2, 3, 1) + res
+    assert _relerr(act[..., 64:], ref) < 1e-6 and float(act[..., :64].abs().max()) == 0.0
+    refp = F.pad(ref.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1) * m.act_scale
+    assert _relerr(_recon(cat_hi, cat_lo, m.fmt)[..., 64:], refp) < tol
+    assert int(cat_hi[..., :64].abs().max()) == 0
+    # mean over sources (torch.stack(...).mean(1), model/TSNet.py:400)
+    x3 = torch.randn(6, 8, 8, 64, device="cuda")
+    a3 = torch.empty(2, 8, 8, 64, device="cuda")
+    ops.build_taps(x3, m, L.TAPS_SAME, avg_n=3, act_out=a3, want_taps=False)
+    assert _relerr(a3, torch.stack([x3[0:2], x3[2:4], x3[4:6]], 1).mean(1)) < 2e-7
+
+
+@pytest.mark.parametrize("label_nc", [2, 25])
+def test_stem_taps_and_stem_conv(label_nc):
+    """cat[img/255, lbl] + CoordConv + ReflectionPad2d(3) + 7x7 conv (model/TSNet.py:66, 107-125, 312)."""
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(3)
+    img = torch.rand(2, 3, 128, 128, device="cuda") * 255 - 100
+    lbl = (torch.rand(2, label_nc, 128, 128, device="cuda") > 0.7).float()
+    w = torch.randn(64, 3 + label_nc + 3, 7, 7, device="cuda") * 0.02
+    b = torch.randn(64, device="cuda") * 0.1
+    pc = ops.PackedConv(w, b, m, fold_kw=True)
+    hi, lo, g = ops.stem_taps(img, 255.0, lbl, pc.Cp, m)
+    full = O.coord_channels(torch.cat([img.cpu() / 255.0, lbl.cpu()], 1)).cuda()
+    cin = full.shape[1]
+    fp = F.pad(full, (3, 3, 3, 3), mode="reflect")
+    got = _recon(hi, lo, m.fmt)
+    for s in range(7):
+        assert _relerr(got[..., s * cin:(s + 1) * cin], fp[:, :, :, s:s + 128].permute(0, 2, 3, 1) * m.act_scale) < 2e-6
+    assert float(got[..., 7 * cin:].abs().max()) == 0.0
+    y, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)
+    ref = F.conv2d(fp, w, b).permute(0, 2, 3, 1)
+    assert _relerr(y, ref) < 4e-6
+
+
+def test_l2norm_and_head():
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(4)
+    f = torch.randn(2, 64, 512, device="cuda")
+    f[0, 3] = 0  # all-zero vector: F.normalize gives 0 (eps clamp)
+    hi, lo = ops.l2norm_split(f, m)
+    assert _relerr(_recon(hi, lo, m.fmt).view(2, 64, 512), F.normalize(f, dim=2) * m.corr_scale) < 1e-6
+    a = torch.randn(2, 64, 64, 64, device="cuda")
+    wh = torch.randn(3, 64, 7, 7, device="cuda") * 0.02
+    bh = torch.randn(3, device="cuda") * 0.1
+    ref = torch.tanh(F.conv2d(F.pad(a.permute(0, 3, 1, 2), (3, 3, 3, 3), mode="reflect"), wh, bh))
+    assert float((ops.head_conv_tanh(a, wh, bh) - ref).abs().max()) < 1e-5
+    a = torch.randn(1, 256, 256, 64, device="cuda")
+    fill = (-0.4, -0.44, -0.438)
+    out = ops.head_conv_tanh(a, wh, bh, fore=(64, 192), fill=fill)
+    ref = torch.tanh(F.conv2d(F.pad(a.permute(0, 3, 1, 2), (3, 3, 3, 3), mode="reflect"), wh, bh))
+    assert float((out[..., 64:192] - ref[..., 64:192]).abs().max()) < 1e-5
+    assert torch.equal(out[..., :64], torch.tensor(fill, device="cuda").view(1, 3, 1, 1).expand(1, 3, 256, 64))
+
+
+def _corr_inputs(B, n, kind, seed):
+    g = torch.Generator().manual_seed(seed)
+    tar = torch.relu(torch.randn(B, 512, 32, 32, generator=g))
+    tar[0, :, 3, 5] = 0  # all-zero target vector -> zero logits -> uniform softmax row
+    srcs = [torch.randn(B, 512, 32, 32, generator=g) * 3 for _ in range(n)]
+    if kind == "rect_u8":
+        tb = torch.zeros(B, 1, 256, 256, dtype=torch.uint8)
+        tb[:, :, 40:200, 30:220] = 1
+        sbs = []
+        for i in range(n):
+            sb = torch.zeros(B, 1, 256, 256, dtype=torch.uint8)
+            sb[:, :, 20 + 10 * i:180, 50:230 - 10 * i] = 1
+            sbs.append(sb)
+    elif kind == "random_f32":
+        tb = torch.randint(0, 2, (B, 1, 256, 256), generator=g).float()
+        sbs = [torch.randint(0, 2, (B, 1, 256, 256), generator=g).float() for _ in range(n)]
+    elif kind == "all_one":
+        tb = torch.ones(B, 1, 256, 256)
+        sbs = [torch.ones(B, 1, 256, 256) for _ in range(n)]
+    elif kind == "all_zero_tar":  # nothing matches: every logit 0 -> warp grid = mean coordinate = (0, 0)
+        tb = torch.zeros(B, 1, 256, 256)
+        sbs = [torch.ones(B, 1, 256, 256) for _ in range(n)]
+    else:  # soft (non-binary) float masks: general weight mt*ms + (1-mt)(1-ms)
+        tb = torch.rand(B, 1, 256, 256, generator=g)
+        sbs = [torch.rand(B, 1, 256, 256, generator=g) for _ in range(n)]
+    return tar, srcs, tb, sbs
+
+
+@pytest.mark.parametrize("B,n,kind", [(1, 1, "random_f32"), (2, 3, "rect_u8"), (1, 5, "random_f32"), (1, 8, "rect_u8"),
+                                      (1, 2, "all_one"), (1, 2, "all_zero_tar"), (1, 2, "soft")])
+def test_corr_warp_vs_oracle(B, n, kind):
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    tar, srcs, tb, sbs = _corr_inputs(B, n, kind, seed=10 + n)
+    ref_mean, ref_grids = O.corr_warp(tar, srcs, tb, sbs)
+    tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda()
+    src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).cuda()
+    tar_ops = ops.l2norm_split(tar_d.view(B, 1024, 512), m)
+    src_ops = ops.l2norm_split(src_d.view(n * B, 1024, 512), m)
+    coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
+    out, grids = ops.corr_warp(tar_ops, src_ops, [src_d[i].view(B, 1024, 512) for i in range(n)],
+                               tb.squeeze(1).contiguous().cuda(), [s.squeeze(1).contiguous().cuda() for s in sbs], coord,
+                               B, 512, 32, 32, m, want_grids=True)
+    torch.cuda.synchronize()
+    gerr = max(float((grids[i].cpu() - ref_grids[i]).abs().max()) for i in range(n))
+    assert gerr < 5e-5, gerr          # in [-1, 1] units; 5e-5 = 8e-4 feature pixels
+    assert _relerr(out.view(B, 32, 32, 512).permute(0, 3, 1, 2).cpu(), ref_mean) < 1e-3
+    if kind == "all_zero_tar":
+        assert float(torch.stack([g for g in grids]).abs().max()) < 1e-5
+    # uint8 and float masks with the same {0,1} content must give identical bits (integer-exact mask path)
+    if kind == "rect_u8":
+        out2, grids2 = ops.corr_warp(tar_ops, src_ops, [src_d[i].view(B, 1024, 512) for i in range(n)],
+                                     tb.squeeze(1).float().contiguous().cuda(),
+                                     [s.squeeze(1).float().contiguous().cuda() for s in sbs], coord, B, 512, 32, 32, m,
+                                     want_grids=True)
+        assert torch.equal(out, out2) and torch.equal(grids, grids2)
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode("fp16x3")
+    x = torch.randn(1, 10, 10, 64, device="cuda")  # 100 pixels: not a multiple of the 128-pixel tile
+    w = torch.randn(64, 64, 1, 1, device="cuda")
+    pc = ops.PackedConv(w, torch.zeros(64, device="cuda"), m)
+    hi, lo, g = ops.build_taps(x, m, L.TAPS_SAME)
+    with pytest.raises(L.TSNetLibraryError, match="multiple of 128"):
+        ops.conv_gemm(hi, lo, g, pc, "1x1", 1, 10, 10, m, m.act_scale)

@@ -105,6 +105,7 @@ struct TapsArgs {
   int B, H, W, C, mode, relu, Cp_total, c_off, fmt;
   float scale;
   int Hd, Wd, planes;  // destination geometry
+  int act_C_total, act_c_off, avg_n;
 };
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -160,6 +161,26 @@ __global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
     bool interior = false;  // destination pixel that owns the (unique) act_out write of its source pixel
     if (a.mode == TSNET_TAPS_SAME) {
       fetch_act8(a, b, yd, xd, c, mean, rstd, v);
+      if (a.avg_n > 1) {  // mean over sources: samples b, B + b, 2B + b, ...
+        for (int i = 1; i < a.avg_n; ++i) {
+          const int bi = i * a.B + b;
+          if (a.mean_rstd) {
+            const float* mr = a.mean_rstd + (static_cast<size_t>(bi) * a.C + c) * 2;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float4 t = *reinterpret_cast<const float4*>(mr + j * 2);
+              mean[j] = t.x; rstd[j] = t.y; mean[j + 1] = t.z; rstd[j + 1] = t.w;
+            }
+          }
+          float u[8];
+          fetch_act8(a, bi, yd, xd, c, mean, rstd, u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += u[j];
+        }
+        const float nf = static_cast<float>(a.avg_n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __fdiv_rn(v[j], nf);
+      }
       interior = true;
     } else if (a.mode == TSNET_TAPS_REFLECT1) {
       const int y = reflect_idx(yd - 1, a.H), x = reflect_idx(xd - 1, a.W);
@@ -194,7 +215,7 @@ __global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
     }
     if (a.act_out && interior) {
       const int y = a.mode == TSNET_TAPS_SAME ? yd : yd - 1, x = a.mode == TSNET_TAPS_SAME ? xd : xd - 1;
-      float* o = a.act_out + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.C + c;
+      float* o = a.act_out + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.act_C_total + a.act_c_off + c;
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
 // ------------------------------------------------------------------------------------------------
 // stem tap source: [B, H+6, W, Cp], kw folded into channels.  One thread = one destination pixel.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_scale,
+__global__ void __launch_bounds__(128) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_div,
                                                         const float* __restrict__ lbl, int Clbl, int B, int H, int W,
                                                         int Cp, int fmt, float scale, uint16_t* __restrict__ hi,
                                                         uint16_t* __restrict__ lo) {
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(128) stem_taps_kernel(const float* __restrict_
       if (s < 7) {
         const int xs = reflect_idx(x + s - 3, W);
         if (c < Cimg) {
-          v = img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs] * img_scale;
+          v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
         } else if (c < Cimg + Clbl) {
           v = lbl[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane + static_cast<size_t>(ys) * W + xs];
         } else {
@@ -469,6 +490,12 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   a.raw = raw; a.mean_rstd = mean_rstd; a.residual = residual; a.act_out = act_out; a.hi = taps_hi; a.lo = taps_lo;
   a.B = d->B; a.H = d->H; a.W = d->W; a.C = d->C; a.mode = d->mode; a.relu = d->relu; a.Cp_total = d->Cp_total;
   a.c_off = d->c_off; a.fmt = d->fmt; a.scale = d->scale == 0.f ? 1.f : d->scale;
+  a.act_C_total = d->act_C_total > 0 ? d->act_C_total : d->C;
+  a.act_c_off = d->act_c_off;
+  a.avg_n = d->avg_n > 1 ? d->avg_n : 1;
+  TSNET_ARG_CHECK(a.avg_n == 1 || d->mode == TSNET_TAPS_SAME, "build_taps: avg_n needs mode SAME");
+  TSNET_ARG_CHECK(a.act_c_off % 4 == 0 && a.act_C_total % 4 == 0 && a.act_c_off + d->C <= a.act_C_total,
+                  "build_taps: act_out channel window does not fit");
   a.planes = 1;
   switch (d->mode) {
     case TSNET_TAPS_SAME: a.Hd = d->H; a.Wd = d->W; break;
@@ -485,7 +512,7 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   return 0;
 }
 
-extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_scale, const float* lbl_nchw, int Clbl,
+extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const float* lbl_nchw, int Clbl,
                                int B, int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi,
                                uint16_t* taps_lo, void* stream) {
   TSNET_ARG_CHECK(lbl_nchw && taps_hi && taps_lo, "stem_taps: null argument");
@@ -493,7 +520,7 @@ extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_scale,
   TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3), "stem_taps: Cp %d too small", Cp);
   const size_t total = static_cast<size_t>(B) * (H + 6) * W;
   stem_taps_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      img_nchw, Cimg, img_scale, lbl_nchw, Clbl, B, H, W, Cp, fmt, scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
+      img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl_nchw, Clbl, B, H, W, Cp, fmt, scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

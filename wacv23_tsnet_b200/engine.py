@@ -1,0 +1,181 @@
+"""Forward engine: sequences the sm_100a kernels for TSNet.forward().
+
+Reference path being replaced: model/TSNet.py:309-407 (face) and model/TSNet_pose.py:325-417 (pose),
+is_train=False.  All activations stay on the device in NHWC; the only torch ops used are allocations.
+The n sources are run through img_enc / fuse_net as ONE batch of n*B samples (shared weights), the target
+through lbl_enc / dec as a batch of B.
+"""
+import torch
+
+from . import lib as L
+from . import ops
+from .ops import MathMode, PackedConv
+
+
+class ForwardEngine:
+    def __init__(self, img_enc, lbl_enc, fuse_net, dec, label_nc, n_blocks_dec, n_downsampling=3, ngf=64,
+                 math_mode="fp16x3"):
+        if n_downsampling != 3 or ngf != 64:
+            # FuseNet(ngf=1024) is hard-coded in the reference (model/TSNet.py:227): only 64 * 2^3 = 512 fits.
+            raise ValueError("TS-Net geometry requires ngf=64, n_downsampling=3 (FuseNet is fixed at 1024 channels)")
+        self.nets = dict(img_enc=img_enc, lbl_enc=lbl_enc, fuse_net=fuse_net, dec=dec)
+        self.label_nc = label_nc
+        self.n_blocks_dec = n_blocks_dec
+        self.mode = MathMode(math_mode)
+        self._packs = {}
+        self._coord = {}
+
+    # ------------------------------------------------------------------ weights
+    def _pack(self, net, wkey, fold_kw=False, block_n=None):
+        """Packed weight for parameter `wkey` of sub-net `net`; re-packed when the parameter changed
+        (load_state_dict / optimizer step bump the tensor version)."""
+        sd = self.nets[net].state_dict(keep_vars=True)
+        w, b = sd[wkey + ".weight"], sd[wkey + ".bias"]
+        sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, self.mode.name)
+        key = (net, wkey)
+        hit = self._packs.get(key)
+        if hit is None or hit[0] != sig:
+            hit = (sig, PackedConv(w, b, self.mode, fold_kw=fold_kw, block_n=block_n))
+            self._packs[key] = hit
+        return hit[1]
+
+    def _coord_table(self, h, w, device):
+        key = (h, w, str(device))
+        if key not in self._coord:
+            self._coord[key] = torch.cat([torch.linspace(-1, 1, h), torch.linspace(-1, 1, w)]).float().to(device)
+        return self._coord[key]
+
+    # ------------------------------------------------------------------ building blocks
+    def _conv(self, taps, pc, kind, B, H, W, norm=True):
+        hi, lo, geom = taps
+        y, stats = ops.conv_gemm(hi, lo, geom, pc, kind, B, H, W, self.mode, self.mode.act_scale, want_stats=norm)
+        mr = ops.instnorm_reduce(stats, B, H * W, pc.Cout) if norm else None
+        return y, mr
+
+    def _resblock(self, net, prefix, taps, x_res, B, H, W, last_taps=None, last_c_off=0, need_act=True,
+                  want_taps=True, tmode_out=L.TAPS_REFLECT1):
+        """ResnetBlock (model/TSNet.py:10-49). taps = reflect-padded split input, x_res = fp32 input (residual).
+        Returns (taps of the output, fp32 output or None)."""
+        m = self.mode
+        pc1 = self._pack(net, prefix + "conv_block.1")
+        pc5 = self._pack(net, prefix + "conv_block.5")
+        y1, mr1 = self._conv(taps, pc1, "3x3", B, H, W)
+        t1 = ops.build_taps(y1, m, L.TAPS_REFLECT1, mean_rstd=mr1, relu=True)
+        y2, mr2 = self._conv(t1, pc5, "3x3", B, H, W)
+        act_out = torch.empty_like(y2) if need_act else None
+        t2 = ops.build_taps(y2, m, tmode_out, mean_rstd=mr2, residual=x_res, act_out=act_out, taps=last_taps,
+                            c_off=last_c_off, want_taps=want_taps)
+        return t2, act_out
+
+    def _encoder(self, net, img, img_div, lbl, n_blocks, final_taps=None):
+        """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it or None).
+        For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the residual stream."""
+        m = self.mode
+        X, _, H, W = lbl.shape
+        pc = self._pack(net, "model.1", fold_kw=True)
+        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m)
+        y, mr = self._conv(t, pc, "7x1", X, H, W)
+        for k, idx in enumerate((4, 7, 10)):
+            t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
+            pc = self._pack(net, f"model.{idx}")
+            H, W = H // 2, W // 2
+            y, mr = self._conv(t, pc, "3x3s2", X, H, W)
+        if n_blocks == 0:
+            fea = torch.empty_like(y)
+            ops.build_taps(y, m, L.TAPS_SAME, mean_rstd=mr, relu=True, act_out=fea, want_taps=False)
+            return fea, None
+        x = torch.empty_like(y)
+        t = ops.build_taps(y, m, L.TAPS_REFLECT1, mean_rstd=mr, relu=True, act_out=x)
+        for blk in range(n_blocks):
+            last = blk == n_blocks - 1
+            t, x = self._resblock(net, f"model.{13 + blk}.", t, x, X, H, W,
+                                  last_taps=final_taps if last else None)
+        return x, t
+
+    # ------------------------------------------------------------------ whole forward
+    @torch.no_grad()
+    def forward(self, src_imgs, img_divs, src_lbls, src_bboxes, tar_lbl, tar_bbox, return_flow=False,
+                pose_fill=None, collect=None):
+        """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (images NOT yet /255:
+        img_divs[i] is the divisor set_*_input would have applied: 255, or 1 for use_prev sources); src_bboxes / tar_bbox: [B,256,256] uint8|fp32.
+        Returns (rec_tar_img NCHW fp32, list of warp grids [B,h,w,2] or None).
+        `collect`: optional dict receiving intermediates (tests)."""
+        L.require_device()
+        m = self.mode
+        n = len(src_imgs)
+        B, _, H0, W0 = tar_lbl.shape
+        dev = tar_lbl.device
+        h, w, Cf = H0 // 8, W0 // 8, 512
+        hw = h * w
+
+        # ---- encoders.  FuseNet input = cat[src_fea, tar_fea] (model/TSNet.py:196): the last img_enc block writes its
+        # reflect-padded split output straight into channels [0,512) of the 1024-channel tap source.
+        fuse_hi = torch.empty((n * B, h + 2, w + 2, 2 * Cf), dtype=torch.int16, device=dev)
+        fuse_lo = torch.empty_like(fuse_hi)
+        if n > 1 and len(set(img_divs)) > 1:
+            # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
+            src_imgs = [im if dv == 1.0 else im / dv for im, dv in zip(src_imgs, img_divs)]
+            img_divs = [1.0] * n
+        img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
+        lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
+        src_fea, _ = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]), lbl_cat.contiguous(), 9,
+                                   final_taps=(fuse_hi, fuse_lo))                       # [n*B, h, w, 512]
+        tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
+
+        # ---- transformation branch (model/TSNet.py:319-366, 392)
+        tar_ops = ops.l2norm_split(tar_fea.view(B, hw, Cf), m)
+        src_ops = ops.l2norm_split(src_fea.view(n * B, hw, Cf), m)
+        src_fea_v = src_fea.view(n, B, hw, Cf)
+        pg_mean, grids = ops.corr_warp(tar_ops, src_ops, [src_fea_v[i] for i in range(n)], tar_bbox.contiguous(),
+                                       [bb.contiguous() for bb in src_bboxes], self._coord_table(h, w, dev), B, Cf, h,
+                                       w, m, want_grids=return_flow)
+
+        # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400)
+        cat_act = torch.empty((n * B, h, w, 2 * Cf), dtype=torch.float32, device=dev)
+        ops.build_taps(src_fea, m, L.TAPS_SAME, act_out=cat_act, act_c_off=0, want_taps=False)
+        for i in range(n):
+            sl = slice(i * B, (i + 1) * B)
+            ops.build_taps(tar_fea, m, L.TAPS_REFLECT1, act_out=cat_act[sl], act_c_off=Cf,
+                           taps=(fuse_hi[sl], fuse_lo[sl]), c_off=Cf)
+        tf = (fuse_hi, fuse_lo, (1, h + 2, w + 2))
+        tfo, _ = self._resblock("fuse_net", "model.0.", tf, cat_act, n * B, h, w, tmode_out=L.TAPS_SAME,
+                                need_act=False)
+        pcf = self._pack("fuse_net", "conv")
+        sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
+
+        # ---- decoder (model/TSNet.py:128-174): map_conv on cat[pg_mean, mean_i sg_i]
+        dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
+        dec_lo = torch.empty_like(dec_hi)
+        ops.build_taps(pg_mean.view(B, h, w, Cf), m, L.TAPS_SAME, taps=(dec_hi, dec_lo), c_off=0)
+        sg_mean = torch.empty((B, h, w, Cf), dtype=torch.float32, device=dev) if collect is not None else None
+        ops.build_taps(sg, m, L.TAPS_SAME, taps=(dec_hi, dec_lo), c_off=Cf, avg_n=n, act_out=sg_mean)
+        pcm = self._pack("dec", "map_conv")
+        x, _ = self._conv((dec_hi, dec_lo, (1, h, w)), pcm, "1x1", B, h, w, norm=False)
+        nb = self.n_blocks_dec
+        Hc, Wc = h, w
+        if nb > 0:
+            t = ops.build_taps(x, m, L.TAPS_REFLECT1)
+            for blk in range(nb):
+                last = blk == nb - 1
+                t, x = self._resblock("dec", f"model{blk}.0.", t, x, B, Hc, Wc,
+                                      tmode_out=L.TAPS_UP2REFLECT1 if last else L.TAPS_REFLECT1,
+                                      need_act=not last)
+        else:
+            t = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)
+        for i in range(3):
+            pc = self._pack("dec", f"model{nb + i}.2")
+            Hc, Wc = Hc * 2, Wc * 2
+            y, mr = self._conv(t, pc, "3x3", B, Hc, Wc)
+            if i < 2:
+                t = ops.build_taps(y, m, L.TAPS_UP2REFLECT1, mean_rstd=mr, relu=True)
+        act = torch.empty_like(y)
+        ops.build_taps(y, m, L.TAPS_SAME, mean_rstd=mr, relu=True, act_out=act, want_taps=False)
+        sd = self.nets["dec"].state_dict(keep_vars=True)
+        hw_key = f"model{nb + 3}.1"
+        fore, fill = (None, None) if pose_fill is None else ((64, 192), pose_fill)
+        rec = ops.head_conv_tanh(act, sd[hw_key + ".weight"], sd[hw_key + ".bias"], fore=fore, fill=fill)
+
+        if collect is not None:
+            collect.update(src_fea=src_fea_v, tar_fea=tar_fea, pg_mean=pg_mean.view(B, h, w, Cf), sg_mean=sg_mean)
+        grid_list = [grids[i] for i in range(n)] if return_flow else None
+        return rec, grid_list

@@ -1,0 +1,95 @@
+"""ctypes binding of libtsnet_sm100.so (include/tsnet_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C wacv23_tsnet_b200/csrc`.
+There is no fallback: a missing library or a non-sm_100 device raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtsnet_sm100.so")
+
+FMT_FP16, FMT_BF16 = 0, 1
+TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1 = 0, 1, 2, 3
+MAX_TAPS = 49
+
+vp = C.c_void_p
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int), ("Cout_pad", C.c_int),
+                ("Cp", C.c_int), ("Hp", C.c_int), ("Wp", C.c_int), ("planes", C.c_int), ("num_taps", C.c_int),
+                ("tap_dy", C.c_int8 * MAX_TAPS), ("tap_dx", C.c_int8 * MAX_TAPS), ("tap_plane", C.c_int8 * MAX_TAPS),
+                ("block_n", C.c_int), ("split", C.c_int), ("fmt", C.c_int), ("out_scale", C.c_float)]
+
+
+class TapsDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("mode", C.c_int),
+                ("relu", C.c_int), ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int),
+                ("scale", C.c_float), ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("avg_n", C.c_int)]
+
+
+class CorrDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("n_src", C.c_int), ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
+                ("bbox_h", C.c_int), ("bbox_w", C.c_int), ("bbox_dtype", C.c_int), ("temperature", C.c_float),
+                ("split", C.c_int), ("fmt", C.c_int), ("operand_scale", C.c_float)]
+
+
+_SIGNATURES = {
+    "tsnet_abi_version": (C.c_int, []),
+    "tsnet_last_error": (C.c_char_p, []),
+    "tsnet_device_ok": (C.c_int, []),
+    "tsnet_pack_conv_weight": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_int, vp, vp, vp]),
+    "tsnet_conv_gemm_fwd": (C.c_int, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
+    "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
+    "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_float, vp, vp, vp]),
+    "tsnet_l2norm_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
+    "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp, vp,
+                                      vp, vp, C.c_size_t, vp]),
+    "tsnet_corr_warp_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
+    "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
+                                       C.POINTER(C.c_float), vp, vp]),
+    "tsnet_direct_conv_fp32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, vp, vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class TSNetLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise TSNetLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the TS-Net hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.tsnet_abi_version() != 1:
+            raise TSNetLibraryError("libtsnet_sm100.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TSNetLibraryError(f"libtsnet_sm100 error {rc}: {load().tsnet_last_error().decode()}")
+
+
+def require_device():
+    import torch
+    if not torch.cuda.is_available():
+        raise TSNetLibraryError("TS-Net B200 forward needs a CUDA device (sm_100); none is visible")
+    if not load().tsnet_device_ok():
+        raise TSNetLibraryError("TS-Net B200 kernels are built for sm_100a only; current device is not CC 10.x")

@@ -1,0 +1,283 @@
+"""Thin tensor-level wrappers over the C ABI (include/tsnet_b200.h).
+
+torch is used only for device memory and the current stream; every function enqueues exactly one
+kernel of libtsnet_sm100.so.  `LAUNCHES` counts them (bench.py reports it as gpu_launches).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+
+LAUNCHES = 0
+PROFILE = None  # bench.py sets this to a dict: key -> [(start_event, end_event), ...] around every launch
+
+
+class _Prof:
+    """CUDA events on the launching stream around one kernel launch (only while PROFILE is a dict)."""
+
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        self.e0 = None
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None and PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.key, []).append((self.e0, e1))
+        return False
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _count():
+    global LAUNCHES
+    LAUNCHES += 1
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous(), (t.dtype, t.device, t.is_contiguous())
+    return t
+
+
+class MathMode:
+    """Operand format of the tensor-core path.
+
+    fp16x3 (default): x = hi + lo in fp16 (22 significant bits while lo is normal), three MMAs per K step,
+                      fp32 accumulate -- fp32-faithful (DESIGN.md "precision").
+    bf16x3:           same with bf16 (16 significant bits), no range management needed.
+    fp16 / bf16:      hi term only -- fast, NOT parity grade (reported separately, never the headline).
+    Scales are powers of two so they are exact; they keep lo terms out of the fp16 subnormal range.
+    """
+
+    def __init__(self, name="fp16x3"):
+        assert name in ("fp16x3", "bf16x3", "fp16", "bf16"), name
+        self.name = name
+        self.fmt = L.FMT_FP16 if name.startswith("fp16") else L.FMT_BF16
+        self.split = 1 if name.endswith("x3") else 0
+        self.act_scale = 16.0 if self.fmt == L.FMT_FP16 else 1.0
+        self.corr_scale = 4096.0 if self.fmt == L.FMT_FP16 else 1.0
+
+    def weight_scale(self, w):
+        if self.fmt != L.FMT_FP16:
+            return 1.0
+        m = float(w.abs().max())
+        if not math.isfinite(m) or m == 0.0:
+            return 1.0
+        return 2.0 ** math.floor(math.log2(8192.0 / m))  # max |w * s| in (4096, 8192]
+
+
+class PackedConv:
+    """A conv weight packed for tsnet_conv_gemm_fwd (K-major hi/lo, zero padded)."""
+
+    def __init__(self, weight, bias, mode, fold_kw=False, Cp=None, block_n=None):
+        L.require_device()
+        w = _f32(weight.detach())
+        Cout, Cin, KH, KW = w.shape
+        self.Cout, self.Cin, self.KH, self.KW, self.fold_kw = Cout, Cin, KH, KW, bool(fold_kw)
+        need = KW * Cin if fold_kw else Cin
+        self.Cp = Cp if Cp is not None else (need + 63) // 64 * 64
+        assert self.Cp >= need and self.Cp % 64 == 0
+        self.num_taps = KH if fold_kw else KH * KW
+        if block_n is None:
+            block_n = 64 if Cout <= 64 else (128 if Cout <= 128 else 256)
+        self.block_n = block_n
+        self.Cout_pad = (Cout + block_n - 1) // block_n * block_n
+        self.scale = mode.weight_scale(w)
+        K = self.num_taps * self.Cp
+        self.w_hi = torch.empty((self.Cout_pad, K), dtype=torch.int16, device=w.device)
+        self.w_lo = torch.empty_like(self.w_hi)
+        self.bias = None if bias is None else _f32(bias.detach())
+        L.check(L.load().tsnet_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW, int(self.fold_kw), self.Cp, self.Cout_pad,
+                                                C.c_float(self.scale), mode.fmt, _ptr(self.w_hi), _ptr(self.w_lo),
+                                                _stream()))
+        _count()
+
+
+def taps_geometry(mode, H, W):
+    """(planes, Hd, Wd) of the tap source built from an H x W activation."""
+    if mode == L.TAPS_SAME:
+        return 1, H, W
+    if mode == L.TAPS_REFLECT1:
+        return 1, H + 2, W + 2
+    if mode == L.TAPS_S2ZERO:
+        return 4, H // 2 + 1, W // 2 + 1
+    if mode == L.TAPS_UP2REFLECT1:
+        return 1, 2 * H + 2, 2 * W + 2
+    raise ValueError(mode)
+
+
+def conv_taps(kind):
+    """tap tables (dy, dx, plane) for the conv kinds of the network."""
+    if kind == "1x1":
+        return [(0, 0, 0)]
+    if kind == "3x3":  # stride 1 on a pad-1 tap source
+        return [(r, s, 0) for r in range(3) for s in range(3)]
+    if kind == "3x3s2":  # stride 2 on the parity-split zero-padded tap source
+        return [(r >> 1, s >> 1, (r & 1) * 2 + (s & 1)) for r in range(3) for s in range(3)]
+    if kind == "7x1":  # kw-folded 7x7 stem
+        return [(r, 0, 0) for r in range(7)]
+    raise ValueError(kind)
+
+
+def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None):
+    """taps_* : int16 [B*planes, Hp, Wp, Cp]; geom = (planes, Hp, Wp). Returns (y_raw [B,H,W,Cout], stats)."""
+    planes, Hp, Wp = geom
+    d = L.ConvDesc()
+    d.B, d.H, d.W, d.Cout, d.Cout_pad, d.Cp = B, H, W, pc.Cout, pc.Cout_pad, pc.Cp
+    d.Hp, d.Wp, d.planes = Hp, Wp, planes
+    taps = conv_taps(kind)
+    assert len(taps) == pc.num_taps, (kind, pc.num_taps)
+    d.num_taps = len(taps)
+    for t, (dy, dx, pl) in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t], d.tap_plane[t] = dy, dx, pl
+    d.block_n, d.split, d.fmt = pc.block_n, mode.split, mode.fmt
+    d.out_scale = 1.0 / (pc.scale * act_scale)
+    assert taps_hi.shape == (B * planes, Hp, Wp, pc.Cp), (tuple(taps_hi.shape), (B * planes, Hp, Wp, pc.Cp))
+    if y is None:
+        y = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=taps_hi.device)
+    if want_stats and stats is None:
+        stats = torch.empty((B * H * W // 32, pc.Cout, 2), dtype=torch.float32, device=taps_hi.device)
+    cin_eff = pc.Cin * (pc.KW if pc.fold_kw else 1)
+    with _Prof(("conv_gemm", kind, B, H, W, cin_eff, pc.Cout, len(taps))):
+        L.check(L.load().tsnet_conv_gemm_fwd(C.byref(d), _ptr(taps_hi), _ptr(taps_lo), _ptr(pc.w_hi), _ptr(pc.w_lo),
+                                             _ptr(pc.bias), _ptr(y), _ptr(stats) if want_stats else None, _stream()))
+    _count()
+    return y, (stats if want_stats else None)
+
+
+def instnorm_reduce(stats, B, HW, Cch, eps=1e-5, out=None):
+    if out is None:
+        out = torch.empty((B, Cch, 2), dtype=torch.float32, device=stats.device)
+    with _Prof(("instnorm_reduce",)):
+        L.check(L.load().tsnet_instnorm_reduce(_ptr(stats), B, HW, Cch, C.c_float(eps), _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_out=None, act_c_off=0,
+               taps=None, c_off=0, want_taps=True, avg_n=1, act_scale=None):
+    """raw: fp32 [avg_n*B, H, W, C].  Returns (taps_hi, taps_lo, geom) (None, None, geom when want_taps=False).
+    `taps` = (hi, lo) preallocated destination (for channel-concatenation), else allocated here."""
+    Bt, H, W, Cch = raw.shape
+    B = Bt // avg_n
+    planes, Hd, Wd = taps_geometry(tmode, H, W)
+    d = L.TapsDesc()
+    d.B, d.H, d.W, d.C, d.mode, d.relu = B, H, W, Cch, tmode, int(relu)
+    d.fmt = mode.fmt
+    d.scale = mode.act_scale if act_scale is None else act_scale
+    d.avg_n = avg_n
+    hi = lo = None
+    if want_taps:
+        if taps is None:
+            Cp = (Cch + 63) // 64 * 64
+            hi = torch.empty((B * planes, Hd, Wd, Cp), dtype=torch.int16, device=raw.device)
+            lo = torch.empty_like(hi)
+            if Cp != Cch:
+                hi.zero_()
+                lo.zero_()
+        else:
+            hi, lo = taps
+        assert hi.shape[:3] == (B * planes, Hd, Wd), (tuple(hi.shape), (B * planes, Hd, Wd))
+        d.Cp_total, d.c_off = hi.shape[3], c_off
+    if act_out is not None:
+        d.act_C_total, d.act_c_off = act_out.shape[-1], act_c_off
+    with _Prof(("build_taps",)):
+        L.check(L.load().tsnet_build_taps(C.byref(d), _ptr(_f32(raw)), _ptr(mean_rstd), _ptr(residual), _ptr(act_out),
+                                          _ptr(hi), _ptr(lo), _stream()))
+    _count()
+    return hi, lo, (planes, Hd, Wd)
+
+
+def stem_taps(img, img_div, lbl, Cp, mode):
+    """img [B,3,H,W] fp32 NCHW or None (divided by img_div in the kernel); lbl [B,L,H,W].
+    Returns (hi, lo, geom) of the kw-folded tap source."""
+    B, Clbl, H, W = lbl.shape
+    Cimg = 0 if img is None else img.shape[1]
+    hi = torch.empty((B, H + 6, W, Cp), dtype=torch.int16, device=lbl.device)
+    lo = torch.empty_like(hi)
+    with _Prof(("stem_taps",)):
+        L.check(L.load().tsnet_stem_taps(_ptr(None if img is None else _f32(img)), Cimg, C.c_float(img_div),
+                                         _ptr(_f32(lbl)), Clbl, B, H, W, Cp, mode.fmt, C.c_float(mode.act_scale),
+                                         _ptr(hi), _ptr(lo), _stream()))
+    _count()
+    return hi, lo, (1, H + 6, W)
+
+
+def l2norm_split(fea, mode, out=None):
+    """fea fp32 [B, hw, C] (NHWC flattened) -> (hi, lo) int16 [B*hw, C] of F.normalize(dim=C) * corr_scale."""
+    B, HW, Cch = fea.shape
+    if out is None:
+        hi = torch.empty((B * HW, Cch), dtype=torch.int16, device=fea.device)
+        lo = torch.empty_like(hi)
+    else:
+        hi, lo = out
+    with _Prof(("l2norm_split",)):
+        L.check(L.load().tsnet_l2norm_split(_ptr(_f32(fea)), B, HW, Cch, mode.fmt, C.c_float(mode.corr_scale),
+                                            _ptr(hi), _ptr(lo), _stream()))
+    _count()
+    return hi, lo
+
+
+def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode,
+              temperature=100.0, want_grids=False):
+    """tar_ops = (hi, lo) [B*hw, C]; src_ops = (hi, lo) [n*B*hw, C]; src_fea_list n x fp32 [B, hw, C];
+    bboxes [B, Hb, Wb] uint8 or fp32 (full resolution).  Returns (out_mean fp32 [B, hw, C], grids or None)."""
+    n = len(src_fea_list)
+    assert tar_bbox.dtype in (torch.uint8, torch.float32)
+    assert all(bb.dtype == tar_bbox.dtype and bb.is_contiguous() for bb in src_bbox_list) and tar_bbox.is_contiguous()
+    d = L.CorrDesc()
+    d.B, d.n_src, d.C, d.h, d.w = B, n, Cch, h, w
+    d.bbox_h, d.bbox_w = tar_bbox.shape[-2], tar_bbox.shape[-1]
+    d.bbox_dtype = 0 if tar_bbox.dtype == torch.uint8 else 1
+    d.temperature, d.split, d.fmt = temperature, mode.split, mode.fmt
+    d.operand_scale = mode.corr_scale * mode.corr_scale
+    dev = tar_ops[0].device
+    out = torch.empty((B, h * w, Cch), dtype=torch.float32, device=dev)
+    grids = torch.empty((n, B, h, w, 2), dtype=torch.float32, device=dev) if want_grids else None
+    fea_ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in src_fea_list])
+    bb_ptrs = (C.c_void_p * n)(*[bb.data_ptr() for bb in src_bbox_list])
+    with _Prof(("corr_warp",)):
+        L.check(L.load().tsnet_corr_warp_fwd(C.byref(d), _ptr(tar_ops[0]), _ptr(tar_ops[1]), _ptr(src_ops[0]),
+                                             _ptr(src_ops[1]), fea_ptrs, _ptr(tar_bbox), bb_ptrs, _ptr(coord_table),
+                                             _ptr(out), _ptr(grids), None, 0, _stream()))
+    _count()
+    return out, grids
+
+
+def head_conv_tanh(act, weight, bias, fore=None, fill=None):
+    """act fp32 NHWC [B,H,W,Cin] -> NCHW [B,3,H,W] = tanh(conv7x7(reflectpad3(act))) (+ pose compositing)."""
+    B, H, W, Cin = act.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=act.device)
+    x0, x1 = fore if fore is not None else (0, 0)
+    fill_arr = (C.c_float * 3)(*(fill if fill is not None else (0.0, 0.0, 0.0)))
+    with _Prof(("head_conv_tanh",)):
+        L.check(L.load().tsnet_head_conv_tanh(_ptr(_f32(act)), B, H, W, Cin, _ptr(_f32(weight.detach())),
+                                              _ptr(_f32(bias.detach())), x0, x1, fill_arr, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def direct_conv_fp32(x_nhwc, weight, bias, stride=1, pad=0, reflect=False):
+    """Validation-only fp32 direct convolution (NHWC in / out)."""
+    B, H, W, Cin = x_nhwc.shape
+    Cout, _, K, _ = weight.shape
+    Ho, Wo = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x_nhwc.device)
+    L.check(L.load().tsnet_direct_conv_fp32(_ptr(_f32(x_nhwc)), B, H, W, Cin, _ptr(_f32(weight)), _ptr(bias), Cout, K,
+                                            stride, pad, int(reflect), _ptr(y), _stream()))
+    _count()
+    return y
