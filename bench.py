@@ -26,6 +26,13 @@ METRIC = "tsnet_forward_frames_per_sec_256x256_nsrc3"
 ALGO_BYTES_CORR_PER_FRAME = {1: 6299648, 3: 10502144, 5: 14704640, 8: 21008384}  # SURVEY.md section 8d / BASELINE.md section 3
 
 
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -78,14 +85,42 @@ def make_inputs(bs, label_nc, n_source, seed):
     return synth.dataset_like_inputs(bs, label_nc, n_source, seed=seed)
 
 
+def usable_cpus():
+    """CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_forward_fps(sds_np, label_nc, n_blocks, n_source, bs, steps, warmup):
-    """Reference algorithm (oracle port of model/TSNet.py:309-407) on the host cores; returns (frames/s, threads)."""
+    """Reference algorithm (oracle port of model/TSNet.py:309-407) on the host cores; returns (frames/s, threads).
+    The thread count is the best of a short ascending sweep up to all usable CPUs (a bs=1 forward on 128 threads is
+    60x SLOWER than on 16 on the GPU box -- oneDNN oversubscription -- and would be an unfairly weak baseline)."""
     from oracle import tsnet_oracle as O
-    torch.set_num_threads(os.cpu_count())
     inp = make_inputs(bs, label_nc, n_source, seed=4321)
     sds = O.to_torch_sd(sds_np)
+    ncpu = usable_cpus()
+    best_t, best_n = None, None
+    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(nt)
+        O.tsnet_forward(sds, inp, n_blocks)
+        t0 = time.perf_counter()
+        O.tsnet_forward(sds, inp, n_blocks)
+        dt = time.perf_counter() - t0
+        log(f"cpu baseline: {nt} threads -> {dt:.2f} s / forward (usable cpus {ncpu}, os.cpu_count {os.cpu_count()})")
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, nt
+        elif dt > 1.5 * best_t:
+            break
+    torch.set_num_threads(best_n)
     for _ in range(warmup):
         O.tsnet_forward(sds, inp, n_blocks)
+    log("cpu baseline: warm-up done")
     t0 = time.perf_counter()
     for _ in range(steps):
         O.tsnet_forward(sds, inp, n_blocks)
@@ -133,6 +168,7 @@ def run_b200(args):
         net = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, math_mode=args.math)
     D.broadcast_generator(net, src=0)
     net.eval()
+    log("model built")
 
     inp = make_inputs(bs, L, n, seed=1234 + rank)
     host = {k: ([torch.from_numpy(a).pin_memory() for a in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
@@ -140,6 +176,7 @@ def run_b200(args):
     devin = {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in host.items()}
     h2d = sum(t.numel() * t.element_size() for v in host.values() for t in (v if isinstance(v, list) else [v]))
     d2h = bs * 3 * 256 * 256 * 4
+    log("inputs staged")
 
     def step_resident():
         net.set_test_input(devin["src_img"], devin["src_lbl"], devin["src_bbox"], devin["tar_lbl"], devin["tar_bbox"])
@@ -179,11 +216,14 @@ def run_b200(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        log("warm-up done")
         ms, launches, prof = timed(step_resident, args.steps, profile=True)
+        log(f"timed region done: {ms / args.steps:.2f} ms/step")
         clocks = sampler.stop() if rank == 0 else None
         for _ in range(2):
             step_e2e()
         ms_e2e, _, _ = timed(step_e2e, args.steps)
+        log(f"e2e region done: {ms_e2e / args.steps:.2f} ms/step")
 
     frames = bs * world * args.steps
     value = frames / (ms * 1e-3)
@@ -255,7 +295,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")

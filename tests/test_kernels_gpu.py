@@ -67,7 +67,7 @@ def _conv_case(B, H, W, Cin, Cout, kind, mode_name, block_n=None, seed=0):
 ])
 def test_conv_gemm_vs_torch(B, H, W, Cin, Cout, kind, bn, mode):
     y, mr, ref = _conv_case(B, H, W, Cin, Cout, kind, mode, bn)
-    assert _relerr(y, ref) < CONV_TOL[mode] * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
+    assert _relerr(y, ref) < 2 * CONV_TOL[mode] * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
     if mode.endswith("x3"):
         assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
         assert _relerr(mr[..., 1], 1.0 / torch.sqrt(ref.var((1, 2), unbiased=False) + 1e-5)) < 5e-5
@@ -83,7 +83,7 @@ def test_conv_gemm_vs_torch(B, H, W, Cin, Cout, kind, bn, mode):
 ])
 def test_conv_gemm_network_shapes(B, H, W, Cin, Cout, kind, bn):
     y, mr, ref = _conv_case(B, H, W, Cin, Cout, kind, "fp16x3", bn)
-    assert _relerr(y, ref) < 4e-6 * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
+    assert _relerr(y, ref) < 8e-6 * max(1.0, Cin * (1 if kind == "1x1" else 9) / 1024)
     assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
 
 
@@ -165,7 +165,7 @@ def test_stem_taps_and_stem_conv(label_nc):
     assert float(got[..., 7 * cin:].abs().max()) == 0.0
     y, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)
     ref = F.conv2d(fp, w, b).permute(0, 2, 3, 1)
-    assert _relerr(y, ref) < 4e-6
+    assert _relerr(y, ref) < 4e-6 * max(1.0, pc.num_taps * pc.Cp / 1024)
 
 
 def test_l2norm_and_head():

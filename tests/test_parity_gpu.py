@@ -148,3 +148,29 @@ def test_fast_modes_run_and_are_flagged_non_parity():
         net.forward()
     err = float((net.rec_tar_img.cpu() - torch.from_numpy(gold["rec_tar_img"])).abs().max())
     assert np.isfinite(err) and err > IMG_TOL
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """the whole forward captured as one CUDA graph (the demos' one-frame-per-forward loop)."""
+    cfg, gold, inputs, net = _build("face_bs1_nb4")
+    with torch.no_grad():
+        _feed(net, inputs)
+        net.forward()
+        eager = net.rec_tar_img.clone()
+        eager_grids = torch.stack(net.warp_grid2d_list).clone()
+        net.enable_cuda_graph(True)
+        for _ in range(3):  # capture, then two replays with freshly staged inputs
+            _feed(net, inputs)
+            net.forward()
+            assert torch.equal(net.rec_tar_img, eager)
+            assert torch.equal(torch.stack(net.warp_grid2d_list), eager_grids)
+        # different input content through the same graph
+        inputs2 = {k: ([a[::-1].copy() if a.ndim == 3 else a[..., ::-1].copy() for a in v] if isinstance(v, list)
+                       else v[..., ::-1].copy()) for k, v in inputs.items()}
+        _feed(net, inputs2)
+        net.forward()
+        g_out = net.rec_tar_img.clone()
+        net.enable_cuda_graph(False)
+        _feed(net, inputs2)
+        net.forward()
+        assert torch.equal(net.rec_tar_img, g_out)

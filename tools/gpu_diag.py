@@ -275,9 +275,9 @@ def stage_e2e():
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in STAGES:
-        ok = globals()["stage_" + sys.argv[1]]()
-        print(f"STAGE {sys.argv[1]}: {'PASS' if ok else 'FAIL'}", flush=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--stage":
+        ok = globals()["stage_" + sys.argv[2]]()
+        print(f"STAGE {sys.argv[2]}: {'PASS' if ok else 'FAIL'}", flush=True)
         sys.exit(0 if ok else 1)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "w")
@@ -285,7 +285,7 @@ def main():
     for st in stages:
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), st], capture_output=True, text=True,
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", st], capture_output=True, text=True,
                                timeout=600, cwd=ROOT)
             out = p.stdout + ("\n[stderr]\n" + p.stderr[-6000:] if p.returncode != 0 else "")
             rc = p.returncode

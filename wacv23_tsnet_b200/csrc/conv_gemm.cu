@@ -11,8 +11,14 @@
 //   D += Ahi*Bhi ; D += Ahi*Blo ; D += Alo*Bhi      (fp32 accumulation in TMEM).
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM -> registers -> bias -> global store + InstanceNorm partial statistics).
-// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// warps 4-11 = accumulate + epilogue.
+//
+// Accumulation precision: tcgen05.mma adds into the fp32 TMEM accumulator with truncation, and the error grows
+// linearly with the number of accumulating instructions (measured: 2e-5 relative at K = 4608).  The K loop is
+// therefore cut into chunks of `chunk_kb` K-blocks; each chunk accumulates from zero into one of two TMEM
+// buffers, and the 8 accumulate warps add the finished chunk into fp32 REGISTER accumulators with round-to-nearest
+// (each thread owns one output pixel x BLOCK_N/2 channels).  The MMA pipe runs ahead by one chunk.  At the end of
+// the tile the same warps apply scale + bias, store the row, and produce the InstanceNorm partial statistics.
 #include "sm100_prims.cuh"
 #include "host_util.h"
 #include "../../include/tsnet_b200.h"
@@ -24,7 +30,8 @@ namespace tsnet {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 x 16-bit = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 accumulate/epilogue warps
+constexpr int kAccWarps = 8;
 constexpr int kSmemBudget = 200 * 1024;
 
 struct alignas(64) ConvGemmArgs {
@@ -34,7 +41,7 @@ struct alignas(64) ConvGemmArgs {
   float* stats;
   float out_scale;
   int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
-  int Cout, num_taps, kc_per_tap, planes, split, fmt;
+  int Cout, num_taps, kc_per_tap, planes, split, fmt, chunk_kb;
   int8_t tap_dy[TSNET_MAX_TAPS + 7], tap_dx[TSNET_MAX_TAPS + 7], tap_plane[TSNET_MAX_TAPS + 7];
 };
 
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], kAccWarps);  // one arrive per accumulate warp
     }
     fence_barrier_init();
   }
@@ -104,6 +111,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane_id() == 0) {
@@ -146,82 +155,104 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, args.fmt);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+      int cc = 0;  // global chunk counter -> TMEM buffer + phase
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
+          const int buf = cc & 1;
+          const uint32_t buf_phase = (cc >> 1) & 1;
+          mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t a_hi = make_desc_kmajor_sw128(st);
-          const uint64_t a_lo = make_desc_kmajor_sw128(st + Cfg::kABytes);
-          const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes);
-          const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+          const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+          const int kb1 = min(num_kb, kb0 + args.chunk_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint64_t a_hi = make_desc_kmajor_sw128(st);
+            const uint64_t a_lo = make_desc_kmajor_sw128(st + Cfg::kABytes);
+            const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes);
+            const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint32_t off = k * kUmmaK * 2;
-            umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, (kb | k) != 0);
-            if (args.split) {
-              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-              umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint32_t off = k * kUmmaK * 2;
+              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+              if (args.split) {
+                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+              }
             }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          umma_commit(&tmem_full[buf]);
         }
-        umma_commit(&tmem_full[acc]);
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== accumulate + epilogue =====================
+    constexpr int NC = BLOCK_N / 2;     // columns owned by one thread
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;   // which half of the BLOCK_N columns
     const int row = q * 32 + lane_id();
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    int cc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / args.num_n_tiles;
       const int n_tile = tile - m_tile * args.num_n_tiles;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      float acc[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
+        const int buf = cc & 1;
+        const uint32_t buf_phase = (cc >> 1) & 1;
+        mbar_wait(&tmem_full[buf], buf_phase);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * NC;
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(t0 + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += v[j];  // fp32 round-to-nearest promotion
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+      // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
       float* yrow = args.y + gm * args.Cout;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        const int n0 = n_tile * BLOCK_N + c0;
-        if (n0 >= args.Cout) break;  // padded output channels (warp-uniform)
-        float v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        const int n0 = n_tile * BLOCK_N + half * NC + c0;
+        if (n0 < args.Cout) {  // padded output channels are skipped (warp-uniform)
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (srow) {
-          // per-column (sum, centred M2) over this warp's 32 pixels
-          float t[32];
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(acc[c0 + j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) t[j] = v[j];
-          const float colsum = warp_col_sums(t);  // lane j: sum of column j
-          const float mean_l = colsum * (1.f / 32.f);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (srow) {
+            // per-column (sum, centred M2) over this warp's 32 pixels
+            float t[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float mj = __shfl_sync(0xffffffffu, mean_l, j);
-            const float dlt = v[j] - mj;
-            t[j] = dlt * dlt;
+            for (int j = 0; j < 32; ++j) t[j] = v[j];
+            const float colsum = warp_col_sums(t);  // lane j: sum of column j
+            const float mean_l = colsum * (1.f / 32.f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float mj = __shfl_sync(0xffffffffu, mean_l, j);
+              const float dlt = v[j] - mj;
+              t[j] = dlt * dlt;
+            }
+            const float m2 = warp_col_sums(t);
+            *reinterpret_cast<float2*>(srow + (n0 + lane_id()) * 2) = make_float2(colsum, m2);
           }
-          const float m2 = warp_col_sums(t);
-          *reinterpret_cast<float2*>(srow + (n0 + lane_id()) * 2) = make_float2(colsum, m2);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
 
@@ -309,6 +340,7 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   a.planes = d->planes;
   a.split = d->split;
   a.fmt = d->fmt;
+  a.chunk_kb = d->split ? 2 : 6;  // <= 24 accumulating MMAs per TMEM chunk before promotion to registers
   for (int t = 0; t < d->num_taps; ++t) {
     a.tap_dy[t] = d->tap_dy[t];
     a.tap_dx[t] = d->tap_dx[t];

@@ -1,10 +1,12 @@
 // Fused mask-aware correlation -> softmax(100 x) -> expected source coordinate -> bilinear warp -> mean over sources.
 // (model/TSNet.py:319-366, :392 of the reference.)  The hw x hw similarity matrix lives only in TMEM.
 //
-// Work item = (sample b, tile of 128 target positions).  For every source i and every chunk of 256 source
-// positions the tensor cores compute S = T_hat[128 x C] . S_hat_i[256 x C]^T into one of two TMEM accumulators
-// (3-term hi/lo split, fp32 accumulate) while the four epilogue warps run an online softmax with a 2-channel
-// "V" (the source coordinates) over the previous chunk: one thread owns one target row.
+// Work item = (sample b, tile of 128 target positions).  For every source i and every chunk of 128 source
+// positions the tensor cores compute S = T_hat[128 x C] . S_hat_i[128 x C]^T (3-term hi/lo split).  As in the
+// conv GEMM, tcgen05's truncating fp32 accumulation is kept short: every 2 K-blocks (24 MMAs) the partial sum in
+// one of two TMEM buffers is promoted to fp32 REGISTER accumulators of the four softmax warps (one thread owns
+// one target row x 128 columns).  When a chunk is complete the same threads run an online softmax with a
+// 2-channel "V" (the source coordinates) over it, overlapping the tensor-core work on the next chunk.
 // After the last source the epilogue warps gather the 4 bilinear taps per (row, source) from the
 // UN-normalised fp32 source features and write the source mean.
 //
@@ -19,18 +21,19 @@
 namespace tsnet {
 
 constexpr int kCorrM = 128;      // target rows per work item
-constexpr int kCorrN = 256;      // source columns per accumulator
+constexpr int kCorrN = 128;      // source columns per accumulator chunk
+constexpr int kCorrChunkKb = 2;  // K-blocks accumulated in TMEM before promotion to registers
 constexpr int kCorrK = 64;       // K block (one 128 B swizzle row)
 constexpr int kCorrThreads = 256;
 constexpr int kCorrMaxSrc = 16;
 constexpr int kCorrABytes = kCorrM * kCorrK * 2;  // 16 KB
-constexpr int kCorrBBytes = kCorrN * kCorrK * 2;  // 32 KB
-constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 96 KB
-constexpr int kCorrStages = 2;
+constexpr int kCorrBBytes = kCorrN * kCorrK * 2;  // 16 KB
+constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 64 KB
+constexpr int kCorrStages = 3;
 constexpr int kCorrMaxHW = 2048;
 
 struct alignas(64) CorrArgs {
-  CUtensorMap t_hi, t_lo, s_hi, s_lo;  // [B*hw, C] and [n_src*B*hw, C], box {64, 128} / {64, 256}
+  CUtensorMap t_hi, t_lo, s_hi, s_lo;  // [B*hw, C] and [n_src*B*hw, C], boxes {64, 128}
   const float* src_fea[kCorrMaxSrc];
   const void* src_bbox[kCorrMaxSrc];
   const void* tar_bbox;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, 2 * kCorrN);
+  if (warp == 2) tmem_alloc(tmem_base_smem, 2 * kCorrN);  // two partial-sum buffers
   for (int i = threadIdx.x; i < args.w; i += blockDim.x) s_cx[i] = args.coord_table[args.h + i];
   for (int i = threadIdx.x; i < args.h; i += blockDim.x) s_cy[i] = args.coord_table[i];
   tc_fence_before();
@@ -135,35 +138,38 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
       const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;  // accumulator use counter
+      int cc = 0;  // partial-accumulator counter -> TMEM buffer + phase
       for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
-        for (int ic = 0; ic < args.n_src * chunks; ++ic, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * kCorrN;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+        for (int ic = 0; ic < args.n_src * chunks; ++ic) {
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kCorrChunkKb, ++cc) {
+            const int buf = cc & 1;
+            const uint32_t buf_phase = (cc >> 1) & 1;
+            mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
             tc_fence_after();
-            const uint32_t st = smem_u32(smem + stage * kCorrStageBytes);
-            const uint64_t a_hi = make_desc_kmajor_sw128(st);
-            const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
-            const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
-            const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
+            const uint32_t d_tmem = tmem_base + buf * kCorrN;
+            const int kb1 = min(num_kb, kb0 + kCorrChunkKb);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t st = smem_u32(smem + stage * kCorrStageBytes);
+              const uint64_t a_hi = make_desc_kmajor_sw128(st);
+              const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
+              const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
+              const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
 #pragma unroll
-            for (int k = 0; k < kCorrK / 16; ++k) {
-              const uint32_t off = k * 32;
-              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, (kb | k) != 0);
-              if (args.split) {
-                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+              for (int k = 0; k < kCorrK / 16; ++k) {
+                const uint32_t off = k * 32;
+                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                if (args.split) {
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                  umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                }
               }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
+            umma_commit(&tmem_full[buf]);
           }
-          umma_commit(&tmem_full[acc]);
         }
       }
     }
@@ -185,15 +191,30 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
           s_mask[p] = read_mask(args.src_bbox[i], args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, p);
         epi_bar_sync();
         float run_max = -INFINITY, run_sum = 0.f, gx = 0.f, gy = 0.f;
-        for (int ch = 0; ch < chunks; ++ch, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (it >> 1) & 1;
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after();
-#pragma unroll 1
+        for (int ch = 0; ch < chunks; ++ch) {
+          // ---- promote the partial sums of this 128-column chunk into registers
+          float acc[kCorrN];
+#pragma unroll
+          for (int j = 0; j < kCorrN; ++j) acc[j] = 0.f;
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kCorrChunkKb, ++it) {
+            const int buf = it & 1;
+            const uint32_t buf_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[buf], buf_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < kCorrN; c0 += 32) {
+              float v[32];
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrN + c0, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[c0 + j] += v[j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&tmem_empty[buf]);
+          }
+          // ---- online softmax with the source coordinates as V
+#pragma unroll
           for (int c0 = 0; c0 < kCorrN; c0 += 32) {
-            float v[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kCorrN + c0, v);
             const int s0 = ch * kCorrN + c0;
             float gmax = -INFINITY;
 #pragma unroll
@@ -201,8 +222,8 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
               const float m_s = s_mask[s0 + j];
               // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)); exact for binary masks
               const float wgt = m_t * m_s + (1.f - m_t) * (1.f - m_s);
-              v[j] = args.temperature * ((v[j] * args.inv_operand_scale) * wgt);
-              gmax = fmaxf(gmax, v[j]);
+              acc[c0 + j] = args.temperature * ((acc[c0 + j] * args.inv_operand_scale) * wgt);
+              gmax = fmaxf(gmax, acc[c0 + j]);
             }
             const float new_max = fmaxf(run_max, gmax);
             const float corr = exp2f((run_max - new_max) * kLog2e);  // exp2f(-inf) = 0 on the first group
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
             const float mb = new_max * kLog2e;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float p = exp2f(fmaf(v[j], kLog2e, -mb));
+              const float p = exp2f(fmaf(acc[c0 + j], kLog2e, -mb));
               const int s = s0 + j;
               const int sy = s / args.w, sx = s - sy * args.w;
               run_sum += p;
@@ -219,9 +240,6 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
               gy = fmaf(p, s_cy[sy], gy);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
         }
         const float2 g = make_float2(gx / run_sum, gy / run_sum);
         s_grid[i * kCorrM + row] = g;
@@ -312,7 +330,7 @@ extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar
   TSNET_ARG_CHECK(!d->split || (tar_lo && src_lo), "corr_warp: split mode needs the lo operands");
   TSNET_ARG_CHECK(d->n_src >= 1 && d->n_src <= kCorrMaxSrc, "corr_warp: n_src %d (max %d)", d->n_src, kCorrMaxSrc);
   const int hw = d->h * d->w;
-  TSNET_ARG_CHECK(hw % kCorrN == 0 && hw <= kCorrMaxHW, "corr_warp: h*w = %d must be a multiple of 256, <= %d", hw,
+  TSNET_ARG_CHECK(hw % kCorrM == 0 && hw <= kCorrMaxHW, "corr_warp: h*w = %d must be a multiple of 128, <= %d", hw,
                   kCorrMaxHW);
   TSNET_ARG_CHECK(d->h <= 128 && d->w <= 128, "corr_warp: h, w <= 128");
   TSNET_ARG_CHECK(d->C % 128 == 0 && d->C <= 1024, "corr_warp: C %d must be a multiple of 128, <= 1024", d->C);

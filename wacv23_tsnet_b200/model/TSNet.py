@@ -90,7 +90,7 @@ class TSNet(nn.Module):
                  is_train=True, getIntermFeat=True, label_nc=5,
                  debug=False, lambda_dec=1.0,
                  addcoords=True,
-                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3"):
+                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False):
         super().__init__()
         if is_train:
             raise NotImplementedError(_TRAIN_MSG)
@@ -115,6 +115,8 @@ class TSNet(nn.Module):
         self._engine = ForwardEngine(self.img_enc, self.lbl_enc, self.fuse_net, self.dec, label_nc, n_blocks,
                                      n_downsampling=n_downsampling, ngf=ngf, math_mode=math_mode)
         self._pose_fill = None
+        self._use_graph = bool(cuda_graph)
+        self._graphs = {}
         self._src_img_raw, self._src_img_div = None, None
         self.src_lbl_list = None
         self.src_bbox_list = None
@@ -183,13 +185,62 @@ class TSNet(nn.Module):
         return torch.stack([gx, gy], -1).repeat(b, 1, 1, 1).float()
 
     # ---- the hot path -------------------------------------------------------------------------------------------
-    def forward(self, _collect=None):
+    def enable_cuda_graph(self, flag=True):
+        """Replay the whole forward (~250 kernel launches) as one CUDA graph per input signature.  Worth it at the
+        demos' operating point (one frame per forward, demo/demo_face.py:185-192) where eager launches dominate."""
+        self._use_graph = bool(flag)
+        if not flag:
+            self._graphs.clear()
+
+    def _staged(self):
         n = self.n_source
         bbox_dt = self.tar_bbox.dtype
         src_bb = [bb.squeeze(1) if bb.dtype == bbox_dt else bb.squeeze(1).to(bbox_dt) for bb in self.src_bbox_list[:n]]
-        rec, grids = self._engine.forward(self._src_img_raw[:n], self._src_img_div[:n], self.src_lbl_list[:n], src_bb,
-                                          self.tar_lbl, self.tar_bbox.squeeze(1), return_flow=self.return_flow,
-                                          pose_fill=self._pose_fill, collect=_collect)
+        return (list(self._src_img_raw[:n]), list(self._src_img_div[:n]), list(self.src_lbl_list[:n]), src_bb,
+                self.tar_lbl, self.tar_bbox.squeeze(1))
+
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for net in (self.img_enc, self.lbl_enc, self.fuse_net, self.dec)
+                     for p in net.parameters())
+
+    def _forward_graph(self, imgs, divs, lbls, bbs, tar_lbl, tar_bbox):
+        key = (tuple(tar_lbl.shape), len(imgs), tuple(divs), tar_bbox.dtype, self.return_flow, self._param_signature())
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs.clear()  # one live graph: its private pool holds every workspace of the forward
+            static = dict(imgs=[t.clone() for t in imgs], lbls=[t.clone() for t in lbls], bbs=[t.clone() for t in bbs],
+                          tar_lbl=tar_lbl.clone(), tar_bbox=tar_bbox.clone())
+
+            def run():
+                return self._engine.forward(static["imgs"], divs, static["lbls"], static["bbs"], static["tar_lbl"],
+                                            static["tar_bbox"], return_flow=self.return_flow,
+                                            pose_fill=self._pose_fill)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run()  # eager warm-up: packs the weights (needs host syncs that capture forbids)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            entry = (graph, static, out)
+            self._graphs[key] = entry
+        graph, static, out = entry
+        for dst, src in zip(static["imgs"] + static["lbls"] + static["bbs"] + [static["tar_lbl"], static["tar_bbox"]],
+                            list(imgs) + list(lbls) + list(bbs) + [tar_lbl, tar_bbox]):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        rec, grids = out
+        return rec.clone(), (None if grids is None else [g.clone() for g in grids])
+
+    def forward(self, _collect=None):
+        imgs, divs, lbls, bbs, tar_lbl, tar_bbox = self._staged()
+        if self._use_graph and _collect is None:
+            with torch.no_grad():
+                rec, grids = self._forward_graph(imgs, divs, lbls, bbs, tar_lbl, tar_bbox)
+        else:
+            rec, grids = self._engine.forward(imgs, divs, lbls, bbs, tar_lbl, tar_bbox, return_flow=self.return_flow,
+                                              pose_fill=self._pose_fill, collect=_collect)
         self.rec_tar_img = rec
         if self.return_flow:
             self.warp_grid2d_list = grids
