@@ -39,13 +39,14 @@ def nearest_downsample_mask(bbox, h, w):
 def linspace_table(n):
     """torch.linspace(-1, 1, n) of model/TSNet.py:301-302, restated.
 
-    ATen builds it symmetrically: start + k*step for k < n/2, end - (n-1-k)*step otherwise
-    (the naive formula is off by one ulp).
+    ATen (CPU) builds it symmetrically with fused multiply-adds: fma(step, k, start) for k < n/2 and
+    fma(-step, n-1-k, end) otherwise, step = fl32(2/(n-1)) -- the naive start + k*step is off by one ulp
+    (SURVEY.md section 7.3-3b).  The fma is emulated exactly: the product of two fp32 values is exact in fp64.
     """
-    step = np.float32((1.0 - (-1.0)) / (n - 1))
-    k = np.arange(n, dtype=np.float32)
-    lo = np.float32(-1.0) + step * k
-    hi = np.float32(1.0) - step * (np.float32(n - 1) - k)
+    step = np.float64(np.float32(2.0) / np.float32(n - 1))
+    k = np.arange(n, dtype=np.float64)
+    lo = (-1.0 + step * k).astype(np.float32)
+    hi = (1.0 - step * (float(n - 1) - k)).astype(np.float32)
     return np.where(np.arange(n) < n // 2, lo, hi).astype(np.float32)
 
 
@@ -134,13 +135,18 @@ def corr_warp(tar_fea, src_fea_list, tar_bbox, src_bbox_list, temperature=100.0)
     grids [B,h,w,2]).  Follows the reference op by op (two masked bmm, add, softmax, matmul).
     """
     b, c, h, w = tar_fea.shape
+    dt = tar_fea.dtype  # fp32 = the reference; tests also evaluate this in fp64 as the "truth"
     t = F.normalize(tar_fea, p=2, dim=1).view(b, c, h * w).transpose(1, 2)
     mt = torch.from_numpy(nearest_downsample_mask(tar_bbox.numpy(), h, w)).view(b, 1, h * w).transpose(1, 2)
-    grid2d = get_grid(b, h, w).view(b, h * w, 2)
+    grid2d = get_grid(b, h, w).view(b, h * w, 2).to(dt)
+    if dt == torch.float64:
+        mt = mt.to(dt)
     warped, grids = [], []
     for src_fea, src_bbox in zip(src_fea_list, src_bbox_list):
         s = F.normalize(src_fea, p=2, dim=1).view(b, c, h * w)
         ms = torch.from_numpy(nearest_downsample_mask(src_bbox.numpy(), h, w)).view(b, 1, h * w)
+        if dt == torch.float64:
+            ms = ms.to(dt)
         a = torch.bmm(t * mt, s * ms) + torch.bmm(t * (1.0 - mt), s * (1.0 - ms))
         p = F.softmax(temperature * a, dim=2)
         g = torch.matmul(p, grid2d).view(b, h, w, 2)

@@ -29,7 +29,7 @@ def test_nearest_mask_is_bit_exact(h, w, H, W, dtype):
         assert torch.equal(ref, bbox[:, :, ::8, ::8])  # the integer fact the kernel relies on
 
 
-@pytest.mark.parametrize("n", [2, 7, 32, 33, 64])
+@pytest.mark.parametrize("n", [2, 7, 16, 31, 32, 33, 64, 100, 256])
 def test_linspace_table_is_bit_exact(n):
     assert torch.equal(torch.from_numpy(O.linspace_table(n)), torch.linspace(-1, 1, n))
 

@@ -12,10 +12,11 @@ pytestmark = pytest.mark.gpu
 # Stated tolerances (DESIGN.md "precision"): the reference CPU fp32 forward itself sits 3e-4..5e-4 (image) and
 # 1.5e-5 (grids) away from an fp64 evaluation of the same network -- random-init weights + softmax(100 x) amplify
 # rounding noise by ~1e3.  We require agreement with the reference within IMG_TOL / GRID_TOL below.
-IMG_TOL = 6e-3      # max-abs on rec_tar_img, tanh range (-1, 1)
-GRID_TOL = 3e-4     # max-abs on warp grids, [-1, 1] units (= 5e-3 feature pixels)
-FEA_TOL = 1e-4      # encoder features, relative to max|ref|
-MIX_TOL = 4e-3      # pg_mean / sg_mean, relative to max|ref|
+# Measured on B200 (fp16x3): image 3.7e-4 .. 5.8e-4, grids 1.8e-5, features 2.9e-6 rel, pg_mean 2.4e-4 rel.
+IMG_TOL = 2e-3      # max-abs on rec_tar_img, tanh range (-1, 1): 4x the reference's fp32-vs-fp64 noise
+GRID_TOL = 1e-4     # max-abs on warp grids, [-1, 1] units (= 1.6e-3 feature pixels)
+FEA_TOL = 2e-5      # encoder features, relative to max|ref|
+MIX_TOL = 1e-3      # pg_mean / sg_mean, relative to max|ref|
 
 
 def _build(name, math_mode="fp16x3"):

@@ -28,9 +28,11 @@ class TSNet(_face.TSNet):
         self.model_names = ['G', 'D', 'DF']
         self.use_mask = use_mask
         if self.use_mask:
-            # same arithmetic as the reference: fp32 (-mean) / 255.0
-            self.mask_img = torch.from_numpy(-np.asarray(mean, dtype=np.float32)).view(1, 3, 1, 1) \
-                .repeat(1, 1, 256, 256).cuda() / 255.0
+            # same arithmetic as the reference's fp32 (-mean) / 255.0, evaluated on the host: ATen's CUDA kernel for
+            # tensor / python-scalar multiplies by the reciprocal (1 ulp off a true division), and the parity gate
+            # is the reference's CPU forward.
+            self.mask_img = (torch.from_numpy(-np.asarray(mean, dtype=np.float32)).view(1, 3, 1, 1)
+                             .repeat(1, 1, 256, 256) / 255.0).cuda()
             fore_mask = torch.zeros((256, 256), dtype=torch.float32)
             fore_mask[:, 64:192] = 1
             self.fore_mask = fore_mask.view(1, 1, 256, 256).cuda()
