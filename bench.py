@@ -33,6 +33,12 @@ def log(msg):
     print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+def load_traffic():
+    """DRAM bytes per launch from the committed ncu captures (profiles/traffic.json); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.isfile(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -247,8 +253,11 @@ def run_b200(args):
         flops = 2.0 * X * Hh * Ww * Cout * taps * Cin_eff  # algorithmic fp32-conv flops of one launch
         ach = flops / (t / c * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
+        traffic = load_traffic()
+        conv_traffic = traffic.get("conv_gemm_512x512_3x3_x96") if (kind, X, Hh, Cin_eff, Cout) == ("3x3", 96, 32, 512, 512) else None
         roof = {"kernel": f"conv_gemm {kind} {Cin_eff}->{Cout} @{Hh}x{Ww} x{X} samples", "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": conv_traffic,
+                "algorithmic_flops_per_launch": flops,
                 "peak_source": peaks["source"] + ", bf16 sustained",
                 "note": "fp32-faithful mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi): "
                         "frac <= 0.333 by construction; tensor-pipe utilisation = 3 x frac" if net._engine.mode.split
@@ -259,7 +268,8 @@ def run_b200(args):
             byts = ALGO_BYTES_CORR_PER_FRAME.get(n, 4 * 512 * 1024 * (n + 2) + 4 * 1024 * (n + 1)) * bs
             ach = byts / (t / c * 1e-3) / 1e9
             roof_corr = {"kernel": "corr_warp (fused correlation+softmax+warp+mean)", "bound": "hbm", "achieved": ach,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                         "traffic": traffic.get("corr_warp_b32_n3") if (bs, n) == (32, 3) else None,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_launch": byts}
 
     line = None

@@ -175,3 +175,48 @@ def test_cuda_graph_replay_is_bit_identical_to_eager():
         _feed(net, inputs2)
         net.forward()
         assert torch.equal(net.rec_tar_img, g_out)
+
+
+_SHARD_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from oracle import synth
+from wacv23_tsnet_b200 import dist as D
+from wacv23_tsnet_b200.model.TSNet import TSNet
+rank, local, world = D.init_from_env("nccl")
+torch.cuda.set_device(local)
+torch.manual_seed(100 + rank)                      # different initial weights per rank: the broadcast must fix that
+net = TSNet(is_train=False, label_nc=2, n_blocks=1, n_downsampling=3, n_source=2)
+D.broadcast_generator(net, src=0)
+net.eval()
+inp = synth.dataset_like_inputs(4 * world, 2, 2, seed=11)   # the GLOBAL batch, identical on every rank
+t = lambda a: torch.from_numpy(a)
+full = dict(src_img=[t(a) for a in inp["src_img"]], src_lbl=[t(a) for a in inp["src_lbl"]],
+            src_bbox=[t(a) for a in inp["src_bbox"]], tar_lbl=t(inp["tar_lbl"]), tar_bbox=t(inp["tar_bbox"]))
+mine = D.shard_inputs(full, rank, world)
+with torch.no_grad():
+    net.set_test_input(mine["src_img"], mine["src_lbl"], mine["src_bbox"], mine["tar_lbl"], mine["tar_bbox"])
+    net.forward()
+    gathered = D.all_gather_frames(net.rec_tar_img)          # [4*world, 3, 256, 256], rank-major
+    net.set_test_input(full["src_img"], full["src_lbl"], full["src_bbox"], full["tar_lbl"], full["tar_bbox"])
+    net.forward()                                             # the whole batch on ONE GPU
+assert torch.equal(gathered, net.rec_tar_img), "sharded forward differs from the single-GPU forward"
+sys.stdout.write("rank%dok\n" % rank); sys.stdout.flush()
+torch.distributed.destroy_process_group()
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_batch_shards_equal_single_gpu(tmp_path):
+    """rank r owns rows [r*B/R, (r+1)*B/R); NCCL only broadcasts the weights and gathers the frames.
+    The gathered sharded output must be BIT-identical to the same global batch run on one GPU."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER.format(root=root))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "rank0ok" in r.stdout and "rank1ok" in r.stdout

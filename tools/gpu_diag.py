@@ -215,6 +215,7 @@ def stage_corr():
             tb = torch.randint(0, 2, (B, 1, 256, 256), generator=g).float()
             sbs = [torch.randint(0, 2, (B, 1, 256, 256), generator=g).float() for _ in range(n)]
         ref_mean, ref_grids = O.corr_warp(tar, srcs, tb, sbs)
+        tru_mean, tru_grids = O.corr_warp(tar.double(), [s.double() for s in srcs], tb, sbs)
         tar_d = tar.permute(0, 2, 3, 1).contiguous().to(dev)
         src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).to(dev)  # [n,B,h,w,C]
         tar_ops = ops.l2norm_split(tar_d.view(B, 1024, 512), m)
@@ -225,7 +226,10 @@ def stage_corr():
                                    coord, B, 512, 32, 32, m, want_grids=True)
         torch.cuda.synchronize()
         gerr = max((grids[i].cpu() - ref_grids[i]).abs().max().item() for i in range(n))
-        print(f"  corr B{B} n{n} rect{rect} {mode}: grid max|err| {gerr:.3e}", flush=True)
+        kerr = max((grids[i].cpu().double() - tru_grids[i]).abs().max().item() for i in range(n))
+        rerr = max((ref_grids[i].double() - tru_grids[i]).abs().max().item() for i in range(n))
+        print(f"  corr B{B} n{n} rect{rect} {mode}: grid max|err| vs fp32 oracle {gerr:.3e}; vs fp64 truth: kernel {kerr:.3e}, "
+              f"fp32 oracle {rerr:.3e}", flush=True)
         ok &= gerr < (2e-5 if mode == "fp16x3" else 5e-4)
         ok &= _report(f"corr B{B} n{n} {mode} warped mean", out.view(B, 32, 32, 512).permute(0, 3, 1, 2).cpu(), ref_mean,
                       1e-4 if mode == "fp16x3" else 3e-3)

@@ -9,7 +9,7 @@ BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 140 --csv \
     --log-file $OUT/launches_$TAG.csv $BENCH > /dev/null 2>&1
 # 2. the dominant kernel: conv_gemm<256> on the 512->512 3x3 layer of img_enc (96 samples)
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel.*256 -s 40 -c 1 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 50 -c 1 \
     -f -o $OUT/prof_conv_$TAG $BENCH > /dev/null 2>&1
 # 3. the fused correlation + warp kernel
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:corr_warp -s 1 -c 1 \

@@ -1,39 +1,40 @@
 // Fused mask-aware correlation -> softmax(100 x) -> expected source coordinate -> bilinear warp -> mean over sources.
 // (model/TSNet.py:319-366, :392 of the reference.)  The hw x hw similarity matrix lives only in TMEM.
 //
-// Work item = (sample b, tile of 128 target positions).  For every source i and every chunk of 128 source
-// positions the tensor cores compute S = T_hat[128 x C] . S_hat_i[128 x C]^T (3-term hi/lo split).  As in the
-// conv GEMM, tcgen05's truncating fp32 accumulation is kept short: every 2 K-blocks (24 MMAs) the partial sum in
-// one of two TMEM buffers is promoted to fp32 REGISTER accumulators of the four softmax warps (one thread owns
-// one target row x 128 columns).  When a chunk is complete the same threads run an online softmax with a
-// 2-channel "V" (the source coordinates) over it, overlapping the tensor-core work on the next chunk.
-// After the last source the epilogue warps gather the 4 bilinear taps per (row, source) from the
-// UN-normalised fp32 source features and write the source mean.
+// Work item = (sample b, tile of 128 target positions).  For every source i and every chunk of 256 source
+// positions the tensor cores compute S = T_hat[128 x C] . S_hat_i[256 x C]^T (3-term hi/lo split).  As in the
+// conv GEMM, tcgen05's truncating fp32 accumulation is kept short: after every K-block (12 MMAs) the partial sum in
+// one of two TMEM buffers is promoted to fp32 REGISTER accumulators of the eight softmax warps (one thread owns
+// one target row x 128 of the 256 columns).  When a chunk is complete the same threads run an online softmax with a
+// 2-channel "V" (the source coordinates) over it while the tensor cores work on the next chunk; the two column
+// halves of a row are merged through shared memory at the end of each source.
+// After the last source the eight warps gather the 4 bilinear taps per (row, source) from the UN-normalised fp32
+// source features and write the source mean.
 //
-// warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = softmax + gather.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = softmax + gather.
 #include "sm100_prims.cuh"
 #include "host_util.h"
 #include "../../include/tsnet_b200.h"
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <math.h>
 
 namespace tsnet {
 
-constexpr int kCorrM = 128;      // target rows per work item
-constexpr int kCorrN = 128;      // source columns per accumulator chunk
-constexpr int kCorrChunkKb = 2;  // K-blocks accumulated in TMEM before promotion to registers
-constexpr int kCorrK = 64;       // K block (one 128 B swizzle row)
-constexpr int kCorrThreads = 256;
-constexpr int kCorrMaxSrc = 16;
-constexpr int kCorrABytes = kCorrM * kCorrK * 2;  // 16 KB
-constexpr int kCorrBBytes = kCorrN * kCorrK * 2;  // 16 KB
-constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 64 KB
-constexpr int kCorrStages = 3;
-constexpr int kCorrMaxHW = 2048;
+constexpr int kCorrM = 128;       // target rows per work item
+constexpr int kCorrN = 256;       // source columns per chunk
+constexpr int kCorrNC = 128;      // columns owned by one thread
+constexpr int kCorrK = 64;        // K block (one 128 B swizzle row)
+constexpr int kCorrChunkKb = 1;   // K-blocks (12 MMAs) accumulated in TMEM before promotion to registers
+constexpr int kCorrThreads = 384;
+constexpr int kCorrEpiThreads = 256;
+constexpr int kCorrMaxSrc = 12;
+constexpr int kCorrMaxHW = 1024;
+constexpr int kCorrABytes = kCorrM * kCorrK * 2;                    // 16 KB
+constexpr int kCorrBBytes = kCorrN * kCorrK * 2;                    // 32 KB
+constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 96 KB
+constexpr int kCorrStages = 2;
 
 struct alignas(64) CorrArgs {
-  CUtensorMap t_hi, t_lo, s_hi, s_lo;  // [B*hw, C] and [n_src*B*hw, C], boxes {64, 128}
+  CUtensorMap t_hi, t_lo, s_hi, s_lo;  // [B*hw, C] box {64, 128} and [n_src*B*hw, C] box {64, 256}
   const float* src_fea[kCorrMaxSrc];
   const void* src_bbox[kCorrMaxSrc];
   const void* tar_bbox;
@@ -43,7 +44,18 @@ struct alignas(64) CorrArgs {
   int B, n_src, C, h, w, hw, tiles_per_img, num_items;
   int bbox_h, bbox_w, bbox_dtype;
   int split, fmt;
-  float temperature, inv_operand_scale;
+  float logit_scale;  // temperature / operand_scale
+};
+
+struct CorrSmemTail {
+  uint64_t full_bar[kCorrStages], empty_bar[kCorrStages], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad[15];
+  float mask[kCorrMaxHW];            // nearest-down-sampled source mask of the current source
+  float cx[kCorrMaxHW];              // x coordinate of source position s
+  float cy[kCorrMaxHW];              // y coordinate of source position s
+  float2 grid[kCorrMaxSrc][kCorrM];  // expected coordinate per (source, row)
+  float4 merge[kCorrM];              // softmax state of the upper column half
 };
 
 __device__ __forceinline__ float read_mask(const void* bbox, int dtype, int b, int bh, int bw, int h, int w, int pos) {
@@ -56,21 +68,12 @@ __device__ __forceinline__ float read_mask(const void* bbox, int dtype, int b, i
                     : static_cast<const float*>(bbox)[off];
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid_constant__ CorrArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tail = smem + kCorrStages * kCorrStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + kCorrStages;
-  uint64_t* tmem_full = empty_bar + kCorrStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_mask = reinterpret_cast<float*>(tail + 128);                 // [hw] source mask of the current source
-  float* s_cx = s_mask + kCorrMaxHW;                                    // [w]
-  float* s_cy = s_cx + 128;                                             // [h]
-  float2* s_grid = reinterpret_cast<float2*>(s_cy + 128);               // [n_src][128]
+  CorrSmemTail& tl = *reinterpret_cast<CorrSmemTail*>(smem + kCorrStages * kCorrStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int num_kb = args.C / kCorrK;
@@ -86,98 +89,106 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
   }
   if (warp == 1 && lane_id() == 0) {
     for (int s = 0; s < kCorrStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&tl.full_bar[s], 1);
+      mbar_init(&tl.empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tl.tmem_full[a], 1);
+      mbar_init(&tl.tmem_empty[a], 8);  // one arrive per softmax warp
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, 2 * kCorrN);  // two partial-sum buffers
-  for (int i = threadIdx.x; i < args.w; i += blockDim.x) s_cx[i] = args.coord_table[args.h + i];
-  for (int i = threadIdx.x; i < args.h; i += blockDim.x) s_cy[i] = args.coord_table[i];
+  if (warp == 2) tmem_alloc(&tl.tmem_base, 2 * kCorrN);  // two partial-sum buffers
+  for (int s = threadIdx.x; s < args.hw; s += blockDim.x) {
+    const int sy = s / args.w, sx = s - sy * args.w;
+    tl.cx[s] = args.coord_table[args.h + sx];
+    tl.cy[s] = args.coord_table[sy];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
+  const uint32_t tmem_base = tl.tmem_base;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane_id() == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t stage_tx = args.split ? kCorrStageBytes : (kCorrABytes + kCorrBBytes);
-      for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
-        const int b = item / args.tiles_per_img;
-        const int mt = item - b * args.tiles_per_img;
-        const int trow = b * args.hw + mt * kCorrM;
-        for (int i = 0; i < args.n_src; ++i) {
-          for (int ch = 0; ch < chunks; ++ch) {
-            const int srow = (i * args.B + b) * args.hw + ch * kCorrN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* st = smem + stage * kCorrStageBytes;
-              mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-              tma_load_2d(st, &args.t_hi, &full_bar[stage], kb * kCorrK, trow);
-              tma_load_2d(st + 2 * kCorrABytes, &args.s_hi, &full_bar[stage], kb * kCorrK, srow);
-              if (args.split) {
-                tma_load_2d(st + kCorrABytes, &args.t_lo, &full_bar[stage], kb * kCorrK, trow);
-                tma_load_2d(st + 2 * kCorrABytes + kCorrBBytes, &args.s_lo, &full_bar[stage], kb * kCorrK, srow);
-              }
-              if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane_id() == 0) {
-      const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
-      int stage = 0;
-      uint32_t phase = 0;
-      int cc = 0;  // partial-accumulator counter -> TMEM buffer + phase
-      for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
-        for (int ic = 0; ic < args.n_src * chunks; ++ic) {
-          for (int kb0 = 0; kb0 < num_kb; kb0 += kCorrChunkKb, ++cc) {
-            const int buf = cc & 1;
-            const uint32_t buf_phase = (cc >> 1) & 1;
-            mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * kCorrN;
-            const int kb1 = min(num_kb, kb0 + kCorrChunkKb);
-            for (int kb = kb0; kb < kb1; ++kb) {
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint32_t st = smem_u32(smem + stage * kCorrStageBytes);
-              const uint64_t a_hi = make_desc_kmajor_sw128(st);
-              const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
-              const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
-              const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
-#pragma unroll
-              for (int k = 0; k < kCorrK / 16; ++k) {
-                const uint32_t off = k * 32;
-                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane_id() == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t stage_tx = args.split ? kCorrStageBytes : (kCorrABytes + kCorrBBytes);
+        for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
+          const int b = item / args.tiles_per_img;
+          const int mt = item - b * args.tiles_per_img;
+          const int trow = b * args.hw + mt * kCorrM;
+          for (int i = 0; i < args.n_src; ++i) {
+            for (int ch = 0; ch < chunks; ++ch) {
+              const int srow = (i * args.B + b) * args.hw + ch * kCorrN;
+              for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&tl.empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + stage * kCorrStageBytes;
+                mbar_arrive_expect_tx(&tl.full_bar[stage], stage_tx);
+                tma_load_2d(st, &args.t_hi, &tl.full_bar[stage], kb * kCorrK, trow);
+                tma_load_2d(st + 2 * kCorrABytes, &args.s_hi, &tl.full_bar[stage], kb * kCorrK, srow);
                 if (args.split) {
-                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  tma_load_2d(st + kCorrABytes, &args.t_lo, &tl.full_bar[stage], kb * kCorrK, trow);
+                  tma_load_2d(st + 2 * kCorrABytes + kCorrBBytes, &args.s_lo, &tl.full_bar[stage], kb * kCorrK, srow);
                 }
+                if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
               }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tmem_full[buf]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane_id() == 0) {
+        const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
+        int stage = 0;
+        uint32_t phase = 0;
+        int cc = 0;  // partial-accumulator counter -> TMEM buffer + phase
+        for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
+          for (int ic = 0; ic < args.n_src * chunks; ++ic) {
+            for (int kb0 = 0; kb0 < num_kb; kb0 += kCorrChunkKb, ++cc) {
+              const int buf = cc & 1;
+              const uint32_t buf_phase = (cc >> 1) & 1;
+              mbar_wait(&tl.tmem_empty[buf], buf_phase ^ 1);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + buf * kCorrN;
+              const int kb1 = min(num_kb, kb0 + kCorrChunkKb);
+              for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&tl.full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + stage * kCorrStageBytes);
+                const uint64_t a_hi = make_desc_kmajor_sw128(st);
+                const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
+                const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
+                const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
+#pragma unroll
+                for (int k = 0; k < kCorrK / 16; ++k) {
+                  const uint32_t off = k * 32;
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                  if (args.split) {
+                    umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
+                }
+                umma_commit(&tl.empty_bar[stage]);
+                if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
+              }
+              umma_commit(&tl.tmem_full[buf]);
+            }
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== softmax + gather =====================
-    const int q = warp & 3;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int half = (warp - 4) >> 2;  // column half of every 256-column chunk
     const int row = q * 32 + lane_id();
-    const int et = threadIdx.x - 128;  // 0..127 among epilogue threads
+    const int et = threadIdx.x - 128;  // 0..255 among the softmax threads
     constexpr float kLog2e = 1.4426950408889634f;
     int it = 0;
     for (int item = blockIdx.x; item < args.num_items; item += gridDim.x) {
@@ -185,44 +196,46 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
       const int mt = item - b * args.tiles_per_img;
       const int tpos = mt * kCorrM + row;  // target position inside the image
       const float m_t = read_mask(args.tar_bbox, args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, tpos);
+      // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)) = (T.S) * (wa*ms + wb);
+      // exact for binary masks (mismatched pairs get logit 0, not -inf, as in the reference)
+      const float wa = 2.f * m_t - 1.f, wb = 1.f - m_t;
       for (int i = 0; i < args.n_src; ++i) {
-        epi_bar_sync();  // previous source's mask no longer in use
-        for (int p = et; p < args.hw; p += 128)
-          s_mask[p] = read_mask(args.src_bbox[i], args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, p);
+        epi_bar_sync();  // previous source: mask and merge buffer no longer in use
+        for (int p = et; p < args.hw; p += kCorrEpiThreads)
+          tl.mask[p] = read_mask(args.src_bbox[i], args.bbox_dtype, b, args.bbox_h, args.bbox_w, args.h, args.w, p);
         epi_bar_sync();
         float run_max = -INFINITY, run_sum = 0.f, gx = 0.f, gy = 0.f;
         for (int ch = 0; ch < chunks; ++ch) {
-          // ---- promote the partial sums of this 128-column chunk into registers
-          float acc[kCorrN];
+          // ---- promote the partial sums of this chunk into registers
+          float acc[kCorrNC];
 #pragma unroll
-          for (int j = 0; j < kCorrN; ++j) acc[j] = 0.f;
+          for (int j = 0; j < kCorrNC; ++j) acc[j] = 0.f;
           for (int kb0 = 0; kb0 < num_kb; kb0 += kCorrChunkKb, ++it) {
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_full[buf], buf_phase);
+            mbar_wait(&tl.tmem_full[buf], buf_phase);
             tc_fence_after();
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrN + half * kCorrNC;
 #pragma unroll
-            for (int c0 = 0; c0 < kCorrN; c0 += 32) {
+            for (int c0 = 0; c0 < kCorrNC; c0 += 32) {
               float v[32];
-              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrN + c0, v);
+              tmem_ld_32x32(t0 + c0, v);
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[c0 + j] += v[j];
             }
             tc_fence_before();
             __syncwarp();
-            if (lane_id() == 0) mbar_arrive(&tmem_empty[buf]);
+            if (lane_id() == 0) mbar_arrive(&tl.tmem_empty[buf]);
           }
           // ---- online softmax with the source coordinates as V
 #pragma unroll
-          for (int c0 = 0; c0 < kCorrN; c0 += 32) {
-            const int s0 = ch * kCorrN + c0;
+          for (int c0 = 0; c0 < kCorrNC; c0 += 32) {
+            const int s0 = ch * kCorrN + half * kCorrNC + c0;
             float gmax = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float m_s = s_mask[s0 + j];
-              // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)); exact for binary masks
-              const float wgt = m_t * m_s + (1.f - m_t) * (1.f - m_s);
-              acc[c0 + j] = args.temperature * ((acc[c0 + j] * args.inv_operand_scale) * wgt);
+              const float wgt = fmaf(wa, tl.mask[s0 + j], wb);
+              acc[c0 + j] = (acc[c0 + j] * args.logit_scale) * wgt;
               gmax = fmaxf(gmax, acc[c0 + j]);
             }
             const float new_max = fmaxf(run_max, gmax);
@@ -233,61 +246,70 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float p = exp2f(fmaf(acc[c0 + j], kLog2e, -mb));
-              const int s = s0 + j;
-              const int sy = s / args.w, sx = s - sy * args.w;
               run_sum += p;
-              gx = fmaf(p, s_cx[sx], gx);
-              gy = fmaf(p, s_cy[sy], gy);
+              gx = fmaf(p, tl.cx[s0 + j], gx);
+              gy = fmaf(p, tl.cy[s0 + j], gy);
             }
           }
         }
-        const float2 g = make_float2(gx / run_sum, gy / run_sum);
-        s_grid[i * kCorrM + row] = g;
-        if (args.out_grids)
-          *reinterpret_cast<float2*>(args.out_grids + ((static_cast<size_t>(i) * args.B + b) * args.hw + tpos) * 2) = g;
+        // ---- merge the two column halves of the row
+        if (half == 1) tl.merge[row] = make_float4(run_max, run_sum, gx, gy);
+        epi_bar_sync();
+        if (half == 0) {
+          const float4 o = tl.merge[row];
+          const float m = fmaxf(run_max, o.x);
+          const float c0 = exp2f((run_max - m) * kLog2e), c1 = exp2f((o.x - m) * kLog2e);
+          const float l = run_sum * c0 + o.y * c1;
+          const float2 g = make_float2((gx * c0 + o.z * c1) / l, (gy * c0 + o.w * c1) / l);
+          tl.grid[i][row] = g;
+          if (args.out_grids)
+            *reinterpret_cast<float2*>(args.out_grids + ((static_cast<size_t>(i) * args.B + b) * args.hw + tpos) * 2) = g;
+        }
       }
       epi_bar_sync();  // all grids of this item visible
-      // ---- gather: warp q handles rows q*32 .. q*32+31; lane owns channels {128 k + 4 lane .. +3} ----
+      // ---- gather: softmax warp e handles rows e*16 .. e*16+15; lane owns channels {128 k + 4 lane .. +3} ----
       const int nk = args.C / 128;
       const float n_srcf = static_cast<float>(args.n_src);
-      for (int r = 0; r < 32; ++r) {
-        const int grow = q * 32 + r;
+      const int e = warp - 4;
+      for (int r = 0; r < 16; ++r) {
+        const int grow = e * 16 + r;
         const int pos = mt * kCorrM + grow;
         float4 accv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) accv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = 0; i < args.n_src; ++i) {
-          const float2 g = s_grid[i * kCorrM + grow];
+          const float2 g = tl.grid[i][grow];
           // F.grid_sample(bilinear, zeros, align_corners=False): ix = ((x + 1) * W - 1) / 2
           const float ix = ((g.x + 1.f) * args.w - 1.f) * 0.5f;
           const float iy = ((g.y + 1.f) * args.h - 1.f) * 0.5f;
           const float fx = floorf(ix), fy = floorf(iy);
           const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
           const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
-          const float wts[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
-          const float* base = args.src_fea[i] + static_cast<size_t>(b) * args.hw * args.C;
-          float4 res[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          float wts[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
+          const float* base = args.src_fea[i] + static_cast<size_t>(b) * args.hw * args.C + lane_id() * 4;
+          const float* tp[4];
 #pragma unroll
           for (int tap = 0; tap < 4; ++tap) {
             const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-            if (xx >= 0 && xx < args.w && yy >= 0 && yy < args.h) {
-              const float* p = base + static_cast<size_t>(yy * args.w + xx) * args.C + lane_id() * 4;
-              const float wt = wts[tap];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (k < nk) {
-                  const float4 f = __ldg(reinterpret_cast<const float4*>(p + k * 128));
-                  res[k].x = fmaf(f.x, wt, res[k].x); res[k].y = fmaf(f.y, wt, res[k].y);
-                  res[k].z = fmaf(f.z, wt, res[k].z); res[k].w = fmaf(f.w, wt, res[k].w);
-                }
-              }
-            }
+            const bool in = xx >= 0 && xx < args.w && yy >= 0 && yy < args.h;
+            if (!in) wts[tap] = 0.f;  // zeros padding: out-of-range taps contribute nothing
+            const int xc = min(max(xx, 0), args.w - 1), yc = min(max(yy, 0), args.h - 1);
+            tp[tap] = base + static_cast<size_t>(yc * args.w + xc) * args.C;
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            accv[k].x += res[k].x; accv[k].y += res[k].y; accv[k].z += res[k].z; accv[k].w += res[k].w;
+            if (k < nk) {
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(tp[0] + k * 128));
+              const float4 f1 = __ldg(reinterpret_cast<const float4*>(tp[1] + k * 128));
+              const float4 f2 = __ldg(reinterpret_cast<const float4*>(tp[2] + k * 128));
+              const float4 f3 = __ldg(reinterpret_cast<const float4*>(tp[3] + k * 128));
+              float4 res;
+              res.x = fmaf(f3.x, wts[3], fmaf(f2.x, wts[2], fmaf(f1.x, wts[1], f0.x * wts[0])));
+              res.y = fmaf(f3.y, wts[3], fmaf(f2.y, wts[2], fmaf(f1.y, wts[1], f0.y * wts[0])));
+              res.z = fmaf(f3.z, wts[3], fmaf(f2.z, wts[2], fmaf(f1.z, wts[1], f0.z * wts[0])));
+              res.w = fmaf(f3.w, wts[3], fmaf(f2.w, wts[2], fmaf(f1.w, wts[1], f0.w * wts[0])));
+              accv[k].x += res.x; accv[k].y += res.y; accv[k].z += res.z; accv[k].w += res.w;
+            }
           }
         }
         float* o = args.out_mean + (static_cast<size_t>(b) * args.hw + pos) * args.C + lane_id() * 4;
@@ -309,8 +331,8 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
   }
 }
 
-constexpr int kCorrSmemBytes =
-    kCorrStages * kCorrStageBytes + 1024 + 128 + (kCorrMaxHW + 256) * 4 + kCorrMaxSrc * kCorrM * 8;
+constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 + static_cast<int>(sizeof(CorrSmemTail));
+static_assert(kCorrSmemBytes <= 227 * 1024, "corr_warp shared memory budget");
 
 }  // namespace tsnet
 
@@ -330,9 +352,8 @@ extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar
   TSNET_ARG_CHECK(!d->split || (tar_lo && src_lo), "corr_warp: split mode needs the lo operands");
   TSNET_ARG_CHECK(d->n_src >= 1 && d->n_src <= kCorrMaxSrc, "corr_warp: n_src %d (max %d)", d->n_src, kCorrMaxSrc);
   const int hw = d->h * d->w;
-  TSNET_ARG_CHECK(hw % kCorrM == 0 && hw <= kCorrMaxHW, "corr_warp: h*w = %d must be a multiple of 128, <= %d", hw,
+  TSNET_ARG_CHECK(hw % kCorrN == 0 && hw <= kCorrMaxHW, "corr_warp: h*w = %d must be a multiple of 256, <= %d", hw,
                   kCorrMaxHW);
-  TSNET_ARG_CHECK(d->h <= 128 && d->w <= 128, "corr_warp: h, w <= 128");
   TSNET_ARG_CHECK(d->C % 128 == 0 && d->C <= 1024, "corr_warp: C %d must be a multiple of 128, <= 1024", d->C);
   TSNET_ARG_CHECK(d->bbox_dtype == 0 || d->bbox_dtype == 1, "corr_warp: bbox_dtype %d", d->bbox_dtype);
 
@@ -368,8 +389,8 @@ extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar
   a.num_items = d->B * a.tiles_per_img;
   a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
   a.split = d->split; a.fmt = d->fmt;
-  a.temperature = d->temperature;
-  a.inv_operand_scale = 1.f / (d->operand_scale == 0.f ? 1.f : d->operand_scale);
+  // operand_scale is a power of two, so folding it into the temperature is exact up to one rounding of the product
+  a.logit_scale = d->temperature / (d->operand_scale == 0.f ? 1.f : d->operand_scale);
 
   static bool attr_set = false;
   if (!attr_set) {

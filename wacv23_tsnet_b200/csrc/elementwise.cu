@@ -134,28 +134,32 @@ __device__ __forceinline__ void fetch_act8(const TapsArgs& a, int b, int y, int 
   }
 }
 
-__global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
+// grid.x = destination rows (b, plane, yd); the 256 threads of a block sweep (xd, channel group) of that row, so the
+// per-thread index math is 32-bit and, whenever 256 % (C/8) == 0, every thread keeps ONE channel group for the whole
+// row and loads its InstanceNorm statistics once.
+__global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
   const int cg = a.C / 8;
-  const size_t total = static_cast<size_t>(a.B) * a.planes * a.Hd * a.Wd * cg;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cg) * 8;
-    size_t pix = i / cg;
-    const int xd = static_cast<int>(pix % a.Wd);
-    pix /= a.Wd;
-    const int yd = static_cast<int>(pix % a.Hd);
-    pix /= a.Hd;
-    const int plane = static_cast<int>(pix % a.planes);
-    const int b = static_cast<int>(pix / a.planes);
+  int rowid = blockIdx.x;
+  const int yd = rowid % a.Hd;
+  rowid /= a.Hd;
+  const int plane = rowid % a.planes;
+  const int b = rowid / a.planes;
+  const bool fixed_c = (blockDim.x % cg) == 0;
+  const int per_row = a.Wd * cg;
 
-    float mean[8], rstd[8];
-    if (a.mean_rstd) {
+  float mean[8], rstd[8];
+  int c_loaded = -1;
+  for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+    const int xd = idx / cg;
+    const int c = (idx - xd * cg) * 8;
+    if (a.mean_rstd && c != c_loaded) {
       const float* mr = a.mean_rstd + (static_cast<size_t>(b) * a.C + c) * 2;
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         const float4 t = *reinterpret_cast<const float4*>(mr + j * 2);
         mean[j] = t.x; rstd[j] = t.y; mean[j + 1] = t.z; rstd[j + 1] = t.w;
       }
+      if (fixed_c) c_loaded = c;
     }
     float v[8];
     bool interior = false;  // destination pixel that owns the (unique) act_out write of its source pixel
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
               const float4 t = *reinterpret_cast<const float4*>(mr + j * 2);
               mean[j] = t.x; rstd[j] = t.y; mean[j + 1] = t.z; rstd[j + 1] = t.w;
             }
+            c_loaded = -1;
           }
           float u[8];
           fetch_act8(a, bi, yd, xd, c, mean, rstd, u);
@@ -237,57 +242,65 @@ __global__ void __launch_bounds__(256) build_taps_kernel(const TapsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem tap source: [B, H+6, W, Cp], kw folded into channels.  One thread = one destination pixel.
+// stem tap source: [B, H+6, W, Cp], kw folded into channels.  One thread = one destination pixel x 8 folded
+// channels, consecutive threads write consecutive 16-byte pieces (fully coalesced hi / lo stores); the
+// (column tap, input channel) decomposition of every folded channel comes from a shared-memory table.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_div,
+__global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_div,
                                                         const float* __restrict__ lbl, int Clbl, int B, int H, int W,
                                                         int Cp, int fmt, float scale, uint16_t* __restrict__ hi,
                                                         uint16_t* __restrict__ lo) {
+  __shared__ int8_t s_tap[1024], s_chan[1024];
   const int Cin = Cimg + Clbl + 3;
+  for (int j = threadIdx.x; j < Cp; j += blockDim.x) {
+    const int s = j / Cin;
+    s_tap[j] = static_cast<int8_t>(s < 7 ? s : -1);
+    s_chan[j] = static_cast<int8_t>(j - s * Cin);
+  }
+  __syncthreads();
   const int Hd = H + 6;
-  const size_t total = static_cast<size_t>(B) * Hd * W;
+  const int cg = Cp / 8;
+  const size_t total = static_cast<size_t>(B) * Hd * W * cg;
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
-  const int x = static_cast<int>(i % W);
-  const int yd = static_cast<int>((i / W) % Hd);
-  const int b = static_cast<int>(i / (static_cast<size_t>(W) * Hd));
+  const int g = static_cast<int>(i % cg);
+  const size_t pix = i / cg;
+  const int x = static_cast<int>(pix % W);
+  const int yd = static_cast<int>((pix / W) % Hd);
+  const int b = static_cast<int>(pix / (static_cast<size_t>(W) * Hd));
   const int ys = reflect_idx(yd - 3, H);
   // Encoder.coord_conv (model/TSNet.py:117-122): t = idx / (n-1); 2*t - 1; r = sqrt(x^2 + y^2), separate roundings
   const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
-  uint16_t* dh = hi + i * Cp;
-  uint16_t* dl = lo + i * Cp;
   const size_t plane = static_cast<size_t>(H) * W;
-  for (int j0 = 0; j0 < Cp; j0 += 8) {
-    uint16_t h[8], l[8];
+  uint16_t h[8], l[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = j0 + jj;
-      const int s = j / Cin;
-      const int c = j - s * Cin;
-      float v = 0.f;
-      if (s < 7) {
-        const int xs = reflect_idx(x + s - 3, W);
-        if (c < Cimg) {
-          v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
-        } else if (c < Cimg + Clbl) {
-          v = lbl[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane + static_cast<size_t>(ys) * W + xs];
-        } else {
-          const float xx =
-              __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
-          const int k = c - Cimg - Clbl;
-          v = k == 0 ? xx : (k == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
-        }
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = g * 8 + jj;
+    const int s = s_tap[j];
+    const int c = s_chan[j];
+    float v = 0.f;
+    if (s >= 0) {
+      const int xs = reflect_idx(x + s - 3, W);
+      if (c < Cimg) {
+        v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
+      } else if (c < Cimg + Clbl) {
+        v = lbl[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane + static_cast<size_t>(ys) * W + xs];
+      } else {
+        const float xx =
+            __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
+        const int k = c - Cimg - Clbl;
+        v = k == 0 ? xx : (k == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
       }
-      split16(v * scale, fmt, h[jj], l[jj]);
     }
-    uint4 ph, pl;
-    ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
-    ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
-    pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
-    pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
-    *reinterpret_cast<uint4*>(dh + j0) = ph;
-    *reinterpret_cast<uint4*>(dl + j0) = pl;
+    split16(v * scale, fmt, h[jj], l[jj]);
   }
+  uint4 ph, pl;
+  ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+  ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+  pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+  pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+  *reinterpret_cast<uint4*>(hi + i * 8) = ph;
+  *reinterpret_cast<uint4*>(lo + i * 8) = pl;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,11 +342,13 @@ __global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------------
 // output head: reflect-pad 3, 7x7 conv Cin -> 3, tanh, optional pose compositing, NCHW store.
-// block = 32 x 8 output pixels; channels processed in chunks of 16 through shared memory.
+// block = 32 x 16 output pixels, 128 threads; thread = 4 vertically adjacent pixels x 3 outputs.
+// Channels go through shared memory in chunks of 8 (pixel stride 12 floats: conflict-free LDS.128).  For every
+// column tap the thread keeps a 10-row sliding window in registers, so each activation LDS feeds 84 FMAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadTW = 32, kHeadTH = 8, kHeadCC = 8, kHeadPS = 12;  // pixel stride 12 floats: conflict-free LDS.128
+constexpr int kHeadTW = 32, kHeadTH = 16, kHeadCC = 8, kHeadPS = 12, kHeadPPT = 4;
 
-__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ act, int B, int H, int W, int Cin,
+__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ act, int B, int H, int W, int Cin,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         int fore_x0, int fore_x1, float fill0, float fill1,
                                                         float fill2, float* __restrict__ out) {
@@ -341,8 +356,10 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   __shared__ __align__(16) float s_w[49 * kHeadCC * 4];  // [tap][c][4] (3 outputs + pad)
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
-  const int tx = threadIdx.x % kHeadTW, ty = threadIdx.x / kHeadTW;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  const int tx = threadIdx.x % kHeadTW, ty = (threadIdx.x / kHeadTW) * kHeadPPT;
+  float acc[kHeadPPT][3];
+#pragma unroll
+  for (int p = 0; p < kHeadPPT; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
   for (int cc = 0; cc < Cin; cc += kHeadCC) {
     __syncthreads();
     for (int i = threadIdx.x; i < (kHeadTH + 6) * (kHeadTW + 6) * (kHeadCC / 4); i += blockDim.x) {
@@ -365,38 +382,48 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
     }
     __syncthreads();
 #pragma unroll 1
-    for (int r = 0; r < 7; ++r) {
+    for (int s = 0; s < 7; ++s) {
 #pragma unroll
-      for (int s = 0; s < 7; ++s) {
-        const float* ip = &s_in[((ty + r) * (kHeadTW + 6) + tx + s) * kHeadPS];
-        const float* wp = &s_w[(r * 7 + s) * kHeadCC * 4];
+      for (int c4 = 0; c4 < kHeadCC / 4; ++c4) {
+        float4 col[kHeadPPT + 6];
 #pragma unroll
-        for (int c4 = 0; c4 < kHeadCC / 4; ++c4) {
-          const float4 v = *reinterpret_cast<const float4*>(ip + c4 * 4);
-          const float e[4] = {v.x, v.y, v.z, v.w};
+        for (int rr = 0; rr < kHeadPPT + 6; ++rr)
+          col[rr] = *reinterpret_cast<const float4*>(&s_in[((ty + rr) * (kHeadTW + 6) + tx + s) * kHeadPS + c4 * 4]);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          const float* wp = &s_w[((r * 7 + s) * kHeadCC + c4 * 4) * 4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 wv = *reinterpret_cast<const float4*>(wp + (c4 * 4 + j) * 4);
-            acc0 = fmaf(e[j], wv.x, acc0);
-            acc1 = fmaf(e[j], wv.y, acc1);
-            acc2 = fmaf(e[j], wv.z, acc2);
+            const float4 wv = *reinterpret_cast<const float4*>(wp + j * 4);
+#pragma unroll
+            for (int p = 0; p < kHeadPPT; ++p) {
+              const float4 cv = col[p + r];
+              const float e = j == 0 ? cv.x : (j == 1 ? cv.y : (j == 2 ? cv.z : cv.w));
+              acc[p][0] = fmaf(e, wv.x, acc[p][0]);
+              acc[p][1] = fmaf(e, wv.y, acc[p][1]);
+              acc[p][2] = fmaf(e, wv.z, acc[p][2]);
+            }
           }
         }
       }
     }
   }
-  const int x = x0 + tx, y = y0 + ty;
-  if (x < W && y < H) {
-    float o[3] = {tanhf(acc0 + bias[0]), tanhf(acc1 + bias[1]), tanhf(acc2 + bias[2])};
-    if (fore_x1 > fore_x0) {
-      const float fore = (x >= fore_x0 && x < fore_x1) ? 1.f : 0.f;
-      const float fill[3] = {fill0, fill1, fill2};
+  const int x = x0 + tx;
+  const size_t plane = static_cast<size_t>(H) * W;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) o[k] = __fadd_rn(__fmul_rn(o[k], fore), __fmul_rn(fill[k], 1.f - fore));
+  for (int p = 0; p < kHeadPPT; ++p) {
+    const int y = y0 + ty + p;
+    if (x < W && y < H) {
+      float o[3] = {tanhf(acc[p][0] + bias[0]), tanhf(acc[p][1] + bias[1]), tanhf(acc[p][2] + bias[2])};
+      if (fore_x1 > fore_x0) {
+        const float fore = (x >= fore_x0 && x < fore_x1) ? 1.f : 0.f;
+        const float fill[3] = {fill0, fill1, fill2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o[k] = __fadd_rn(__fmul_rn(o[k], fore), __fmul_rn(fill[k], 1.f - fore));
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out[(static_cast<size_t>(b) * 3 + k) * plane + static_cast<size_t>(y) * W + x] = o[k];
     }
-    const size_t plane = static_cast<size_t>(H) * W;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) out[(static_cast<size_t>(b) * 3 + k) * plane + static_cast<size_t>(y) * W + x] = o[k];
   }
 }
 
@@ -506,8 +533,8 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
     case TSNET_TAPS_UP2REFLECT1: a.Hd = 2 * d->H + 2; a.Wd = 2 * d->W + 2; break;
     default: return set_error(-1, "build_taps: unknown mode %d", d->mode);
   }
-  const size_t total = static_cast<size_t>(a.B) * a.planes * a.Hd * a.Wd * (a.C / 8);
-  build_taps_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const unsigned rows = static_cast<unsigned>(a.B) * a.planes * a.Hd;
+  build_taps_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -517,9 +544,10 @@ extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, c
                                uint16_t* taps_lo, void* stream) {
   TSNET_ARG_CHECK(lbl_nchw && taps_hi && taps_lo, "stem_taps: null argument");
   TSNET_ARG_CHECK((img_nchw != nullptr) == (Cimg > 0), "stem_taps: img pointer / Cimg mismatch");
-  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3), "stem_taps: Cp %d too small", Cp);
-  const size_t total = static_cast<size_t>(B) * (H + 6) * W;
-  stem_taps_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3) && Cp <= 1024, "stem_taps: Cp %d out of range", Cp);
+  TSNET_ARG_CHECK(Cimg + Clbl + 3 <= 127, "stem_taps: too many input channels");
+  const size_t total = static_cast<size_t>(B) * (H + 6) * W * (Cp / 8);
+  stem_taps_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl_nchw, Clbl, B, H, W, Cp, fmt, scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -545,7 +573,7 @@ extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, 
   TSNET_ARG_CHECK(fore_x1 <= fore_x0 || fill3, "head_conv: compositing needs fill3 (host pointer to 3 floats)");
   dim3 grid((W + kHeadTW - 1) / kHeadTW, (H + kHeadTH - 1) / kHeadTH, B);
   const float f0 = fill3 ? fill3[0] : 0.f, f1 = fill3 ? fill3[1] : 0.f, f2 = fill3 ? fill3[2] : 0.f;
-  head_conv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, B, H, W, Cin, w_oihw, bias, fore_x0,
+  head_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, B, H, W, Cin, w_oihw, bias, fore_x0,
                                                                           fore_x1, f0, f1, f2, out_nchw);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;

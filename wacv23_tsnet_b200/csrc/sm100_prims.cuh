@@ -59,15 +59,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (visible error) instead of hanging the GPU box.
+// Bounded wait with back-off: a protocol bug must trap (visible launch failure) instead of hanging the GPU box,
+// and a waiting control lane must not steal issue slots from the math warps that share its scheduler.
 #ifndef TSNET_MBAR_TIMEOUT_CYCLES
 #define TSNET_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > TSNET_MBAR_TIMEOUT_CYCLES) __trap();  // surfaces as a launch failure on the host
+  long long t0 = 0;
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (spins > 8) __nanosleep(32);
+    if ((spins & 0xFFF) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TSNET_MBAR_TIMEOUT_CYCLES) __trap();
+    }
   }
 }
 
