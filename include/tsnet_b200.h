@@ -121,8 +121,11 @@ int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* me
  * analytically) and ReflectionPad2d(3) (:66).  Destination [B, H+6, W, Cp]: pixel (yp, x) holds, for
  * s = 0..6, the Cin = Cimg + Clbl + 3 channels of source pixel (reflect(yp-3), reflect(x+s-3)).
  * img may be NULL (label encoder).  The image is DIVIDED by img_div (the /255.0 of set_*_input, :268-286;
- * a true division so the rounding matches the reference). */
-int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const float* lbl_nchw, int Clbl, int B,
+ * a true division so the rounding matches the reference).
+ * lbl_kind 0: lbl = fp32 one-hot planes [B, Clbl, H, W] (what the reference's callers pass);
+ * lbl_kind 1: lbl = uint8 class-index map [B, H, W]; channel c is (lbl == c), i.e. utils/misc.py:50-67 `vl2ch`
+ *             evaluated inside the loader -- 4 x Clbl fewer bytes over PCIe and HBM. */
+int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const void* lbl, int Clbl, int lbl_kind, int B,
                     int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
 
 /* ---- correlation operands ------------------------------------------------------------------------
@@ -167,6 +170,16 @@ size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc* d);
 int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
                          const float* bias, int fore_x0, int fore_x1, const float* fill3, float* out_nchw,
                          void* stream);
+
+/* ---- demo post-processing -------------------------------------------------------
+ * demo/demo_face.py:194-199 + sample_img :96-105 (demo_pose.py analogous): per image and channel
+ *   y = (x - mean) / std * ref_std + ref_mean      (mean / unbiased std of the generated frame, per channel)
+ *   y = clamp(y + img_mean, 0, 1) * 255 ; BGR -> RGB ; uint8 (truncation)
+ * rec_nchw [B,3,H,W] fp32 (device); ref_mean3 / ref_std3 device pointers to 3 floats (statistics of the source
+ * frames, computed by the caller as in demo_face.py:180-182); img_mean3_host = IMG_MEAN/255 (host pointer);
+ * out [B,H,W,3] uint8 RGB (device).  Removes the fp32 D2H + numpy passes per frame. */
+int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* ref_mean3, const float* ref_std3,
+                         const float* img_mean3_host, uint8_t* out_hwc_rgb, void* stream);
 
 /* ---- reference-style direct convolution (validation kernel, fp32 SIMT) ----------------------------
  * Plain NHWC direct convolution with zero or reflect padding; used by the tests to cross-check the

@@ -269,3 +269,39 @@ def test_argument_errors_are_reported_not_crashed():
     hi, lo, g = ops.build_taps(x, m, L.TAPS_SAME)
     with pytest.raises(L.TSNetLibraryError, match="multiple of 128"):
         ops.conv_gemm(hi, lo, g, pc, "1x1", 1, 10, 10, m, m.act_scale)
+
+
+def test_stem_taps_classmap_equals_onehot():
+    """uint8 class-index labels expanded inside the loader (vl2ch, utils/misc.py:50-67) == feeding the one-hot planes."""
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(6)
+    for L_ in (2, 25):
+        cls = torch.randint(0, L_, (2, 128, 128), device="cuda", dtype=torch.uint8)
+        onehot = torch.stack([(cls == c).float() for c in range(L_)], 1).contiguous()
+        img = torch.rand(2, 3, 128, 128, device="cuda") * 255 - 100
+        Cp = (7 * (3 + L_ + 3) + 63) // 64 * 64
+        a = ops.stem_taps(img, 255.0, onehot, Cp, m)
+        b = ops.stem_taps(img, 255.0, cls, Cp, m, label_nc=L_)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        a = ops.stem_taps(None, 1.0, onehot, (7 * (L_ + 3) + 63) // 64 * 64, m)
+        b = ops.stem_taps(None, 1.0, cls, (7 * (L_ + 3) + 63) // 64 * 64, m, label_nc=L_)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_postprocess_u8_matches_demo_arithmetic():
+    """demo/demo_face.py:194-199 + sample_img (:96-105), restated in torch, vs the fused kernel."""
+    from wacv23_tsnet_b200 import ops
+    torch.manual_seed(7)
+    rec = torch.tanh(torch.randn(3, 3, 256, 256, device="cuda"))
+    ref_mean = torch.tensor([0.05, -0.02, 0.01], device="cuda")
+    ref_std = torch.tensor([0.21, 0.19, 0.2], device="cuda")
+    img_mean = [101.848 / 255, 112.108 / 255, 111.660 / 255]
+    got = ops.postprocess_u8(rec, ref_mean, ref_std, img_mean)
+    gm = rec.view(3, 3, -1).mean(2).view(3, 3, 1, 1)
+    gs = rec.view(3, 3, -1).std(2).view(3, 3, 1, 1)
+    y = (rec - gm) / gs * ref_std.view(1, 3, 1, 1) + ref_mean.view(1, 3, 1, 1)
+    y = (y + torch.tensor(img_mean, device="cuda").view(1, 3, 1, 1)).clamp(0, 1) * 255
+    ref = y.permute(0, 2, 3, 1).flip(-1).to(torch.uint8)             # BGR -> RGB, astype('uint8')
+    diff = (got.int() - ref.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 2e-3  # truncation boundaries only

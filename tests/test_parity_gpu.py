@@ -220,3 +220,47 @@ def test_two_gpu_batch_shards_equal_single_gpu(tmp_path):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
+
+
+def test_frame_pipeline_matches_synchronous_forward():
+    """wacv23_tsnet_b200.pipeline.FramePipeline (overlapped H2D / forward / D2H) returns, in order, exactly what
+    set_test_input + forward + .cpu() returns for each batch."""
+    from oracle import synth
+    from wacv23_tsnet_b200.pipeline import FramePipeline
+    cfg, gold, inputs, net = _build("quickstart_bs1")
+    batches = []
+    for k in range(4):
+        inp = synth.quick_start_inputs(2, 2, 3, seed=50 + k)
+        batches.append({key: ([torch.from_numpy(a).pin_memory() for a in v] if isinstance(v, list)
+                              else torch.from_numpy(v).pin_memory()) for key, v in inp.items() if key != "tar_img"})
+    expect = []
+    with torch.no_grad():
+        for bt in batches:
+            net.set_test_input(bt["src_img"], bt["src_lbl"], bt["src_bbox"], bt["tar_lbl"], bt["tar_bbox"])
+            net.forward()
+            expect.append(net.rec_tar_img.cpu())
+    got = list(FramePipeline(net).run(batches))
+    assert len(got) == len(expect)
+    for g, e in zip(got, expect):
+        assert torch.equal(g, e)
+
+
+def test_classmap_labels_give_identical_forward():
+    """uint8 class-index labels ([B,H,W]) staged on the device == the one-hot float planes."""
+    from oracle import synth
+    from wacv23_tsnet_b200.model.TSNet import TSNet
+    torch.manual_seed(3)
+    net = TSNet(is_train=False, label_nc=2, n_blocks=0, n_downsampling=3, n_source=2)
+    net.eval()
+    inp = synth.dataset_like_inputs(2, 2, 2, seed=9)                 # one-hot labels
+    cls = lambda oh: torch.from_numpy(oh.argmax(1).astype(np.uint8))
+    t = torch.from_numpy
+    with torch.no_grad():
+        net.set_test_input([t(a) for a in inp["src_img"]], [t(a) for a in inp["src_lbl"]],
+                           [t(a) for a in inp["src_bbox"]], t(inp["tar_lbl"]), t(inp["tar_bbox"]))
+        net.forward()
+        a = net.rec_tar_img.clone()
+        net.set_test_input([t(a_) for a_ in inp["src_img"]], [cls(a_) for a_ in inp["src_lbl"]],
+                           [t(a_) for a_ in inp["src_bbox"]], cls(inp["tar_lbl"]), t(inp["tar_bbox"]))
+        net.forward()
+        assert torch.equal(net.rec_tar_img, a)

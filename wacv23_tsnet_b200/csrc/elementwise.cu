@@ -242,14 +242,20 @@ __global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem tap source: [B, H+6, W, Cp], kw folded into channels.  One thread = one destination pixel x 8 folded
-// channels, consecutive threads write consecutive 16-byte pieces (fully coalesced hi / lo stores); the
-// (column tap, input channel) decomposition of every folded channel comes from a shared-memory table.
+// stem tap source: [B, H+6, W, Cp], kw folded into channels.
+// block = one destination row (b, yd) x 64 pixels.  Phase 1 stages the Cin input channels of the 70 source pixels
+// (64 + 6 halo, reflect-indexed) in shared memory with coalesced plane reads (CoordConv channels are generated, the
+// /255 is applied).  Phase 2: thread = destination pixel x 8 folded channels, consecutive threads write consecutive
+// 16-byte pieces (fully coalesced hi / lo stores); (column tap, channel) of a folded channel comes from a table.
+// lbl_kind: 0 = fp32 one-hot planes [B, Clbl, H, W]; 1 = uint8 class-index map [B, H, W] (utils/misc.py:50-67 vl2ch).
 // ------------------------------------------------------------------------------------------------
+constexpr int kStemTW = 64;
+
 __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_div,
-                                                        const float* __restrict__ lbl, int Clbl, int B, int H, int W,
-                                                        int Cp, int fmt, float scale, uint16_t* __restrict__ hi,
-                                                        uint16_t* __restrict__ lo) {
+                                                        const void* __restrict__ lbl, int Clbl, int lbl_kind, int B,
+                                                        int H, int W, int Cp, int fmt, float scale,
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  extern __shared__ float s_src[];  // [Cin][kStemTW + 6]
   __shared__ int8_t s_tap[1024], s_chan[1024];
   const int Cin = Cimg + Clbl + 3;
   for (int j = threadIdx.x; j < Cp; j += blockDim.x) {
@@ -257,50 +263,57 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
     s_tap[j] = static_cast<int8_t>(s < 7 ? s : -1);
     s_chan[j] = static_cast<int8_t>(j - s * Cin);
   }
-  __syncthreads();
   const int Hd = H + 6;
-  const int cg = Cp / 8;
-  const size_t total = static_cast<size_t>(B) * Hd * W * cg;
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int g = static_cast<int>(i % cg);
-  const size_t pix = i / cg;
-  const int x = static_cast<int>(pix % W);
-  const int yd = static_cast<int>((pix / W) % Hd);
-  const int b = static_cast<int>(pix / (static_cast<size_t>(W) * Hd));
+  const int xt = blockIdx.x * kStemTW;
+  const int yd = blockIdx.y;
+  const int b = blockIdx.z;
   const int ys = reflect_idx(yd - 3, H);
+  const size_t plane = static_cast<size_t>(H) * W;
   // Encoder.coord_conv (model/TSNet.py:117-122): t = idx / (n-1); 2*t - 1; r = sqrt(x^2 + y^2), separate roundings
   const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
-  const size_t plane = static_cast<size_t>(H) * W;
-  uint16_t h[8], l[8];
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const int j = g * 8 + jj;
-    const int s = s_tap[j];
-    const int c = s_chan[j];
-    float v = 0.f;
-    if (s >= 0) {
-      const int xs = reflect_idx(x + s - 3, W);
-      if (c < Cimg) {
-        v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
-      } else if (c < Cimg + Clbl) {
-        v = lbl[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane + static_cast<size_t>(ys) * W + xs];
-      } else {
-        const float xx =
-            __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
-        const int k = c - Cimg - Clbl;
-        v = k == 0 ? xx : (k == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
-      }
+  constexpr int SW = kStemTW + 6;
+  for (int i = threadIdx.x; i < Cin * SW; i += blockDim.x) {
+    const int c = i / SW, k = i - c * SW;
+    const int xs = reflect_idx(xt + k - 3, W);
+    float v;
+    if (c < Cimg) {
+      v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
+    } else if (c < Cimg + Clbl) {
+      if (lbl_kind == 0)
+        v = static_cast<const float*>(lbl)[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane +
+                                           static_cast<size_t>(ys) * W + xs];
+      else
+        v = static_cast<const uint8_t*>(lbl)[static_cast<size_t>(b) * plane + static_cast<size_t>(ys) * W + xs] ==
+                    (c - Cimg) ? 1.f : 0.f;
+    } else {
+      const float xx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
+      const int kk = c - Cimg - Clbl;
+      v = kk == 0 ? xx : (kk == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
     }
-    split16(v * scale, fmt, h[jj], l[jj]);
+    s_src[i] = v;
   }
-  uint4 ph, pl;
-  ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
-  ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
-  pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
-  pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
-  *reinterpret_cast<uint4*>(hi + i * 8) = ph;
-  *reinterpret_cast<uint4*>(lo + i * 8) = pl;
+  __syncthreads();
+  const int cg = Cp / 8;
+  const size_t row_base = ((static_cast<size_t>(b) * Hd + yd) * W + xt) * Cp;
+  for (int i = threadIdx.x; i < kStemTW * cg; i += blockDim.x) {
+    const int px = i / cg, g = i - px * cg;
+    if (xt + px >= W) break;
+    uint16_t h[8], l[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = g * 8 + jj;
+      const int s = s_tap[j];
+      const float v = s >= 0 ? s_src[s_chan[j] * SW + px + s] : 0.f;
+      split16(v * scale, fmt, h[jj], l[jj]);
+    }
+    uint4 ph, pl;
+    ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+    ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+    pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+    pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+    *reinterpret_cast<uint4*>(hi + row_base + static_cast<size_t>(i) * 8) = ph;
+    *reinterpret_cast<uint4*>(lo + row_base + static_cast<size_t>(i) * 8) = pl;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,6 +441,56 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// demo post-processing (demo/demo_face.py:96-105, 194-199): per image and channel, re-normalise the generated frame
+// to the reference statistics of the source video, add the dataset mean, clamp, x255, BGR -> RGB, uint8.
+//   y = (x - mean_c) / std_c * ref_std_c + ref_mean_c ;  y = clamp(y + img_mean_c, 0, 1) * 255 ;  out[.., 2 - c] = (u8) y
+// std is the unbiased torch.std.  One block per (image, channel); two-pass statistics in fp32 + block reduction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) postprocess_u8_kernel(const float* __restrict__ x, int HW,
+                                                             const float* __restrict__ ref_mean,
+                                                             const float* __restrict__ ref_std, float m0, float m1,
+                                                             float m2, uint8_t* __restrict__ out) {
+  __shared__ float s_red[16];
+  __shared__ float s_bcast;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* p = x + (static_cast<size_t>(b) * 3 + c) * HW;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) s_bcast = t;
+    }
+    __syncthreads();
+    const float r = s_bcast;
+    __syncthreads();
+    return r;
+  };
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += p[i];
+  const float mean = block_sum(acc) / static_cast<float>(HW);
+  acc = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float d = p[i] - mean;
+    acc = fmaf(d, d, acc);
+  }
+  const float stdv = sqrtf(block_sum(acc) / static_cast<float>(HW - 1));
+  const float rs = ref_std[c], rm = ref_mean[c];
+  const float im = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  uint8_t* o = out + static_cast<size_t>(b) * HW * 3 + (2 - c);
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float y = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(p[i], -mean), stdv), rs), rm);
+    y = __fadd_rn(y, im);
+    y = fminf(fmaxf(y, 0.f), 1.f) * 255.f;
+    o[static_cast<size_t>(i) * 3] = static_cast<uint8_t>(y);  // astype('uint8'): truncation
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // validation-only direct convolution, fp32 FMA, NHWC. One thread = one output element.
 // ------------------------------------------------------------------------------------------------
 __global__ void direct_conv_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
@@ -539,16 +602,20 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   return 0;
 }
 
-extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const float* lbl_nchw, int Clbl,
-                               int B, int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi,
+extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const void* lbl, int Clbl,
+                               int lbl_kind, int B, int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi,
                                uint16_t* taps_lo, void* stream) {
-  TSNET_ARG_CHECK(lbl_nchw && taps_hi && taps_lo, "stem_taps: null argument");
+  TSNET_ARG_CHECK(lbl && taps_hi && taps_lo, "stem_taps: null argument");
   TSNET_ARG_CHECK((img_nchw != nullptr) == (Cimg > 0), "stem_taps: img pointer / Cimg mismatch");
+  TSNET_ARG_CHECK(lbl_kind == 0 || lbl_kind == 1, "stem_taps: lbl_kind %d", lbl_kind);
   TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3) && Cp <= 1024, "stem_taps: Cp %d out of range", Cp);
   TSNET_ARG_CHECK(Cimg + Clbl + 3 <= 127, "stem_taps: too many input channels");
-  const size_t total = static_cast<size_t>(B) * (H + 6) * W * (Cp / 8);
-  stem_taps_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl_nchw, Clbl, B, H, W, Cp, fmt, scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
+  TSNET_ARG_CHECK(W % kStemTW == 0 && W >= 4 && H >= 4, "stem_taps: W %d must be a multiple of %d", W, kStemTW);
+  dim3 grid(W / kStemTW, H + 6, B);
+  const size_t smem = static_cast<size_t>(Cimg + Clbl + 3) * (kStemTW + 6) * sizeof(float);
+  stem_taps_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl, Clbl, lbl_kind, B, H, W, Cp, fmt,
+      scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -575,6 +642,18 @@ extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, 
   const float f0 = fill3 ? fill3[0] : 0.f, f1 = fill3 ? fill3[1] : 0.f, f2 = fill3 ? fill3[2] : 0.f;
   head_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, B, H, W, Cin, w_oihw, bias, fore_x0,
                                                                           fore_x1, f0, f1, f2, out_nchw);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* ref_mean3,
+                                    const float* ref_std3, const float* img_mean3_host, uint8_t* out_hwc_rgb,
+                                    void* stream) {
+  TSNET_ARG_CHECK(rec_nchw && ref_mean3 && ref_std3 && img_mean3_host && out_hwc_rgb, "postprocess_u8: null argument");
+  TSNET_ARG_CHECK(H * W >= 2, "postprocess_u8: image too small");
+  dim3 grid(3, B);
+  postprocess_u8_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+      rec_nchw, H * W, ref_mean3, ref_std3, img_mean3_host[0], img_mean3_host[1], img_mean3_host[2], out_hwc_rgb);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

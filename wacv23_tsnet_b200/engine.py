@@ -71,9 +71,9 @@ class ForwardEngine:
         """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it or None).
         For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the residual stream."""
         m = self.mode
-        X, _, H, W = lbl.shape
+        X, H, W = lbl.shape[0], lbl.shape[-2], lbl.shape[-1]
         pc = self._pack(net, "model.1", fold_kw=True)
-        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m)
+        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc)
         y, mr = self._conv(t, pc, "7x1", X, H, W)
         for k, idx in enumerate((4, 7, 10)):
             t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
@@ -96,14 +96,15 @@ class ForwardEngine:
     @torch.no_grad()
     def forward(self, src_imgs, img_divs, src_lbls, src_bboxes, tar_lbl, tar_bbox, return_flow=False,
                 pose_fill=None, collect=None):
-        """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (images NOT yet /255:
+        """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (labels may instead be
+        uint8 class-index maps [B,256,256]: vl2ch is then evaluated inside the stem loader; images NOT yet /255:
         img_divs[i] is the divisor set_*_input would have applied: 255, or 1 for use_prev sources); src_bboxes / tar_bbox: [B,256,256] uint8|fp32.
         Returns (rec_tar_img NCHW fp32, list of warp grids [B,h,w,2] or None).
         `collect`: optional dict receiving intermediates (tests)."""
         L.require_device()
         m = self.mode
         n = len(src_imgs)
-        B, _, H0, W0 = tar_lbl.shape
+        B, H0, W0 = tar_lbl.shape[0], tar_lbl.shape[-2], tar_lbl.shape[-1]
         dev = tar_lbl.device
         h, w, Cf = H0 // 8, W0 // 8, 512
         hw = h * w

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "tsnet_conv_gemm_fwd": (C.c_int, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
-    "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_float, vp, vp, vp]),
     "tsnet_l2norm_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
     "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp, vp,
@@ -52,6 +52,7 @@ _SIGNATURES = {
     "tsnet_corr_warp_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
     "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                        C.POINTER(C.c_float), vp, vp]),
+    "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_float), vp, vp]),
     "tsnet_direct_conv_fp32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, vp, vp]),
 }

@@ -136,6 +136,16 @@ class TSNet(nn.Module):
         return t if t.dtype == torch.float32 else t.float()
 
     @staticmethod
+    def _lbl(t):
+        """Labels: fp32 one-hot planes [B, L, H, W] as the reference's callers pass them, or (extension, SURVEY
+        section 8f row 2) a uint8 class-index map [B, H, W] whose one-hot expansion (utils/misc.py:50-67 `vl2ch`)
+        happens inside the stem loader kernel."""
+        t = t.cuda()
+        if t.dtype == torch.uint8 and t.dim() == 3:
+            return t.contiguous()
+        return t if t.dtype == torch.float32 else t.float()
+
+    @staticmethod
     def _mask(t):
         t = t.cuda()
         return t if t.dtype in (torch.uint8, torch.float32) else t.float()
@@ -152,10 +162,10 @@ class TSNet(nn.Module):
         self._src_img_raw = [self._f32(x) for x in src_img_list]
         self._src_img_div = [1.0 if (use_prev is not None and use_prev[i]) else 255.0
                              for i in range(len(self._src_img_raw))]
-        self.src_lbl_list = [self._f32(x) for x in src_lbl_list]
+        self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
         self.src_bbox_list = [self._mask(x).unsqueeze(dim=1) for x in src_bbox_list]
         self.tar_img = self._f32(tar_img) / 255.0
-        self.tar_lbl = self._f32(tar_lbl)
+        self.tar_lbl = self._lbl(tar_lbl)
         self.tar_bbox = self._mask(tar_bbox).unsqueeze(dim=1)
 
     def set_test_input(self, src_img_list, src_lbl_list, src_bbox_list,
@@ -163,9 +173,9 @@ class TSNet(nn.Module):
                        prev_tar_img=None, prev_tar_lbl=None, prev_tar_bbox=None):
         self._src_img_raw = [self._f32(x) for x in src_img_list]
         self._src_img_div = [255.0] * len(self._src_img_raw)
-        self.src_lbl_list = [self._f32(x) for x in src_lbl_list]
+        self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
         self.src_bbox_list = [self._mask(x).unsqueeze(dim=1) for x in src_bbox_list]
-        self.tar_lbl = self._f32(tar_lbl)
+        self.tar_lbl = self._lbl(tar_lbl)
         self.tar_bbox = self._mask(tar_bbox).unsqueeze(dim=1)
         if prev_tar_img is not None:
             self.prev_tar_img = prev_tar_img.cuda() / 255.0

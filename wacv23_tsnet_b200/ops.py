@@ -202,16 +202,20 @@ def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_
     return hi, lo, (planes, Hd, Wd)
 
 
-def stem_taps(img, img_div, lbl, Cp, mode):
-    """img [B,3,H,W] fp32 NCHW or None (divided by img_div in the kernel); lbl [B,L,H,W].
-    Returns (hi, lo, geom) of the kw-folded tap source."""
-    B, Clbl, H, W = lbl.shape
+def stem_taps(img, img_div, lbl, Cp, mode, label_nc=None):
+    """img [B,3,H,W] fp32 NCHW or None (divided by img_div in the kernel); lbl [B,L,H,W] fp32 one-hot planes, or a
+    uint8 class-index map [B,H,W] together with label_nc.  Returns (hi, lo, geom) of the kw-folded tap source."""
+    if lbl.dtype == torch.uint8:
+        assert lbl.dim() == 3 and label_nc is not None and lbl.is_contiguous()
+        (B, H, W), Clbl, kind = lbl.shape, label_nc, 1
+    else:
+        (B, Clbl, H, W), kind = _f32(lbl).shape, 0
     Cimg = 0 if img is None else img.shape[1]
     hi = torch.empty((B, H + 6, W, Cp), dtype=torch.int16, device=lbl.device)
     lo = torch.empty_like(hi)
     with _Prof(("stem_taps",)):
         L.check(L.load().tsnet_stem_taps(_ptr(None if img is None else _f32(img)), Cimg, C.c_float(img_div),
-                                         _ptr(_f32(lbl)), Clbl, B, H, W, Cp, mode.fmt, C.c_float(mode.act_scale),
+                                         _ptr(lbl), Clbl, kind, B, H, W, Cp, mode.fmt, C.c_float(mode.act_scale),
                                          _ptr(hi), _ptr(lo), _stream()))
     _count()
     return hi, lo, (1, H + 6, W)
@@ -267,6 +271,20 @@ def head_conv_tanh(act, weight, bias, fore=None, fill=None):
     with _Prof(("head_conv_tanh",)):
         L.check(L.load().tsnet_head_conv_tanh(_ptr(_f32(act)), B, H, W, Cin, _ptr(_f32(weight.detach())),
                                               _ptr(_f32(bias.detach())), x0, x1, fill_arr, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def postprocess_u8(rec, ref_mean, ref_std, img_mean):
+    """rec fp32 NCHW [B,3,H,W] -> uint8 RGB [B,H,W,3]: the demos' colour re-normalisation + sample_img
+    (demo/demo_face.py:96-105, 194-199) in one kernel.  ref_mean / ref_std: CUDA tensors with 3 floats;
+    img_mean: 3 python floats (IMG_MEAN / 255)."""
+    B, _, H, W = rec.shape
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=rec.device)
+    im = (C.c_float * 3)(*[float(v) for v in img_mean])
+    with _Prof(("postprocess_u8",)):
+        L.check(L.load().tsnet_postprocess_u8(_ptr(_f32(rec)), B, H, W, _ptr(_f32(ref_mean.reshape(3))),
+                                              _ptr(_f32(ref_std.reshape(3))), im, _ptr(out), _stream()))
     _count()
     return out
 
