@@ -79,6 +79,10 @@ typedef struct {
   int split;        /* 1: hi*hi + hi*lo + lo*hi (fp32-faithful); 0: hi*hi only (fast, non-parity) */
   int fmt;          /* TSNET_FMT_* */
   float out_scale;  /* accumulators are multiplied by this before bias (undo operand pre-scaling) */
+  const float* addend; /* optional fp32 [addend_rows, Cout] (device): y[m] += addend[m % addend_rows] before the
+                          statistics.  Lets a conv over cat[a_i, t] be computed as conv(a_i) + conv(t) with the
+                          source-independent half evaluated once per frame (FuseNet, model/TSNet.py:196-198) */
+  int addend_rows;
 } tsnet_conv_desc;
 
 int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,

@@ -305,3 +305,28 @@ def test_postprocess_u8_matches_demo_arithmetic():
     ref = y.permute(0, 2, 3, 1).flip(-1).to(torch.uint8)             # BGR -> RGB, astype('uint8')
     diff = (got.int() - ref.int()).abs()
     assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 2e-3  # truncation boundaries only
+
+
+def test_conv_gemm_addend_broadcast_over_sources():
+    """conv over cat[a_i, t] == conv_a(a_i) + conv_t(t): the source-independent half is computed once and added (fp32)
+    in the GEMM epilogue with row index modulo (FuseNet, model/TSNet.py:196-198)."""
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(8)
+    n, B, C = 3, 2, 128
+    a = torch.randn(n * B, 32, 32, C, device="cuda")
+    t = torch.randn(B, 32, 32, C, device="cuda")
+    w = torch.randn(256, 2 * C, 3, 3, device="cuda") * 0.05
+    b = torch.randn(256, device="cuda")
+    cat = torch.cat([a, t.repeat(n, 1, 1, 1)], -1).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(cat, (1, 1, 1, 1), mode="reflect").double(), w.double(), b.double()).permute(0, 2, 3, 1).float()
+    pc_t = ops.PackedConv(w, None, m, cin_range=(C, 2 * C))
+    pc_a = ops.PackedConv(w, b, m, cin_range=(0, C))
+    th, tl, tg = ops.build_taps(t, m, L.TAPS_REFLECT1)
+    y_t, _ = ops.conv_gemm(th, tl, tg, pc_t, "3x3", B, 32, 32, m, m.act_scale, want_stats=False)
+    ah, al, ag = ops.build_taps(a, m, L.TAPS_REFLECT1)
+    y, st = ops.conv_gemm(ah, al, ag, pc_a, "3x3", n * B, 32, 32, m, m.act_scale, addend=y_t)
+    mr = ops.instnorm_reduce(st, n * B, 1024, 256)
+    torch.cuda.synchronize()
+    assert _relerr(y, ref) < CONV_TOL["fp16x3"]
+    assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5   # statistics include the addend

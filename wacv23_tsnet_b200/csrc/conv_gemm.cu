@@ -37,9 +37,11 @@ constexpr int kSmemBudget = 200 * 1024;
 struct alignas(64) ConvGemmArgs {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   const float* bias;
+  const float* addend;
   float* y;
   float* stats;
   float out_scale;
+  int addend_rows;
   int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
   int Cout, num_taps, kc_per_tap, planes, split, fmt, chunk_kb;
   int8_t tap_dy[TSNET_MAX_TAPS + 7], tap_dx[TSNET_MAX_TAPS + 7], tap_plane[TSNET_MAX_TAPS + 7];
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
       float* yrow = args.y + gm * args.Cout;
+      const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -232,6 +235,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             v[j] = fmaf(acc[c0 + j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
+          if (arow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow + n0 + j));
+              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -325,6 +335,9 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
     if (d->split && (r = encode_tmap_u16_sw128(&a.b_lo, w_lo, 2, dims, str, box))) return r;
   }
   a.bias = bias;
+  a.addend = d->addend;
+  a.addend_rows = d->addend_rows;
+  TSNET_ARG_CHECK(!d->addend || d->addend_rows > 0, "conv_gemm: addend needs addend_rows > 0");
   a.y = y_raw;
   a.stats = stats_partial;
   a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;

@@ -26,16 +26,17 @@ class ForwardEngine:
         self._coord = {}
 
     # ------------------------------------------------------------------ weights
-    def _pack(self, net, wkey, fold_kw=False, block_n=None):
+    def _pack(self, net, wkey, fold_kw=False, block_n=None, cin_range=None, with_bias=True):
         """Packed weight for parameter `wkey` of sub-net `net`; re-packed when the parameter changed
         (load_state_dict / optimizer step bump the tensor version)."""
         sd = self.nets[net].state_dict(keep_vars=True)
         w, b = sd[wkey + ".weight"], sd[wkey + ".bias"]
         sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, self.mode.name)
-        key = (net, wkey)
+        key = (net, wkey, cin_range, with_bias)
         hit = self._packs.get(key)
         if hit is None or hit[0] != sig:
-            hit = (sig, PackedConv(w, b, self.mode, fold_kw=fold_kw, block_n=block_n))
+            hit = (sig, PackedConv(w, b if with_bias else None, self.mode, fold_kw=fold_kw, block_n=block_n,
+                                   cin_range=cin_range))
             self._packs[key] = hit
         return hit[1]
 
@@ -46,9 +47,10 @@ class ForwardEngine:
         return self._coord[key]
 
     # ------------------------------------------------------------------ building blocks
-    def _conv(self, taps, pc, kind, B, H, W, norm=True):
+    def _conv(self, taps, pc, kind, B, H, W, norm=True, addend=None):
         hi, lo, geom = taps
-        y, stats = ops.conv_gemm(hi, lo, geom, pc, kind, B, H, W, self.mode, self.mode.act_scale, want_stats=norm)
+        y, stats = ops.conv_gemm(hi, lo, geom, pc, kind, B, H, W, self.mode, self.mode.act_scale, want_stats=norm,
+                                 addend=addend)
         mr = ops.instnorm_reduce(stats, B, H * W, pc.Cout) if norm else None
         return y, mr
 
@@ -109,9 +111,9 @@ class ForwardEngine:
         h, w, Cf = H0 // 8, W0 // 8, 512
         hw = h * w
 
-        # ---- encoders.  FuseNet input = cat[src_fea, tar_fea] (model/TSNet.py:196): the last img_enc block writes its
-        # reflect-padded split output straight into channels [0,512) of the 1024-channel tap source.
-        fuse_hi = torch.empty((n * B, h + 2, w + 2, 2 * Cf), dtype=torch.int16, device=dev)
+        # ---- encoders.  The last img_enc block writes its reflect-padded split output straight into the tap source
+        # of FuseNet's first conv.
+        fuse_hi = torch.empty((n * B, h + 2, w + 2, Cf), dtype=torch.int16, device=dev)
         fuse_lo = torch.empty_like(fuse_hi)
         if n > 1 and len(set(img_divs)) > 1:
             # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
@@ -131,16 +133,22 @@ class ForwardEngine:
                                        [bb.contiguous() for bb in src_bboxes], self._coord_table(h, w, dev), B, Cf, h,
                                        w, m, want_grids=return_flow)
 
-        # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400)
-        cat_act = torch.empty((n * B, h, w, 2 * Cf), dtype=torch.float32, device=dev)
+        # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400).
+        # conv1(reflpad(cat[s_i, t])) = W[:, :512] * reflpad(s_i) + W[:, 512:] * reflpad(t): pad and conv are linear, so
+        # the target half is evaluated ONCE per frame and added (fp32) in the epilogue of the per-source GEMM.
+        cat_act = torch.empty((n * B, h, w, 2 * Cf), dtype=torch.float32, device=dev)   # x of "x + conv_block(x)"
         ops.build_taps(src_fea, m, L.TAPS_SAME, act_out=cat_act, act_c_off=0, want_taps=False)
         for i in range(n):
-            sl = slice(i * B, (i + 1) * B)
-            ops.build_taps(tar_fea, m, L.TAPS_REFLECT1, act_out=cat_act[sl], act_c_off=Cf,
-                           taps=(fuse_hi[sl], fuse_lo[sl]), c_off=Cf)
-        tf = (fuse_hi, fuse_lo, (1, h + 2, w + 2))
-        tfo, _ = self._resblock("fuse_net", "model.0.", tf, cat_act, n * B, h, w, tmode_out=L.TAPS_SAME,
-                                need_act=False)
+            ops.build_taps(tar_fea, m, L.TAPS_SAME, act_out=cat_act[i * B:(i + 1) * B], act_c_off=Cf, want_taps=False)
+        t_taps = ops.build_taps(tar_fea, m, L.TAPS_REFLECT1)
+        pc_t = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(Cf, 2 * Cf), with_bias=False)
+        y_t, _ = self._conv(t_taps, pc_t, "3x3", B, h, w, norm=False)                     # [B, h, w, 1024]
+        pc_s = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(0, Cf))
+        y1, mr1 = self._conv((fuse_hi, fuse_lo, (1, h + 2, w + 2)), pc_s, "3x3", n * B, h, w, addend=y_t)
+        t1 = ops.build_taps(y1, m, L.TAPS_REFLECT1, mean_rstd=mr1, relu=True)
+        pc5 = self._pack("fuse_net", "model.0.conv_block.5")
+        y2, mr2 = self._conv(t1, pc5, "3x3", n * B, h, w)
+        tfo = ops.build_taps(y2, m, L.TAPS_SAME, mean_rstd=mr2, residual=cat_act)
         pcf = self._pack("fuse_net", "conv")
         sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
 

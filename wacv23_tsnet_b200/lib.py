@@ -20,7 +20,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int), ("Cout_pad", C.c_int),
                 ("Cp", C.c_int), ("Hp", C.c_int), ("Wp", C.c_int), ("planes", C.c_int), ("num_taps", C.c_int),
                 ("tap_dy", C.c_int8 * MAX_TAPS), ("tap_dx", C.c_int8 * MAX_TAPS), ("tap_plane", C.c_int8 * MAX_TAPS),
-                ("block_n", C.c_int), ("split", C.c_int), ("fmt", C.c_int), ("out_scale", C.c_float)]
+                ("block_n", C.c_int), ("split", C.c_int), ("fmt", C.c_int), ("out_scale", C.c_float),
+                ("addend", C.c_void_p), ("addend_rows", C.c_int)]
 
 
 class TapsDesc(C.Structure):

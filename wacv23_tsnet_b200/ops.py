@@ -83,9 +83,12 @@ class MathMode:
 class PackedConv:
     """A conv weight packed for tsnet_conv_gemm_fwd (K-major hi/lo, zero padded)."""
 
-    def __init__(self, weight, bias, mode, fold_kw=False, Cp=None, block_n=None):
+    def __init__(self, weight, bias, mode, fold_kw=False, Cp=None, block_n=None, cin_range=None):
         L.require_device()
-        w = _f32(weight.detach())
+        w = weight.detach()
+        if cin_range is not None:  # a slice of the input channels (conv over a channel-concatenation, split by operand)
+            w = w[:, cin_range[0]:cin_range[1]].contiguous()
+        w = _f32(w)
         Cout, Cin, KH, KW = w.shape
         self.Cout, self.Cin, self.KH, self.KW, self.fold_kw = Cout, Cin, KH, KW, bool(fold_kw)
         need = KW * Cin if fold_kw else Cin
@@ -133,7 +136,8 @@ def conv_taps(kind):
     raise ValueError(kind)
 
 
-def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None):
+def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None,
+              addend=None):
     """taps_* : int16 [B*planes, Hp, Wp, Cp]; geom = (planes, Hp, Wp). Returns (y_raw [B,H,W,Cout], stats)."""
     planes, Hp, Wp = geom
     d = L.ConvDesc()
@@ -146,6 +150,9 @@ def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_s
         d.tap_dy[t], d.tap_dx[t], d.tap_plane[t] = dy, dx, pl
     d.block_n, d.split, d.fmt = pc.block_n, mode.split, mode.fmt
     d.out_scale = 1.0 / (pc.scale * act_scale)
+    if addend is not None:  # fp32 [rows, Cout], broadcast over the leading batch dimension by row index modulo
+        assert addend.shape[-1] == pc.Cout and addend.is_contiguous() and addend.dtype == torch.float32
+        d.addend, d.addend_rows = addend.data_ptr(), addend.numel() // pc.Cout
     assert taps_hi.shape == (B * planes, Hp, Wp, pc.Cp), (tuple(taps_hi.shape), (B * planes, Hp, Wp, pc.Cp))
     if y is None:
         y = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=taps_hi.device)
