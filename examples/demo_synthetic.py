@@ -1,0 +1,57 @@
+"""The reference's demo loop (demo/demo_face.py:170-231) on synthetic frames, through the drop-in class.
+
+One driving frame per forward (bs=1), three fixed source frames, uint8 bboxes, colour re-normalisation and uint8
+conversion -- the demo's exact operating point -- with the forward replayed as a CUDA graph and the post-processing
+done by `tsnet_postprocess_u8` on the device.  Usage (on a B200):  python examples/demo_synthetic.py [--frames 60]
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from model.TSNet import TSNet  # noqa: E402  (the reference's own import line)
+from oracle import synth  # noqa: E402  (synthetic frames only)
+from wacv23_tsnet_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=60)
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    torch.manual_seed(1234)
+    model = TSNet(is_train=False, label_nc=2, n_blocks=4, n_downsampling=3, n_source=3, cuda_graph=not args.no_graph)
+    model.eval()
+    vid = synth.dataset_like_inputs(args.frames, 2, 3, seed=7)
+    t = torch.from_numpy
+    # demo style: sources are 5-D tensors [n, 1, C, H, W] iterated over dim 0 (demo_face.py:176-178)
+    src_img = torch.stack([t(a[:1]) for a in vid["src_img"]])
+    src_lbl = torch.stack([t(a[:1]) for a in vid["src_lbl"]])
+    src_bbox = torch.stack([t(a[:1]) for a in vid["src_bbox"]])
+    tar_lbl, tar_bbox = t(vid["tar_lbl"]), t(vid["tar_bbox"])
+    ref = src_img[:, 0].cuda() / 255.0
+    ref_mean = ref.permute(1, 0, 2, 3).reshape(3, -1).mean(1)
+    ref_std = ref.permute(1, 0, 2, 3).reshape(3, -1).std(1)
+    img_mean = [float(v) / 255.0 for v in synth.IMG_MEAN]
+    frames = []
+    with torch.no_grad():
+        for warm in (True, False):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for ind in range(args.frames):
+                model.set_test_input(src_img, src_lbl, src_bbox, tar_lbl[ind:ind + 1], tar_bbox[ind:ind + 1])
+                model.forward()
+                frames.append(ops.postprocess_u8(model.rec_tar_img, ref_mean, ref_std, img_mean).cpu())
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if not warm:
+                print(f"{args.frames} frames, bs=1, n_source=3, n_blocks=4, graph={not args.no_graph}: "
+                      f"{dt / args.frames * 1e3:.2f} ms/frame = {args.frames / dt:.1f} frames/s "
+                      f"(uint8 RGB {tuple(frames[-1].shape)} on the host)")
+
+
+if __name__ == "__main__":
+    main()
