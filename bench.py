@@ -86,9 +86,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(bs, label_nc, n_source, seed):
+def make_inputs(bs, label_nc, n_source, seed, pose=False):
     from oracle import synth  # data generator only
-    return synth.dataset_like_inputs(bs, label_nc, n_source, seed=seed)
+    return synth.dataset_like_inputs(bs, label_nc, n_source, seed=seed, pose=pose)
 
 
 def usable_cpus():
@@ -159,24 +159,30 @@ def run_b200(args):
     from wacv23_tsnet_b200 import dist as D
     from wacv23_tsnet_b200 import ops
     from wacv23_tsnet_b200.model.TSNet import TSNet
+    from wacv23_tsnet_b200.model.TSNet_pose import TSNet as TSNetPose
     import torch.distributed as tdist
 
     rank, local_rank, world = D.init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    L, nb, n, bs = 2, args.n_blocks, args.n_source, args.batch
+    L, nb, n, bs = (25 if args.pose else 2), args.n_blocks, args.n_source, args.batch
     peaks = load_peaks()
 
     import contextlib
     import io
     torch.manual_seed(1234)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, math_mode=args.math)
+        if args.pose:  # BASELINE.json config 3 (Youtube-dance): label_nc=25, foreground compositing
+            from oracle.synth import IMG_MEAN
+            net = TSNetPose(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, use_mask=True,
+                            mean=IMG_MEAN, math_mode=args.math)
+        else:
+            net = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, math_mode=args.math)
     D.broadcast_generator(net, src=0)
     net.eval()
     log("model built")
 
-    inp = make_inputs(bs, L, n, seed=1234 + rank)
+    inp = make_inputs(bs, L, n, seed=1234 + rank, pose=args.pose)
     host = {k: ([torch.from_numpy(a).pin_memory() for a in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
             for k, v in inp.items() if k != "tar_img"}
     devin = {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in host.items()}
@@ -297,7 +303,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             sds_np = {k: {kk: vv.detach().cpu().numpy() for kk, vv in getattr(net, k).state_dict().items()}
                       for k in D.GENERATOR_NETS}
-            fps, cores, spf = cpu_forward_fps(sds_np, L, nb, n, 1, 5, 1)
+            fps, cores, spf = cpu_forward_fps(sds_np, L, nb, n, 1, 5, 1)  # (compositing is negligible on the CPU side)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "5 forwards of bs=1 of the same config (oracle/tsnet_oracle.py = bit-exact CPU "
                              "restatement of the reference forward), 1 warm-up"}
@@ -306,7 +312,7 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (fp16 hi/lo 3-term split operands, fp32 accumulate)" if args.math == "fp16x3" else args.math,
                 "data": "synthetic",
-                "config": {"workload": f"FaceForensics config: bs={bs}/GPU, 256x256, label_nc=2, n_source={n}, "
+                "config": {"workload": f"{'Youtube-dance (pose)' if args.pose else 'FaceForensics'} config: bs={bs}/GPU, 256x256, label_nc={L}, n_source={n}, "
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
                            "math_mode": args.math,
@@ -334,6 +340,7 @@ def main():
     ap.add_argument("--n-blocks", dest="n_blocks", type=int, default=4)
     ap.add_argument("--math", default="fp16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"],
                     help="fp16x3 is the parity-grade default; single-pass modes are non-parity speed points")
+    ap.add_argument("--pose", action="store_true", help="TSNet_pose, label_nc=25 (BASELINE.json config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-mode", dest="e2e_mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined: wacv23_tsnet_b200.pipeline.FramePipeline; sync: set_test_input + forward + .cpu()")

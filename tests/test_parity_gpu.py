@@ -264,3 +264,26 @@ def test_classmap_labels_give_identical_forward():
                            [t(a_) for a_ in inp["src_bbox"]], cls(inp["tar_lbl"]), t(inp["tar_bbox"]))
         net.forward()
         assert torch.equal(net.rec_tar_img, a)
+
+
+def test_use_prev_sources_skip_the_255_division():
+    """set_train_input(use_prev=...) (model/TSNet.py:266-276): flagged sources are used as they are, the others /255."""
+    from oracle import synth
+    from wacv23_tsnet_b200.model.TSNet import TSNet
+    torch.manual_seed(5)
+    net = TSNet(is_train=False, label_nc=2, n_blocks=0, n_downsampling=3, n_source=3)
+    net.eval()
+    inp = synth.dataset_like_inputs(1, 2, 3, seed=21)
+    t = torch.from_numpy
+    imgs = [t(a) for a in inp["src_img"]]
+    pre = [imgs[0], imgs[1] / 255.0, imgs[2]]                     # source 1 arrives already scaled ("previous output")
+    with torch.no_grad():
+        net.set_train_input(pre, [t(a) for a in inp["src_lbl"]], [t(a) for a in inp["src_bbox"]], t(inp["tar_img"]),
+                            t(inp["tar_lbl"]), t(inp["tar_bbox"]), use_prev=[False, True, False])
+        net.forward()
+        a = net.rec_tar_img.clone()
+        net.set_test_input(imgs, [t(x) for x in inp["src_lbl"]], [t(x) for x in inp["src_bbox"]], t(inp["tar_lbl"]),
+                           t(inp["tar_bbox"]))
+        net.forward()
+    # identical up to the rounding of x/255 done on the host (true division) vs in the mixed-divisor staging path
+    assert float((net.rec_tar_img - a).abs().max()) < 2e-3

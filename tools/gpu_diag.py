@@ -142,7 +142,7 @@ def _gemm_case(torch, name, B, H, W, Cin, Cout, kind, mode_name, block_n=None, v
     y, stats = ops.conv_gemm(hi, lo, g, pc, "3x3" if kind == "up3x3" else kind, B, Ho, Wo, m, m.act_scale)
     torch.cuda.synchronize()
     tol = {"fp16x3": 2e-6, "bf16x3": 5e-5, "fp16": 2e-3, "bf16": 2e-2}[mode_name]
-    ok = _report(f"{name} {kind} B{B} {H}x{W} {Cin}->{Cout} bn={pc.block_n} {mode_name}", y, ref, tol)
+    ok = _report(f"{name} {kind} B{B} {H}x{W} {Cin}->{Cout} bn={pc.block_n or 'auto'} {mode_name}", y, ref, tol)
     if not ok and verbose:
         d = (y - ref).abs()
         print("    err by row-in-tile (first 8 of 128):", d.view(-1, 128, Cout).amax((0, 2))[:8].tolist())

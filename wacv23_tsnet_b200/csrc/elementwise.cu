@@ -47,43 +47,42 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 }
 
 // ------------------------------------------------------------------------------------------------
-// InstanceNorm statistics: [B*nsub, C, 2] (sum, M2 of 32 pixels) -> [B, C, 2] (mean, rstd)
-// block = (32 channels) x (8 segments); fixed merge order => bit-reproducible.
+// InstanceNorm statistics: [B*nsub, C, 2] (sum, centred M2 of 32 pixels) -> [B, C, 2] (mean, rstd)
+// block = (32 channels) x (8 segments).  All partials cover 32 pixels, so the merge is
+//   mean = (sum_k sum_k) / N ;  M2 = sum_k [ M2_k + 32 (sum_k/32 - mean)^2 ]
+// evaluated in fp64 with a fixed summation order (bit-reproducible), one division and one sqrt per (b, c).
 // ------------------------------------------------------------------------------------------------
 __global__ void instnorm_reduce_kernel(const float* __restrict__ part, int nsub, int C, float eps,
                                        float* __restrict__ out) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int seg = threadIdx.y;
-  __shared__ double s_n[8][32], s_mean[8][32], s_m2[8][32];
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  if (c < C) {
-    const int per = (nsub + 7) / 8;
-    const int k0 = seg * per, k1 = min(nsub, k0 + per);
-    const float* p = part + (static_cast<size_t>(b) * nsub) * C * 2 + static_cast<size_t>(c) * 2;
-    for (int k = k0; k < k1; ++k) {
-      const float2 sm = *reinterpret_cast<const float2*>(p + static_cast<size_t>(k) * C * 2);
-      const double nb = 32.0, mb = static_cast<double>(sm.x) / 32.0, m2b = sm.y;
-      const double nn = n + nb, delta = mb - mean;
-      mean += delta * nb / nn;
-      m2 += m2b + delta * delta * n * nb / nn;
-      n = nn;
-    }
+  __shared__ double s_acc[8][32];
+  const int per = (nsub + 7) / 8;
+  const int k0 = seg * per, k1 = min(nsub, k0 + per);
+  const float* p = part + (static_cast<size_t>(b) * nsub) * C * 2 + static_cast<size_t>(min(c, C - 1)) * 2;
+  double acc = 0.0;
+  for (int k = k0; k < k1; ++k) acc += static_cast<double>(p[static_cast<size_t>(k) * C * 2]);
+  s_acc[seg][threadIdx.x] = acc;
+  __syncthreads();
+  double total = 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) total += s_acc[s][threadIdx.x];
+  const double n = 32.0 * nsub;
+  const double mean = total / n;
+  __syncthreads();
+  acc = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const float2 sm = *reinterpret_cast<const float2*>(p + static_cast<size_t>(k) * C * 2);
+    const double d = static_cast<double>(sm.x) * (1.0 / 32.0) - mean;
+    acc += static_cast<double>(sm.y) + 32.0 * d * d;
   }
-  s_n[seg][threadIdx.x] = n;
-  s_mean[seg][threadIdx.x] = mean;
-  s_m2[seg][threadIdx.x] = m2;
+  s_acc[seg][threadIdx.x] = acc;
   __syncthreads();
   if (seg == 0 && c < C) {
-    for (int s = 1; s < 8; ++s) {
-      const double nb = s_n[s][threadIdx.x];
-      if (nb == 0.0) continue;
-      const double mb = s_mean[s][threadIdx.x], m2b = s_m2[s][threadIdx.x];
-      const double nn = n + nb, delta = mb - mean;
-      mean += delta * nb / nn;
-      m2 += m2b + delta * delta * n * nb / nn;
-      n = nn;
-    }
+    double m2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) m2 += s_acc[s][threadIdx.x];
     const double var = m2 / n;  // biased, as nn.InstanceNorm2d
     float2 r;
     r.x = static_cast<float>(mean);

@@ -95,10 +95,10 @@ class PackedConv:
         self.Cp = Cp if Cp is not None else (need + 63) // 64 * 64
         assert self.Cp >= need and self.Cp % 64 == 0
         self.num_taps = KH if fold_kw else KH * KW
-        if block_n is None:
-            block_n = 64 if Cout <= 64 else (128 if Cout <= 128 else 256)
+        # block_n = None: chosen per launch from the tile count (see conv_gemm); rows are padded so any width fits
         self.block_n = block_n
-        self.Cout_pad = (Cout + block_n - 1) // block_n * block_n
+        pad_to = block_n if block_n is not None else (64 if Cout <= 64 else (128 if Cout <= 128 else 256))
+        self.Cout_pad = (Cout + pad_to - 1) // pad_to * pad_to
         self.scale = mode.weight_scale(w)
         K = self.num_taps * self.Cp
         self.w_hi = torch.empty((self.Cout_pad, K), dtype=torch.int16, device=w.device)
@@ -136,6 +136,24 @@ def conv_taps(kind):
     raise ValueError(kind)
 
 
+_NUM_SMS = None
+
+
+def _pick_block_n(pc, m_tiles):
+    """Widest N tile (best operand reuse) that still gives every SM a tile; small batches (the demos' bs=1) fall back
+    to narrower tiles so that e.g. a 512->512 conv over 3 samples is 192 tiles instead of 48."""
+    global _NUM_SMS
+    if pc.block_n is not None:
+        return pc.block_n
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    widest = 64 if pc.Cout <= 64 else (128 if pc.Cout <= 128 else 256)
+    bn = widest
+    while bn > 64 and m_tiles * (pc.Cout_pad // bn) < _NUM_SMS:
+        bn //= 2
+    return bn
+
+
 def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None,
               addend=None):
     """taps_* : int16 [B*planes, Hp, Wp, Cp]; geom = (planes, Hp, Wp). Returns (y_raw [B,H,W,Cout], stats)."""
@@ -148,7 +166,7 @@ def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_s
     d.num_taps = len(taps)
     for t, (dy, dx, pl) in enumerate(taps):
         d.tap_dy[t], d.tap_dx[t], d.tap_plane[t] = dy, dx, pl
-    d.block_n, d.split, d.fmt = pc.block_n, mode.split, mode.fmt
+    d.block_n, d.split, d.fmt = _pick_block_n(pc, B * H * W // 128), mode.split, mode.fmt
     d.out_scale = 1.0 / (pc.scale * act_scale)
     if addend is not None:  # fp32 [rows, Cout], broadcast over the leading batch dimension by row index modulo
         assert addend.shape[-1] == pc.Cout and addend.is_contiguous() and addend.dtype == torch.float32
