@@ -243,9 +243,9 @@ def run_b200(args):
             pipe = FramePipeline(net)
 
             def run_pipe():
-                for _ in pipe.run(host for _ in range(args.steps)):
+                for _ in pipe.run((host for _ in range(args.steps)), copy_out=False):
                     pass
-            run_pipe_once = lambda: [None for _ in pipe.run([host, host])]
+            run_pipe_once = lambda: [None for _ in pipe.run([host, host, host], copy_out=False)]
             run_pipe_once()
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
