@@ -83,6 +83,24 @@ typedef struct {
                           statistics.  Lets a conv over cat[a_i, t] be computed as conv(a_i) + conv(t) with the
                           source-independent half evaluated once per frame (FuseNet, model/TSNet.py:196-198) */
   int addend_rows;
+  /* ---- fused InstanceNorm epilogue (optional; requires H*W == 1024, i.e. 8 tiles of 128 pixels per image) ----
+   * fuse_in = 1: the 8 CTAs of a thread-block cluster compute the 8 pixel tiles of one image for one channel slab,
+   * exchange the per-tile statistics over distributed shared memory and apply, in registers,
+   *   v = (conv + bias [+ addend] - mean) * rstd ; if fuse_relu: v = max(v, 0) ; if fuse_residual: v += residual
+   * then write fuse_act_out (fp32, optional) and the NEXT layer's tap source (hi / lo, mode SAME or REFLECT1,
+   * optional) directly: y_raw / stats_partial are not written, and the separate tsnet_instnorm_reduce +
+   * tsnet_build_taps launches of that layer disappear (model/TSNet.py:27-48: conv -> IN -> ReLU / + x -> pad). */
+  int fuse_in;
+  int fuse_relu;
+  int fuse_mode;               /* TSNET_TAPS_SAME or TSNET_TAPS_REFLECT1 */
+  const float* fuse_residual;  /* fp32 [B, H, W, Cout] or NULL */
+  float* fuse_act_out;         /* fp32 [B, H, W, fuse_act_C_total] or NULL */
+  int fuse_act_C_total, fuse_act_c_off;
+  uint16_t* fuse_taps_hi;      /* [B, Hd, Wd, fuse_taps_Cp] or NULL */
+  uint16_t* fuse_taps_lo;
+  int fuse_taps_Cp, fuse_taps_c_off;
+  float fuse_act_scale;        /* power-of-two scale of the written operands */
+  float fuse_eps;              /* 1e-5 */
 } tsnet_conv_desc;
 
 int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,

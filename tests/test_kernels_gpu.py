@@ -330,3 +330,54 @@ def test_conv_gemm_addend_broadcast_over_sources():
     torch.cuda.synchronize()
     assert _relerr(y, ref) < CONV_TOL["fp16x3"]
     assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5   # statistics include the addend
+
+
+@pytest.mark.parametrize("Cin,Cout,kind,tmode,relu,res", [
+    (128, 256, "3x3", "reflect", True, False),     # ResnetBlock conv1: conv -> IN -> ReLU -> pad
+    (256, 256, "3x3", "reflect", False, True),     # ResnetBlock conv2: conv -> IN -> + x -> pad (+ fp32 output)
+    (128, 512, "3x3s2", "reflect", True, False),   # third down-sampling conv of the encoders
+    (256, 1024, "3x3", "same", False, True),       # FuseNet conv2 -> operand of the 1x1 conv
+])
+def test_conv_gemm_fused_instance_norm_epilogue(Cin, Cout, kind, tmode, relu, res):
+    """tsnet_conv_desc.fuse_in: 8-CTA clusters exchange the InstanceNorm statistics over DSMEM and write the next
+    layer's operands directly; must equal conv -> F.instance_norm -> ReLU / + residual -> ReflectionPad2d."""
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(9)
+    B = 5
+    Hin = 64 if kind == "3x3s2" else 32
+    x = torch.randn(B, Hin, Hin, Cin, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    b = torch.randn(Cout, device="cuda")
+    xn = x.permute(0, 3, 1, 2).double()
+    if kind == "3x3s2":
+        conv = F.conv2d(xn, w.double(), b.double(), stride=2, padding=1)
+        tin = ops.build_taps(x, m, L.TAPS_S2ZERO)
+    else:
+        conv = F.conv2d(F.pad(xn, (1, 1, 1, 1), mode="reflect"), w.double(), b.double())
+        tin = ops.build_taps(x, m, L.TAPS_REFLECT1)
+    ref = F.instance_norm(conv, eps=1e-5)
+    if relu:
+        ref = F.relu(ref)
+    resid = torch.randn(B, 32, 32, Cout, device="cuda") if res else None
+    if res:
+        ref = ref + resid.permute(0, 3, 1, 2).double()
+    act = torch.zeros(B, 32, 32, Cout + 64, device="cuda")
+    tm = L.TAPS_REFLECT1 if tmode == "reflect" else L.TAPS_SAME
+    _, Hd, Wd = ops.taps_geometry(tm, 32, 32)
+    th = torch.zeros(B, Hd, Wd, Cout + 64, dtype=torch.int16, device="cuda")
+    tl = torch.zeros_like(th)
+    pc = ops.PackedConv(w, b, m)
+    outs = []
+    for _ in range(2):
+        ops.conv_gemm(tin[0], tin[1], tin[2], pc, kind, B, 32, 32, m, m.act_scale,
+                      fuse=dict(relu=relu, tmode=tm, residual=resid, act_out=act, act_c_off=64, taps=(th, tl), c_off=64))
+        torch.cuda.synchronize()
+        outs.append((act.clone(), th.clone(), tl.clone()))
+    assert all(torch.equal(a, b_) for a, b_ in zip(outs[0], outs[1]))            # deterministic
+    ref_nhwc = ref.permute(0, 2, 3, 1).float()
+    assert _relerr(act[..., 64:], ref_nhwc) < 5e-6 and float(act[..., :64].abs().max()) == 0.0
+    refp = ref if tmode == "same" else F.pad(ref, (1, 1, 1, 1), mode="reflect")
+    got = _recon(th, tl, m.fmt)
+    assert _relerr(got[..., 64:], refp.permute(0, 2, 3, 1).float() * m.act_scale) < 5e-6
+    assert int(th[..., :64].abs().max()) == 0

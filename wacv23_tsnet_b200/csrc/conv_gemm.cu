@@ -44,6 +44,13 @@ struct alignas(64) ConvGemmArgs {
   int addend_rows;
   int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
   int Cout, num_taps, kc_per_tap, planes, split, fmt, chunk_kb;
+  // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
+  const float* f_residual;   // fp32 [B, H, W, Cout] or null
+  float* f_act_out;          // fp32, channel window [f_act_c_off, +Cout) of f_act_C_total, or null
+  uint16_t* f_taps_hi;       // destination tap source (hi / lo) or null
+  uint16_t* f_taps_lo;
+  int f_relu, f_mode, f_act_C_total, f_act_c_off, f_taps_Cp, f_taps_c_off, f_H, f_W;
+  float f_act_scale, f_eps;
   int8_t tap_dy[TSNET_MAX_TAPS + 7], tap_dx[TSNET_MAX_TAPS + 7], tap_plane[TSNET_MAX_TAPS + 7];
 };
 
@@ -55,7 +62,60 @@ struct GemmCfg {
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 6 ? 6 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // fused-IN variant: + per-warp partials [4][N] float2, per-CTA partials [2][N] double2 (read by peers over DSMEM),
+  // (mean, rstd) [N] float2
+  static constexpr int kFusedExtra = 4 * BLOCK_N * 8 + 2 * BLOCK_N * 16 + BLOCK_N * 8;
+  static constexpr int kSmemBytesFused = kSmemBytes + kFusedExtra;
+  static_assert(kSmemBytesFused <= 227 * 1024, "fused conv shared memory budget");
 };
+
+// ---- cluster helpers (fused variant) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    if (spins > 8) __nanosleep(32);
+    if ((spins & 0xFFF) == 0xFFF) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TSNET_MBAR_TIMEOUT_CYCLES) __trap();
+    }
+  }
+}
+__device__ __forceinline__ double2 ld_cluster_double2(uint32_t cluster_addr) {
+  double2 v;
+  asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Lane j of the warp ends with sum over the 32 lanes of v[j] (transpose-reduce butterfly, 31 shuffles).
 __device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
@@ -73,7 +133,28 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
   return v[0];
 }
 
-template <int BLOCK_N>
+// Tile enumeration.  Plain variant: tile = blockIdx.x + k * gridDim.x.  FUSED variant: the 8 CTAs of a cluster take the
+// 8 pixel tiles of ONE image for the same channel slab, so that the InstanceNorm statistics of that (image, slab)
+// are complete inside the cluster: item = cluster_id + k * num_clusters, (img, n_tile) = item / % num_n_tiles.
+template <bool FUSED>
+__device__ __forceinline__ bool tile_at(const ConvGemmArgs& args, int k, int& m_tile, int& n_tile) {
+  if constexpr (FUSED) {
+    const int item = static_cast<int>(blockIdx.x >> 3) + k * static_cast<int>(gridDim.x >> 3);
+    if (item >= (args.num_m_tiles >> 3) * args.num_n_tiles) return false;
+    const int img = item / args.num_n_tiles;
+    n_tile = item - img * args.num_n_tiles;
+    m_tile = img * 8 + static_cast<int>(cluster_ctarank());
+    return true;
+  } else {
+    const int tile = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+    if (tile >= args.num_m_tiles * args.num_n_tiles) return false;
+    m_tile = tile / args.num_n_tiles;
+    n_tile = tile - m_tile * args.num_n_tiles;
+    return true;
+  }
+}
+
+template <int BLOCK_N, bool FUSED>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs args) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -83,10 +164,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* stats_ready = tmem_empty + 3;  // fused variant: 8 arrivals (one per CTA of the cluster) per item
+  // fused-variant scratch behind the barrier block
+  uint8_t* fx = smem + Cfg::kStages * Cfg::kStageBytes + 256;
+  float2* s_part = reinterpret_cast<float2*>(fx);                                  // [4][BLOCK_N]
+  double2* s_cta = reinterpret_cast<double2*>(fx + 4 * BLOCK_N * 8);               // [2][BLOCK_N]
+  float2* s_mr = reinterpret_cast<float2*>(fx + 4 * BLOCK_N * 8 + 2 * BLOCK_N * 16);  // [BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int num_kb = args.num_taps * args.kc_per_tap;
-  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
 
   if (warp == 0 && lane_id() == 0) {
     tma_prefetch_desc(&args.a_hi);
@@ -105,6 +191,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kAccWarps);  // one arrive per accumulate warp
     }
+    if constexpr (FUSED) mbar_init(stats_ready, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
@@ -112,6 +199,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if constexpr (FUSED) cluster_sync_all();  // every CTA's barriers exist before any remote arrive
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -121,9 +209,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = args.split ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / args.num_n_tiles;
-        const int n_tile = tile - m_tile * args.num_n_tiles;
+      int m_tile, n_tile;
+      for (int k = 0; tile_at<FUSED>(args, k, m_tile, n_tile); ++k) {
         const int img = m_tile / args.tiles_per_img;
         const int t = m_tile - img * args.tiles_per_img;
         const int ty = t / args.wtiles_per_row;
@@ -158,7 +245,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       int cc = 0;  // global chunk counter -> TMEM buffer + phase
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_tile, n_tile;
+      for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile); ++kt) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
           const int buf = cc & 1;
           const uint32_t buf_phase = (cc >> 1) & 1;
@@ -199,9 +287,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int half = (warp - 4) >> 2;   // which half of the BLOCK_N columns
     const int row = q * 32 + lane_id();
     int cc = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / args.num_n_tiles;
-      const int n_tile = tile - m_tile * args.num_n_tiles;
+    int m_tile, n_tile;
+    for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile); ++kt) {
       float acc[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) acc[j] = 0.f;
@@ -222,10 +309,146 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&tmem_empty[buf]);
       }
-      // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
-      float* yrow = args.y + gm * args.Cout;
       const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
+      if constexpr (FUSED) {
+        // ================= fused epilogue: InstanceNorm (+ReLU, +residual) + tap building =================
+        const int et = threadIdx.x - 128;            // 0..255 among the accumulate threads
+        const int nb0 = n_tile * BLOCK_N;            // first channel of this slab
+        const int buf = kt & 1;
+        // (a) scale + bias (+ addend)
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+          const int n0 = nb0 + half * NC + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc[c0 + j] = fmaf(acc[c0 + j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
+          if (arow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow + n0 + j));
+              acc[c0 + j] += t4.x; acc[c0 + j + 1] += t4.y; acc[c0 + j + 2] += t4.z; acc[c0 + j + 3] += t4.w;
+            }
+          }
+          // (b) per-column (sum, centred M2) over this warp's 32 pixels
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = acc[c0 + j];
+          const float colsum = warp_col_sums(t);
+          const float mean_l = colsum * (1.f / 32.f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dlt = acc[c0 + j] - __shfl_sync(0xffffffffu, mean_l, j);
+            t[j] = dlt * dlt;
+          }
+          const float m2 = warp_col_sums(t);
+          s_part[q * BLOCK_N + half * NC + c0 + lane_id()] = make_float2(colsum, m2);
+        }
+        epi_bar();
+        // (c) CTA partial (128 pixels) per column, fixed order over the 4 lane quarters, fp64
+        if (et < BLOCK_N) {
+          double n = 0.0, mean = 0.0, m2 = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float2 pm = s_part[qq * BLOCK_N + et];
+            const double nb = 32.0, mb = static_cast<double>(pm.x) * (1.0 / 32.0), nn = n + nb, dl = mb - mean;
+            mean += dl * nb / nn;
+            m2 += static_cast<double>(pm.y) + dl * dl * n * nb / nn;
+            n = nn;
+          }
+          s_cta[buf * BLOCK_N + et] = make_double2(mean, m2);
+        }
+        epi_bar();
+        // (d) publish to the cluster: one release-arrive on every CTA's stats_ready (count 8), then wait for ours
+        if (et == 0) {
+          const uint32_t local = smem_u32(stats_ready);
+#pragma unroll
+          for (uint32_t r = 0; r < 8; ++r) mbar_arrive_remote(map_to_cta(local, r));
+        }
+        mbar_wait_cluster(stats_ready, kt & 1);
+        // (e) merge the 8 tiles of the image in rank order (identical in every CTA) -> mean, rstd
+        if (et < BLOCK_N) {
+          const uint32_t local = smem_u32(&s_cta[buf * BLOCK_N + et]);
+          double n = 0.0, mean = 0.0, m2 = 0.0;
+#pragma unroll
+          for (uint32_t r = 0; r < 8; ++r) {
+            const double2 pm = ld_cluster_double2(map_to_cta(local, r));
+            const double nb = 128.0, nn = n + nb, dl = pm.x - mean;
+            mean += dl * nb / nn;
+            m2 += pm.y + dl * dl * n * nb / nn;
+            n = nn;
+          }
+          const double var = m2 / n;  // biased, as nn.InstanceNorm2d
+          s_mr[et] = make_float2(static_cast<float>(mean),
+                                 static_cast<float>(1.0 / sqrt(var + static_cast<double>(args.f_eps))));
+        }
+        epi_bar();
+        // (f) normalise, ReLU, residual, then write what the next layer reads
+        const int tpi = m_tile & 7;
+        const int img = m_tile >> 3;
+        const int py = tpi * args.rows_per_tile + row / args.Wt;   // pixel of this thread inside the image
+        const int px = row % args.Wt;
+        const size_t pix = (static_cast<size_t>(img) * args.f_H + py) * args.f_W + px;
+        const int ncol = nb0 + half * NC;
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 mr = s_mr[half * NC + c0 + j];
+            float v = (acc[c0 + j] - mr.x) * mr.y;
+            if (args.f_relu) v = fmaxf(v, 0.f);
+            acc[c0 + j] = v;
+          }
+          if (args.f_residual) {
+            const float* rp = args.f_residual + pix * args.Cout + ncol + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+              acc[c0 + j] += t4.x; acc[c0 + j + 1] += t4.y; acc[c0 + j + 2] += t4.z; acc[c0 + j + 3] += t4.w;
+            }
+          }
+          if (args.f_act_out) {
+            float* op = args.f_act_out + pix * args.f_act_C_total + args.f_act_c_off + ncol + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(op + j) = make_float4(acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
+          }
+        }
+        if (args.f_taps_hi) {
+          // destination pixels: (py, px) itself, plus its mirror images in the reflect-pad ring (mode REFLECT1)
+          int ys[2], xs[2], nys = 1, nxs = 1, Hd = args.f_H, Wd = args.f_W;
+          ys[0] = py; xs[0] = px;
+          if (args.f_mode == TSNET_TAPS_REFLECT1) {
+            Hd += 2; Wd += 2;
+            ys[0] = py + 1; xs[0] = px + 1;
+            if (py == 1) ys[nys++] = 0;
+            if (py == args.f_H - 2) ys[nys++] = args.f_H + 1;
+            if (px == 1) xs[nxs++] = 0;
+            if (px == args.f_W - 2) xs[nxs++] = args.f_W + 1;
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < NC; c0 += 8) {
+            uint16_t h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split16(acc[c0 + j] * args.f_act_scale, args.fmt, h[j], l[j]);
+            uint4 ph, pl;
+            ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+            ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+            pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+            pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+            for (int a = 0; a < nys; ++a)
+              for (int b2 = 0; b2 < nxs; ++b2) {
+                const size_t d = ((static_cast<size_t>(img) * Hd + ys[a]) * Wd + xs[b2]) * args.f_taps_Cp +
+                                 args.f_taps_c_off + ncol + c0;
+                *reinterpret_cast<uint4*>(args.f_taps_hi + d) = ph;
+                *reinterpret_cast<uint4*>(args.f_taps_lo + d) = pl;
+              }
+          }
+        }
+        continue;
+      }
+      // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
+      float* yrow = args.y + gm * args.Cout;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -268,6 +491,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (FUSED) cluster_sync_all();  // no CTA leaves while a peer may still read its shared memory
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -279,14 +503,44 @@ static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg::kSmemBytes));
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_gemm_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a);
+  conv_gemm_kernel<BLOCK_N, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a);
   TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Fused-InstanceNorm variant: clusters of 8 CTAs, one cluster per (image, channel slab) item.
+template <int BLOCK_N>
+static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytesFused));
+    attr_set = true;
+  }
+  const int items = (a.num_m_tiles / 8) * a.num_n_tiles;
+  const int max_clusters = num_sms() / 8;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * 8);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytesFused;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, true>, a));
   return 0;
 }
 
@@ -297,7 +551,7 @@ using namespace tsnet;
 extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,
                                    const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
                                    float* stats_partial, void* stream) {
-  TSNET_ARG_CHECK(d && taps_hi && w_hi && y_raw, "conv_gemm: null argument");
+  TSNET_ARG_CHECK(d && taps_hi && w_hi && (y_raw || d->fuse_in), "conv_gemm: null argument");
   TSNET_ARG_CHECK(!d->split || (taps_lo && w_lo), "conv_gemm: split mode needs the lo operands");
   TSNET_ARG_CHECK(d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "conv_gemm: block_n %d", d->block_n);
   TSNET_ARG_CHECK(d->Cp > 0 && d->Cp % 64 == 0, "conv_gemm: Cp %d must be a multiple of 64", d->Cp);
@@ -360,6 +614,40 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
     a.tap_plane[t] = d->tap_plane[t];
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d->fuse_in) {
+    TSNET_ARG_CHECK(a.tiles_per_img == 8, "conv_gemm: fuse_in needs H*W == 1024 (8 tiles per image), got %d tiles",
+                    a.tiles_per_img);
+    TSNET_ARG_CHECK(d->Cout % d->block_n == 0, "conv_gemm: fuse_in needs Cout %% block_n == 0");
+    TSNET_ARG_CHECK(d->fuse_mode == TSNET_TAPS_SAME || d->fuse_mode == TSNET_TAPS_REFLECT1, "conv_gemm: fuse_mode %d",
+                    d->fuse_mode);
+    TSNET_ARG_CHECK((d->fuse_taps_hi == nullptr) == (d->fuse_taps_lo == nullptr), "conv_gemm: fuse taps hi/lo");
+    TSNET_ARG_CHECK(d->fuse_taps_hi || d->fuse_act_out, "conv_gemm: fuse_in without any output");
+    TSNET_ARG_CHECK(!d->fuse_taps_hi || (d->fuse_taps_Cp % 8 == 0 && d->fuse_taps_c_off % 8 == 0 &&
+                                         d->fuse_taps_c_off + d->Cout <= d->fuse_taps_Cp),
+                    "conv_gemm: fused tap window does not fit");
+    TSNET_ARG_CHECK(!d->fuse_act_out || (d->fuse_act_c_off % 4 == 0 && d->fuse_act_c_off + d->Cout <= d->fuse_act_C_total),
+                    "conv_gemm: fused act_out window does not fit");
+    TSNET_ARG_CHECK(d->H >= 4 && d->W >= 4, "conv_gemm: fused reflect pad needs H, W >= 4");
+    a.f_residual = d->fuse_residual;
+    a.f_act_out = d->fuse_act_out;
+    a.f_taps_hi = d->fuse_taps_hi;
+    a.f_taps_lo = d->fuse_taps_lo;
+    a.f_relu = d->fuse_relu;
+    a.f_mode = d->fuse_mode;
+    a.f_act_C_total = d->fuse_act_C_total;
+    a.f_act_c_off = d->fuse_act_c_off;
+    a.f_taps_Cp = d->fuse_taps_Cp;
+    a.f_taps_c_off = d->fuse_taps_c_off;
+    a.f_H = d->H;
+    a.f_W = d->W;
+    a.f_act_scale = d->fuse_act_scale == 0.f ? 1.f : d->fuse_act_scale;
+    a.f_eps = d->fuse_eps == 0.f ? 1e-5f : d->fuse_eps;
+    switch (d->block_n) {
+      case 64: return launch_conv_gemm_fused<64>(a, s);
+      case 128: return launch_conv_gemm_fused<128>(a, s);
+      default: return launch_conv_gemm_fused<256>(a, s);
+    }
+  }
   switch (d->block_n) {
     case 64: return launch_conv_gemm<64>(a, s);
     case 128: return launch_conv_gemm<128>(a, s);

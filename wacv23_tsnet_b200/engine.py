@@ -22,6 +22,10 @@ class ForwardEngine:
         self.label_nc = label_nc
         self.n_blocks_dec = n_blocks_dec
         self.mode = MathMode(math_mode)
+        # InstanceNorm + ReLU + residual + tap building fused into the GEMM epilogue for the 32x32 layers
+        # (8-CTA clusters, tsnet_conv_desc.fuse_in); TSNET_FUSED_IN=0 selects the unfused 3-kernel sequence.
+        import os
+        self.fused_in = os.environ.get("TSNET_FUSED_IN", "1") == "1"
         self._packs = {}
         self._coord = {}
 
@@ -54,20 +58,37 @@ class ForwardEngine:
         mr = ops.instnorm_reduce(stats, B, H * W, pc.Cout) if norm else None
         return y, mr
 
+    def _conv_in(self, taps, pc, kind, B, H, W, tmode, relu=False, residual=None, need_act=False, dest=None, c_off=0,
+                 want_taps=True, addend=None, act_out=None, act_c_off=0):
+        """conv -> InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> tap source of the next layer (tmode).
+        One fused kernel when the output is 32x32 (8 tiles per image), else conv + instnorm_reduce + build_taps.
+        Returns ((hi, lo, geom) or None, act_out or None)."""
+        m = self.mode
+        if act_out is None and need_act:
+            act_out = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=taps[0].device)
+        if self.fused_in and H * W == 1024 and tmode in (L.TAPS_SAME, L.TAPS_REFLECT1):
+            planes, Hd, Wd = ops.taps_geometry(tmode, H, W)
+            if want_taps and dest is None:
+                hi = torch.empty((B, Hd, Wd, pc.Cout), dtype=torch.int16, device=taps[0].device)
+                dest = (hi, torch.empty_like(hi))
+            ops.conv_gemm(taps[0], taps[1], taps[2], pc, kind, B, H, W, m, m.act_scale, addend=addend,
+                          fuse=dict(relu=relu, tmode=tmode, residual=residual, act_out=act_out, act_c_off=act_c_off,
+                                    taps=dest if want_taps else None, c_off=c_off))
+            return ((dest[0], dest[1], (planes, Hd, Wd)) if want_taps else None), act_out
+        y, mr = self._conv(taps, pc, kind, B, H, W, addend=addend)
+        t = ops.build_taps(y, m, tmode, mean_rstd=mr, relu=relu, residual=residual, act_out=act_out,
+                           act_c_off=act_c_off, taps=dest, c_off=c_off, want_taps=want_taps)
+        return (t if want_taps else None), act_out
+
     def _resblock(self, net, prefix, taps, x_res, B, H, W, last_taps=None, last_c_off=0, need_act=True,
                   want_taps=True, tmode_out=L.TAPS_REFLECT1):
         """ResnetBlock (model/TSNet.py:10-49). taps = reflect-padded split input, x_res = fp32 input (residual).
         Returns (taps of the output, fp32 output or None)."""
-        m = self.mode
         pc1 = self._pack(net, prefix + "conv_block.1")
         pc5 = self._pack(net, prefix + "conv_block.5")
-        y1, mr1 = self._conv(taps, pc1, "3x3", B, H, W)
-        t1 = ops.build_taps(y1, m, L.TAPS_REFLECT1, mean_rstd=mr1, relu=True)
-        y2, mr2 = self._conv(t1, pc5, "3x3", B, H, W)
-        act_out = torch.empty_like(y2) if need_act else None
-        t2 = ops.build_taps(y2, m, tmode_out, mean_rstd=mr2, residual=x_res, act_out=act_out, taps=last_taps,
-                            c_off=last_c_off, want_taps=want_taps)
-        return t2, act_out
+        t1, _ = self._conv_in(taps, pc1, "3x3", B, H, W, L.TAPS_REFLECT1, relu=True)
+        return self._conv_in(t1, pc5, "3x3", B, H, W, tmode_out, residual=x_res, need_act=need_act, dest=last_taps,
+                             c_off=last_c_off, want_taps=want_taps)
 
     def _encoder(self, net, img, img_div, lbl, n_blocks, final_taps=None):
         """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it or None).
@@ -77,17 +98,18 @@ class ForwardEngine:
         pc = self._pack(net, "model.1", fold_kw=True)
         t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc)
         y, mr = self._conv(t, pc, "7x1", X, H, W)
-        for k, idx in enumerate((4, 7, 10)):
+        for k, idx in enumerate((4, 7)):
             t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
             pc = self._pack(net, f"model.{idx}")
             H, W = H // 2, W // 2
             y, mr = self._conv(t, pc, "3x3s2", X, H, W)
-        if n_blocks == 0:
-            fea = torch.empty_like(y)
-            ops.build_taps(y, m, L.TAPS_SAME, mean_rstd=mr, relu=True, act_out=fea, want_taps=False)
+        t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
+        pc = self._pack(net, "model.10")
+        H, W = H // 2, W // 2
+        if n_blocks == 0:   # lbl_enc: the feature is relu(IN(conv))
+            _, fea = self._conv_in(t, pc, "3x3s2", X, H, W, L.TAPS_SAME, relu=True, need_act=True, want_taps=False)
             return fea, None
-        x = torch.empty_like(y)
-        t = ops.build_taps(y, m, L.TAPS_REFLECT1, mean_rstd=mr, relu=True, act_out=x)
+        t, x = self._conv_in(t, pc, "3x3s2", X, H, W, L.TAPS_REFLECT1, relu=True, need_act=True)
         for blk in range(n_blocks):
             last = blk == n_blocks - 1
             t, x = self._resblock(net, f"model.{13 + blk}.", t, x, X, H, W,
@@ -144,11 +166,10 @@ class ForwardEngine:
         pc_t = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(Cf, 2 * Cf), with_bias=False)
         y_t, _ = self._conv(t_taps, pc_t, "3x3", B, h, w, norm=False)                     # [B, h, w, 1024]
         pc_s = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(0, Cf))
-        y1, mr1 = self._conv((fuse_hi, fuse_lo, (1, h + 2, w + 2)), pc_s, "3x3", n * B, h, w, addend=y_t)
-        t1 = ops.build_taps(y1, m, L.TAPS_REFLECT1, mean_rstd=mr1, relu=True)
+        t1, _ = self._conv_in((fuse_hi, fuse_lo, (1, h + 2, w + 2)), pc_s, "3x3", n * B, h, w, L.TAPS_REFLECT1,
+                              relu=True, addend=y_t)
         pc5 = self._pack("fuse_net", "model.0.conv_block.5")
-        y2, mr2 = self._conv(t1, pc5, "3x3", n * B, h, w)
-        tfo = ops.build_taps(y2, m, L.TAPS_SAME, mean_rstd=mr2, residual=cat_act)
+        tfo, _ = self._conv_in(t1, pc5, "3x3", n * B, h, w, L.TAPS_SAME, residual=cat_act)
         pcf = self._pack("fuse_net", "conv")
         sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
 

@@ -21,7 +21,13 @@ class ConvDesc(C.Structure):
                 ("Cp", C.c_int), ("Hp", C.c_int), ("Wp", C.c_int), ("planes", C.c_int), ("num_taps", C.c_int),
                 ("tap_dy", C.c_int8 * MAX_TAPS), ("tap_dx", C.c_int8 * MAX_TAPS), ("tap_plane", C.c_int8 * MAX_TAPS),
                 ("block_n", C.c_int), ("split", C.c_int), ("fmt", C.c_int), ("out_scale", C.c_float),
-                ("addend", C.c_void_p), ("addend_rows", C.c_int)]
+                ("addend", C.c_void_p), ("addend_rows", C.c_int),
+                ("fuse_in", C.c_int), ("fuse_relu", C.c_int), ("fuse_mode", C.c_int),
+                ("fuse_residual", C.c_void_p), ("fuse_act_out", C.c_void_p),
+                ("fuse_act_C_total", C.c_int), ("fuse_act_c_off", C.c_int),
+                ("fuse_taps_hi", C.c_void_p), ("fuse_taps_lo", C.c_void_p),
+                ("fuse_taps_Cp", C.c_int), ("fuse_taps_c_off", C.c_int),
+                ("fuse_act_scale", C.c_float), ("fuse_eps", C.c_float)]
 
 
 class TapsDesc(C.Structure):

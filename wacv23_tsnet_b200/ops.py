@@ -155,7 +155,7 @@ def _pick_block_n(pc, m_tiles):
 
 
 def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None,
-              addend=None):
+              addend=None, fuse=None):
     """taps_* : int16 [B*planes, Hp, Wp, Cp]; geom = (planes, Hp, Wp). Returns (y_raw [B,H,W,Cout], stats)."""
     planes, Hp, Wp = geom
     d = L.ConvDesc()
@@ -172,6 +172,30 @@ def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_s
         assert addend.shape[-1] == pc.Cout and addend.is_contiguous() and addend.dtype == torch.float32
         d.addend, d.addend_rows = addend.data_ptr(), addend.numel() // pc.Cout
     assert taps_hi.shape == (B * planes, Hp, Wp, pc.Cp), (tuple(taps_hi.shape), (B * planes, Hp, Wp, pc.Cp))
+    if fuse is not None:
+        # fused InstanceNorm epilogue: fuse = dict(relu, tmode, residual, act_out, act_c_off, taps=(hi, lo), c_off)
+        d.fuse_in, d.fuse_relu, d.fuse_mode = 1, int(fuse.get("relu", False)), fuse["tmode"]
+        d.fuse_act_scale, d.fuse_eps = act_scale, 1e-5
+        keep = []
+        if fuse.get("residual") is not None:
+            r = _f32(fuse["residual"])
+            assert r.shape == (B, H, W, pc.Cout)
+            d.fuse_residual = r.data_ptr()
+        if fuse.get("act_out") is not None:
+            a = fuse["act_out"]
+            assert a.dtype == torch.float32 and a.is_contiguous() and a.shape[:3] == (B, H, W)
+            d.fuse_act_out, d.fuse_act_C_total, d.fuse_act_c_off = a.data_ptr(), a.shape[3], fuse.get("act_c_off", 0)
+        if fuse.get("taps") is not None:
+            th, tl = fuse["taps"]
+            _, Hd, Wd = taps_geometry(fuse["tmode"], H, W)
+            assert th.shape[:3] == (B, Hd, Wd) and th.is_contiguous() and tl.shape == th.shape
+            d.fuse_taps_hi, d.fuse_taps_lo = th.data_ptr(), tl.data_ptr()
+            d.fuse_taps_Cp, d.fuse_taps_c_off = th.shape[3], fuse.get("c_off", 0)
+        with _Prof(("conv_gemm_fused_in", kind, B, H, W, pc.Cin * (pc.KW if pc.fold_kw else 1), pc.Cout, len(taps))):
+            L.check(L.load().tsnet_conv_gemm_fwd(C.byref(d), _ptr(taps_hi), _ptr(taps_lo), _ptr(pc.w_hi),
+                                                 _ptr(pc.w_lo), _ptr(pc.bias), None, None, _stream()))
+        _count()
+        return None, None
     if y is None:
         y = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=taps_hi.device)
     if want_stats and stats is None:
