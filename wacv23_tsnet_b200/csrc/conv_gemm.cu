@@ -525,11 +525,8 @@ static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int items = (a.num_m_tiles / 8) * a.num_n_tiles;
-  const int max_clusters = num_sms() / 8;
-  const int clusters = items < max_clusters ? items : max_clusters;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * 8);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytesFused;
   cfg.stream = stream;
@@ -540,6 +537,17 @@ static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // The persistent loop needs every cluster to be CO-RESIDENT: a cluster lives inside one GPC, and GPCs of 16/18/20 SMs
+  // hold two 8-CTA clusters each (16 on a B200, not 148/8 = 18).  Ask the runtime instead of guessing.
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(num_sms() / 8 * 8);
+    int n = 0;
+    TSNET_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BLOCK_N, true>, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cfg.gridDim = dim3(clusters * 8);
   TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, true>, a));
   return 0;
 }

@@ -22,10 +22,12 @@ class ForwardEngine:
         self.label_nc = label_nc
         self.n_blocks_dec = n_blocks_dec
         self.mode = MathMode(math_mode)
-        # InstanceNorm + ReLU + residual + tap building fused into the GEMM epilogue for the 32x32 layers
-        # (8-CTA clusters, tsnet_conv_desc.fuse_in); TSNET_FUSED_IN=0 selects the unfused 3-kernel sequence.
+        # TSNET_FUSED_IN=1: InstanceNorm + ReLU + residual + tap building fused into the GEMM epilogue of the 32x32
+        # layers (8-CTA clusters exchanging statistics over DSMEM, tsnet_conv_desc.fuse_in).  Correct and tested, but
+        # measured SLOWER on B200 (54.4 vs 49.8 ms/step): only 16 such clusters (128 of 148 SMs) can be co-resident
+        # and the longer epilogue serialises with the MMA pipe -- see DESIGN.md section 4.  Default: unfused.
         import os
-        self.fused_in = os.environ.get("TSNET_FUSED_IN", "1") == "1"
+        self.fused_in = os.environ.get("TSNET_FUSED_IN", "0") == "1"
         self._packs = {}
         self._coord = {}
 
