@@ -51,7 +51,7 @@ struct CorrSmemTail {
   uint64_t full_bar[kCorrStages], empty_bar[kCorrStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad[15];
-  float mask[kCorrMaxHW];            // nearest-down-sampled source mask of the current source
+  alignas(16) float mask[kCorrMaxHW];  // nearest-down-sampled source mask of the current source
   float cx[kCorrMaxHW];              // x coordinate of source position s
   float cy[kCorrMaxHW];              // y coordinate of source position s
   float2 grid[kCorrMaxSrc][kCorrM];  // expected coordinate per (source, row)
@@ -69,6 +69,13 @@ __device__ __forceinline__ float read_mask(const void* bbox, int dtype, int b, i
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 2^x for x <= 0 (softmax weights): MUFU.EX2, results below 2^-126 flush to zero (they are < 1e-38 of the row maximum)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid_constant__ CorrArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -227,28 +234,39 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&tl.tmem_empty[buf]);
           }
-          // ---- online softmax with the source coordinates as V
+          // ---- online softmax with the source coordinates as V (tables read as float4: 3 LDS.128 per 4 columns)
 #pragma unroll
           for (int c0 = 0; c0 < kCorrNC; c0 += 32) {
             const int s0 = ch * kCorrN + half * kCorrNC + c0;
             float gmax = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float wgt = fmaf(wa, tl.mask[s0 + j], wb);
-              acc[c0 + j] = (acc[c0 + j] * args.logit_scale) * wgt;
-              gmax = fmaxf(gmax, acc[c0 + j]);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 mk = *reinterpret_cast<const float4*>(&tl.mask[s0 + j]);
+              const float mv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float wgt = fmaf(wa, mv[u], wb);
+                acc[c0 + j + u] = (acc[c0 + j + u] * args.logit_scale) * wgt;
+                gmax = fmaxf(gmax, acc[c0 + j + u]);
+              }
             }
             const float new_max = fmaxf(run_max, gmax);
-            const float corr = exp2f((run_max - new_max) * kLog2e);  // exp2f(-inf) = 0 on the first group
+            const float corr = ex2_approx((run_max - new_max) * kLog2e);  // 2^(-inf) = 0 on the first group
             run_sum *= corr; gx *= corr; gy *= corr;
             run_max = new_max;
             const float mb = new_max * kLog2e;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float p = exp2f(fmaf(acc[c0 + j], kLog2e, -mb));
-              run_sum += p;
-              gx = fmaf(p, tl.cx[s0 + j], gx);
-              gy = fmaf(p, tl.cy[s0 + j], gy);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 vx = *reinterpret_cast<const float4*>(&tl.cx[s0 + j]);
+              const float4 vy = *reinterpret_cast<const float4*>(&tl.cy[s0 + j]);
+              const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float p = ex2_approx(fmaf(acc[c0 + j + u], kLog2e, -mb));  // argument <= 0
+                run_sum += p;
+                gx = fmaf(p, xs[u], gx);
+                gy = fmaf(p, ys[u], gy);
+              }
             }
           }
         }
@@ -258,7 +276,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
         if (half == 0) {
           const float4 o = tl.merge[row];
           const float m = fmaxf(run_max, o.x);
-          const float c0 = exp2f((run_max - m) * kLog2e), c1 = exp2f((o.x - m) * kLog2e);
+          const float c0 = ex2_approx((run_max - m) * kLog2e), c1 = ex2_approx((o.x - m) * kLog2e);
           const float l = run_sum * c0 + o.y * c1;
           const float2 g = make_float2((gx * c0 + o.z * c1) / l, (gy * c0 + o.w * c1) / l);
           tl.grid[i][row] = g;
