@@ -290,9 +290,11 @@ def run_b200(args):
         ck = [k for k in kern if k[0] == "corr_warp"]
         if ck:
             t, c = kern[ck[0]]
+            t += sum(kern[k][0] for k in kern if k[0] == "warp_mean_taps")  # K1 + K2 = the reference's corr+warp
             byts = ALGO_BYTES_CORR_PER_FRAME.get(n, 4 * 512 * 1024 * (n + 2) + 4 * 1024 * (n + 1)) * bs
             ach = byts / (t / c * 1e-3) / 1e9
-            roof_corr = {"kernel": "corr_warp (fused correlation+softmax+warp+mean)", "bound": "hbm", "achieved": ach,
+            roof_corr = {"kernel": "corr_warp (correlation+softmax+coordinate expectation) + warp_mean_taps (grid_sample"
+                                   "+source mean written as map_conv's operand)", "bound": "hbm", "achieved": ach,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                          "traffic": traffic.get("corr_warp_b32_n3") if (bs, n) == (32, 3) else None,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_launch": byts}

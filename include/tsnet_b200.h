@@ -182,6 +182,18 @@ int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const 
                         const float* coord_table, float* out_mean, float* out_grids, void* workspace,
                         size_t workspace_bytes, void* stream);
 size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc* d);
+/* out_mean may be NULL (then out_grids is required and src_fea is not read): the gather then runs in
+ * tsnet_warp_mean_taps below, which is the faster split on B200 -- inside the correlation kernel almost no L1 is left
+ * (224 KB of shared memory) and the 4-tap gather costs 191 of 445 us at bs=32. */
+
+/* ---- warp + source mean written as the decoder's operand ---------------------------------------
+ * F.grid_sample(src_fea_i, G_i, bilinear, zeros, align_corners=False) (model/TSNet.py:366), the mean over sources
+ * (:392) and the first half of torch.cat([pg, sg]) feeding Decoder.map_conv (:163), in one pass:
+ *   grids [n_src, B, h, w, 2] (from tsnet_corr_warp_fwd) -> out_mean fp32 [B, hw, C] (optional) and/or the hi/lo
+ *   tap source [B, h, w, Cp_total] channel window [c_off, c_off + C) of the 1x1 conv that consumes it. */
+int tsnet_warp_mean_taps(const float* const* src_fea, int n_src, const float* grids, int B, int h, int w, int C,
+                         float* out_mean, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off, int fmt,
+                         float scale, void* stream);
 
 /* ---- output head ---------------------------------------------------------------------------------
  * ReflectionPad2d(3) + Conv2d(64 -> 3, 7x7) + Tanh (model/TSNet.py:151-152) on the fp32 NHWC

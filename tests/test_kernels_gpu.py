@@ -381,3 +381,25 @@ def test_conv_gemm_fused_instance_norm_epilogue(Cin, Cout, kind, tmode, relu, re
     got = _recon(th, tl, m.fmt)
     assert _relerr(got[..., 64:], refp.permute(0, 2, 3, 1).float() * m.act_scale) < 5e-6
     assert int(th[..., :64].abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,n", [(2, 3), (1, 1), (1, 8)])
+def test_warp_mean_taps_vs_grid_sample(B, n):
+    """K2: F.grid_sample (bilinear, zeros, align_corners=False) of every source at given grids + mean over sources,
+    as fp32 and as the hi/lo operand window of the consumer (model/TSNet.py:366, :392, :163)."""
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    g = torch.Generator().manual_seed(40 + n)
+    srcs = [torch.randn(B, 512, 32, 32, generator=g) * 3 for _ in range(n)]
+    grids = [torch.rand(B, 32, 32, 2, generator=g) * 2.2 - 1.1 for _ in range(n)]   # includes out-of-range samples
+    ref = torch.stack([F.grid_sample(s, gr, align_corners=False) for s, gr in zip(srcs, grids)], 1).mean(1)
+    src_d = [s.permute(0, 2, 3, 1).contiguous().view(B, 1024, 512).cuda() for s in srcs]
+    grid_d = torch.stack(grids).cuda().contiguous()
+    hi = torch.zeros(B, 32, 32, 1024, dtype=torch.int16, device="cuda")
+    lo = torch.zeros_like(hi)
+    out = ops.warp_mean_taps(src_d, grid_d, B, 32, 32, 512, m, taps=(hi, lo), c_off=512, want_mean=True)
+    torch.cuda.synchronize()
+    ref_nhwc = ref.permute(0, 2, 3, 1).cuda()
+    assert _relerr(out.view(B, 32, 32, 512), ref_nhwc) < 2e-6
+    assert _relerr(_recon(hi, lo, m.fmt)[..., 512:], ref_nhwc * m.act_scale) < 2e-6
+    assert int(hi[..., :512].abs().max()) == 0

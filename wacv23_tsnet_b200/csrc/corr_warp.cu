@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
       const int nk = args.C / 128;
       const float n_srcf = static_cast<float>(args.n_src);
       const int e = warp - 4;
-      for (int r = 0; r < 16; ++r) {
+      for (int r = 0; r < (args.out_mean ? 16 : 0); ++r) {
         const int grow = e * 16 + r;
         const int pos = mt * kCorrM + grow;
         float4 accv[8];
@@ -355,9 +355,110 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_warp_kernel(const __grid
 constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 + static_cast<int>(sizeof(CorrSmemTail));
 static_assert(kCorrSmemBytes <= 227 * 1024, "corr_warp shared memory budget");
 
+// ------------------------------------------------------------------------------------------------
+// K2: bilinear grid_sample of the n source feature maps at the warp grids + mean over sources, written as the
+// operand (hi / lo tap source) of the decoder's map_conv -- "grid_sample fused with the following conv's load"
+// (model/TSNet.py:366, :392, :163).  One warp = one target position; lane owns channels {128 k + 4 lane .. +3}.
+// Runs with the whole L1 available (K1 leaves ~4 KB), which is what the 4-tap gather wants.
+// ------------------------------------------------------------------------------------------------
+struct WarpTapsArgs {
+  const float* src_fea[kCorrMaxSrc];
+  const float* grids;   // [n, B, hw, 2]
+  float* out_mean;      // fp32 [B, hw, C] or null
+  uint16_t* hi;         // [B, hw, Cp_total] or null
+  uint16_t* lo;
+  int B, n_src, C, h, w, Cp_total, c_off, fmt;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) warp_mean_taps_kernel(const WarpTapsArgs a) {
+  const int hw = a.h * a.w;
+  const size_t gpos = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gpos >= static_cast<size_t>(a.B) * hw) return;
+  const int b = static_cast<int>(gpos / hw);
+  const int lane = threadIdx.x & 31;
+  const int nk = a.C / 128;
+  float4 accv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < a.n_src; ++i) {
+    const float2 g = *reinterpret_cast<const float2*>(a.grids + (static_cast<size_t>(i) * a.B * hw + gpos) * 2);
+    // F.grid_sample(bilinear, zeros, align_corners=False): ix = ((x + 1) * W - 1) / 2
+    const float ix = ((g.x + 1.f) * a.w - 1.f) * 0.5f;
+    const float iy = ((g.y + 1.f) * a.h - 1.f) * 0.5f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+    const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+    float wts[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
+    const float* base = a.src_fea[i] + static_cast<size_t>(b) * hw * a.C + lane * 4;
+    const float* tp[4];
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+      if (!(xx >= 0 && xx < a.w && yy >= 0 && yy < a.h)) wts[tap] = 0.f;  // zeros padding
+      const int xc = min(max(xx, 0), a.w - 1), yc = min(max(yy, 0), a.h - 1);
+      tp[tap] = base + static_cast<size_t>(yc * a.w + xc) * a.C;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < nk) {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(tp[0] + k * 128));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(tp[1] + k * 128));
+        const float4 f2 = __ldg(reinterpret_cast<const float4*>(tp[2] + k * 128));
+        const float4 f3 = __ldg(reinterpret_cast<const float4*>(tp[3] + k * 128));
+        accv[k].x += fmaf(f3.x, wts[3], fmaf(f2.x, wts[2], fmaf(f1.x, wts[1], f0.x * wts[0])));
+        accv[k].y += fmaf(f3.y, wts[3], fmaf(f2.y, wts[2], fmaf(f1.y, wts[1], f0.y * wts[0])));
+        accv[k].z += fmaf(f3.z, wts[3], fmaf(f2.z, wts[2], fmaf(f1.z, wts[1], f0.z * wts[0])));
+        accv[k].w += fmaf(f3.w, wts[3], fmaf(f2.w, wts[2], fmaf(f1.w, wts[1], f0.w * wts[0])));
+      }
+    }
+  }
+  const float nf = static_cast<float>(a.n_src);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < nk) {
+      const float v[4] = {accv[k].x / nf, accv[k].y / nf, accv[k].z / nf, accv[k].w / nf};
+      const int c = k * 128 + lane * 4;
+      if (a.out_mean) *reinterpret_cast<float4*>(a.out_mean + gpos * a.C + c) = make_float4(v[0], v[1], v[2], v[3]);
+      if (a.hi) {
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split16(v[j] * a.scale, a.fmt, h[j], l[j]);
+        const size_t d = gpos * a.Cp_total + a.c_off + c;
+        *reinterpret_cast<uint2*>(a.hi + d) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+        *reinterpret_cast<uint2*>(a.lo + d) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+      }
+    }
+  }
+}
+
 }  // namespace tsnet
 
 using namespace tsnet;
+
+extern "C" int tsnet_warp_mean_taps(const float* const* src_fea, int n_src, const float* grids, int B, int h, int w,
+                                    int C, float* out_mean, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total,
+                                    int c_off, int fmt, float scale, void* stream) {
+  TSNET_ARG_CHECK(src_fea && grids && (out_mean || taps_hi), "warp_mean_taps: null argument");
+  TSNET_ARG_CHECK(n_src >= 1 && n_src <= kCorrMaxSrc, "warp_mean_taps: n_src %d (max %d)", n_src, kCorrMaxSrc);
+  TSNET_ARG_CHECK(C % 128 == 0 && C <= 1024, "warp_mean_taps: C %d must be a multiple of 128, <= 1024", C);
+  TSNET_ARG_CHECK((taps_hi == nullptr) == (taps_lo == nullptr), "warp_mean_taps: hi/lo must both be given or both NULL");
+  TSNET_ARG_CHECK(!taps_hi || (Cp_total % 4 == 0 && c_off % 4 == 0 && c_off + C <= Cp_total),
+                  "warp_mean_taps: channel window does not fit");
+  WarpTapsArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < n_src; ++i) {
+    TSNET_ARG_CHECK(src_fea[i], "warp_mean_taps: null source %d", i);
+    a.src_fea[i] = src_fea[i];
+  }
+  a.grids = grids; a.out_mean = out_mean; a.hi = taps_hi; a.lo = taps_lo;
+  a.B = B; a.n_src = n_src; a.C = C; a.h = h; a.w = w; a.Cp_total = Cp_total; a.c_off = c_off; a.fmt = fmt;
+  a.scale = scale == 0.f ? 1.f : scale;
+  const size_t rows = static_cast<size_t>(B) * h * w;
+  warp_mean_taps_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc*) { return 0; }
 
@@ -368,8 +469,9 @@ extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar
                                    void* stream) {
   (void)workspace;
   (void)workspace_bytes;
-  TSNET_ARG_CHECK(d && tar_hi && src_hi && src_fea && tar_bbox && src_bbox && coord_table && out_mean,
+  TSNET_ARG_CHECK(d && tar_hi && src_hi && tar_bbox && src_bbox && coord_table && (out_mean || out_grids),
                   "corr_warp: null argument");
+  TSNET_ARG_CHECK(!out_mean || src_fea, "corr_warp: out_mean needs the source features");
   TSNET_ARG_CHECK(!d->split || (tar_lo && src_lo), "corr_warp: split mode needs the lo operands");
   TSNET_ARG_CHECK(d->n_src >= 1 && d->n_src <= kCorrMaxSrc, "corr_warp: n_src %d (max %d)", d->n_src, kCorrMaxSrc);
   const int hw = d->h * d->w;
@@ -397,8 +499,8 @@ extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar
     if (d->split && (r = encode_tmap_u16_sw128(&a.s_lo, src_lo, 2, dims, str, box))) return r;
   }
   for (int i = 0; i < d->n_src; ++i) {
-    TSNET_ARG_CHECK(src_fea[i] && src_bbox[i], "corr_warp: null source %d", i);
-    a.src_fea[i] = src_fea[i];
+    TSNET_ARG_CHECK((!out_mean || src_fea[i]) && src_bbox[i], "corr_warp: null source %d", i);
+    a.src_fea[i] = out_mean ? src_fea[i] : nullptr;
     a.src_bbox[i] = src_bbox[i];
   }
   a.tar_bbox = tar_bbox;

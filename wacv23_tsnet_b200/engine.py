@@ -153,9 +153,15 @@ class ForwardEngine:
         tar_ops = ops.l2norm_split(tar_fea.view(B, hw, Cf), m)
         src_ops = ops.l2norm_split(src_fea.view(n * B, hw, Cf), m)
         src_fea_v = src_fea.view(n, B, hw, Cf)
-        pg_mean, grids = ops.corr_warp(tar_ops, src_ops, [src_fea_v[i] for i in range(n)], tar_bbox.contiguous(),
-                                       [bb.contiguous() for bb in src_bboxes], self._coord_table(h, w, dev), B, Cf, h,
-                                       w, m, want_grids=return_flow)
+        # K1 emits the warp grids only; the 4-tap gather + source mean run in K2 (warp_mean_taps), which writes the
+        # decoder's map_conv operand directly (torch.cat([pg, sg]) channels [0, 512), model/TSNet.py:163)
+        _, grids = ops.corr_warp(tar_ops, src_ops, [src_fea_v[i] for i in range(n)], tar_bbox.contiguous(),
+                                 [bb.contiguous() for bb in src_bboxes], self._coord_table(h, w, dev), B, Cf, h, w, m,
+                                 want_grids=True, want_mean=False)
+        dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
+        dec_lo = torch.empty_like(dec_hi)
+        pg_mean = ops.warp_mean_taps([src_fea_v[i] for i in range(n)], grids, B, h, w, Cf, m, taps=(dec_hi, dec_lo),
+                                     c_off=0, want_mean=collect is not None)
 
         # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400).
         # conv1(reflpad(cat[s_i, t])) = W[:, :512] * reflpad(s_i) + W[:, 512:] * reflpad(t): pad and conv are linear, so
@@ -176,9 +182,6 @@ class ForwardEngine:
         sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
 
         # ---- decoder (model/TSNet.py:128-174): map_conv on cat[pg_mean, mean_i sg_i]
-        dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
-        dec_lo = torch.empty_like(dec_hi)
-        ops.build_taps(pg_mean.view(B, h, w, Cf), m, L.TAPS_SAME, taps=(dec_hi, dec_lo), c_off=0)
         sg_mean = torch.empty((B, h, w, Cf), dtype=torch.float32, device=dev) if collect is not None else None
         ops.build_taps(sg, m, L.TAPS_SAME, taps=(dec_hi, dec_lo), c_off=Cf, avg_n=n, act_out=sg_mean)
         pcm = self._pack("dec", "map_conv")

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsnet_sm100.so")
+LIB_PATH = os.environ.get("TSNET_LIB_PATH", os.path.join(_HERE, "libtsnet_sm100.so"))  # override: experiments only
 
 FMT_FP16, FMT_BF16 = 0, 1
 TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1 = 0, 1, 2, 3
@@ -57,6 +57,8 @@ _SIGNATURES = {
     "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp, vp,
                                       vp, vp, C.c_size_t, vp]),
     "tsnet_corr_warp_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
+    "tsnet_warp_mean_taps": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                                       C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                        C.POINTER(C.c_float), vp, vp]),
     "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_float), vp, vp]),

@@ -286,7 +286,7 @@ def l2norm_split(fea, mode, out=None):
 
 
 def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode,
-              temperature=100.0, want_grids=False):
+              temperature=100.0, want_grids=False, want_mean=True):
     """tar_ops = (hi, lo) [B*hw, C]; src_ops = (hi, lo) [n*B*hw, C]; src_fea_list n x fp32 [B, hw, C];
     bboxes [B, Hb, Wb] uint8 or fp32 (full resolution).  Returns (out_mean fp32 [B, hw, C], grids or None)."""
     n = len(src_fea_list)
@@ -299,8 +299,8 @@ def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_tab
     d.temperature, d.split, d.fmt = temperature, mode.split, mode.fmt
     d.operand_scale = mode.corr_scale * mode.corr_scale
     dev = tar_ops[0].device
-    out = torch.empty((B, h * w, Cch), dtype=torch.float32, device=dev)
-    grids = torch.empty((n, B, h, w, 2), dtype=torch.float32, device=dev) if want_grids else None
+    out = torch.empty((B, h * w, Cch), dtype=torch.float32, device=dev) if want_mean else None
+    grids = torch.empty((n, B, h, w, 2), dtype=torch.float32, device=dev) if (want_grids or not want_mean) else None
     fea_ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in src_fea_list])
     bb_ptrs = (C.c_void_p * n)(*[bb.data_ptr() for bb in src_bbox_list])
     with _Prof(("corr_warp",)):
@@ -309,6 +309,21 @@ def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_tab
                                              _ptr(out), _ptr(grids), None, 0, _stream()))
     _count()
     return out, grids
+
+
+def warp_mean_taps(src_fea_list, grids, B, h, w, Cch, mode, taps=None, c_off=0, want_mean=False):
+    """grids [n,B,h,w,2] + n x fp32 [B,hw,C] source features -> mean_i grid_sample(src_i, G_i): fp32 [B,hw,C] (optional)
+    and / or written as hi/lo operands into the channel window [c_off, c_off+C) of `taps` = (hi, lo) [B,h,w,Cp]."""
+    n = len(src_fea_list)
+    out = torch.empty((B, h * w, Cch), dtype=torch.float32, device=grids.device) if want_mean else None
+    hi, lo = taps if taps is not None else (None, None)
+    fea_ptrs = (C.c_void_p * n)(*[_f32(f).data_ptr() for f in src_fea_list])
+    with _Prof(("warp_mean_taps",)):
+        L.check(L.load().tsnet_warp_mean_taps(fea_ptrs, n, _ptr(_f32(grids)), B, h, w, Cch, _ptr(out), _ptr(hi), _ptr(lo),
+                                              0 if hi is None else hi.shape[-1], c_off, mode.fmt,
+                                              C.c_float(mode.act_scale), _stream()))
+    _count()
+    return out
 
 
 def head_conv_tanh(act, weight, bias, fore=None, fill=None):
