@@ -287,17 +287,25 @@ def run_b200(args):
                 "note": "fp32-faithful mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi): "
                         "frac <= 0.333 by construction; tensor-pipe utilisation = 3 x frac" if net._engine.mode.split
                 else "single-pass 16-bit operands"}
-        ck = [k for k in kern if k[0] == "corr_warp"]
-        if ck:
-            t, c = kern[ck[0]]
-            t += sum(kern[k][0] for k in kern if k[0] == "warp_mean_taps")  # K1 + K2 = the reference's corr+warp
+        chain = ("corr_prepare", "l2norm_split", "corr_tiles", "corr_finish")
+        if all((k,) in kern for k in chain):
+            # the reference's corr+warp (model/TSNet.py:319-366, :392) = ALL four kernels of the chain: mask sort / work
+            # list, F.normalize + operand split, tensor-core similarity tiles + softmax, merge + grid_sample + mean
+            per = {k: kern[(k,)][0] / args.steps * 1e3 for k in chain}       # us per forward
+            t_us = sum(per.values())
             byts = ALGO_BYTES_CORR_PER_FRAME.get(n, 4 * 512 * 1024 * (n + 2) + 4 * 1024 * (n + 1)) * bs
-            ach = byts / (t / c * 1e-3) / 1e9
-            roof_corr = {"kernel": "corr_warp (correlation+softmax+coordinate expectation) + warp_mean_taps (grid_sample"
-                                   "+source mean written as map_conv's operand)", "bound": "hbm", "achieved": ach,
+            ach = byts / (t_us * 1e-6) / 1e9
+            tiles_ach = byts / (per["corr_tiles"] * 1e-6) / 1e9
+            roof_corr = {"kernel": "correlation chain: corr_prepare (mask class sort + work list) + l2norm_split x2 + "
+                                   "corr_tiles (tcgen05 similarity + softmax states) + corr_finish (merge + grid_sample"
+                                   " + source mean written as map_conv's operand)", "bound": "hbm", "achieved": ach,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                         "traffic": traffic.get("corr_warp_b32_n3") if (bs, n) == (32, 3) else None,
-                         "peak_source": peaks["source"], "algorithmic_bytes_per_launch": byts}
+                         "traffic": traffic.get("corr_chain_b32_n3") if (bs, n) == (32, 3) else None,
+                         "peak_source": peaks["source"], "algorithmic_bytes_per_launch": byts,
+                         "us_per_forward": per,
+                         "corr_tiles_alone": {"achieved": tiles_ach, "frac": tiles_ach / peaks["hbm_gbs"]},
+                         "note": "fp32-faithful 3-term MMAs make the similarity tensor-bound: the ceiling of corr_tiles "
+                                 "alone is ~0.27 of the HBM roofline when every tile is computed (DESIGN.md section 4)"}
 
     line = None
     if rank == 0:

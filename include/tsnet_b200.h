@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TSNET_ABI_VERSION 1
+#define TSNET_ABI_VERSION 2
 
 /* 16-bit operand format of the tensor-core path */
 #define TSNET_FMT_FP16 0
@@ -150,47 +150,70 @@ int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* me
 int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const void* lbl, int Clbl, int lbl_kind, int B,
                     int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
 
-/* ---- correlation operands ------------------------------------------------------------------------
- * F.normalize(fea, p=2, dim=1) (model/TSNet.py:319, :339; eps = 1e-12) of an fp32 NHWC feature map
- * [B, HW, C], written as 16-bit hi/lo K-major operands [B*HW, C] (scaled by `scale`). */
-int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, uint16_t* out_hi,
-                       uint16_t* out_lo, void* stream);
-
-/* ---- fused mask-aware correlation -> softmax -> coordinate expectation -> warp -> source mean ---
- * model/TSNet.py:322-323 (target mask), :347-366 (per source: mask, two masked bmm, softmax(100 x),
- * expected coordinate, grid_sample) and :392 (mean over sources).  The HW x HW matrix is never
- * materialised.  bbox pointers are the FULL-RESOLUTION masks [B, bbox_h, bbox_w] (uint8 or fp32);
- * nearest down-sampling to (h, w) is done by integer indexing inside the kernel.
- *   tar_hi/lo        [B*hw, C]   normalised target operands (tsnet_l2norm_split)
- *   src_hi/lo        ONE buffer [n_src, B*hw, C]: normalised operands of all sources, source-major
- *   src_fea          n_src pointers (host array) to fp32 NHWC un-normalised source features (sampled)
- *   coord_table      h + w floats: torch.linspace(-1,1,h) then torch.linspace(-1,1,w) (:301-302)
- *   out_mean         fp32 NHWC [B, hw, C]  = mean_i grid_sample(src_fea_i, G_i)
- *   out_grids        NULL or [n_src, B, h, w, 2] (x, y) -- the reference's warp_grid2d_list (:369-370)
- *   operand_scale    product of the two operand pre-scales (accumulators are divided by it)          */
+/* ---- correlation: masks -> class-sorted order, operands, tensor-core tiles, warp + mean -----------------------
+ * model/TSNet.py:319-323 (normalise, target mask), :339-366 (per source: normalise, mask, two masked bmm,
+ * softmax(100 x), expected coordinate, grid_sample), :392 (mean over sources) and the first half of
+ * torch.cat([pg, sg]) feeding Decoder.map_conv (:163).  The HW x HW matrix is never materialised.
+ *
+ * Call order on one stream (SURVEY section 8b names this group `tsnet_corr_warp_fwd`):
+ *   1. tsnet_corr_prepare     masks -> per-map class-sorted order, tile classes, work list, closed forms
+ *   2. tsnet_l2norm_split x2  F.normalize of target / source features, rows written in the sorted order
+ *   3. tsnet_corr_warp_fwd    = tsnet_corr_tiles (tcgen05 similarity tiles -> partial softmax states)
+ *                             + tsnet_corr_finish (merge -> warp grid -> grid_sample -> source mean)
+ *
+ * Why sorted: the reference's similarity is (T.S) * (mt*ms + (1-mt)*(1-ms)) -- for {0,1} bbox masks every pair of
+ * positions whose classes differ has logit exactly 0.  With the positions of each map stably sorted by class, a
+ * 128-row target tile and a 256-column source chunk of different pure classes need no tensor work: their softmax
+ * contribution (max 0, weight 256, coordinate sums) is written by tsnet_corr_prepare.  Soft (non-binary) masks are
+ * handled exactly (they sort between the classes and are never skipped).
+ *
+ * bbox pointers are the FULL-RESOLUTION masks [B, bbox_h, bbox_w] (uint8 or fp32); nearest down-sampling to (h, w)
+ * is integer indexing inside tsnet_corr_prepare.  coord_table = h + w floats: torch.linspace(-1,1,h) then
+ * torch.linspace(-1,1,w) (:301-302).  The workspace (tsnet_corr_workspace_bytes, 256 B aligned, caller-owned) carries
+ * everything between the calls; it may be reused by the next forward on the same stream. */
 typedef struct {
   int B, n_src, C, h, w;
   int bbox_h, bbox_w, bbox_dtype; /* 0 = uint8, 1 = fp32 */
   float temperature;              /* 100 (model/TSNet.py:359) */
   int split, fmt;
-  float operand_scale;
+  float operand_scale;            /* product of the two operand pre-scales (accumulators are divided by it) */
+  int sort;                       /* 1: class-sorted order + tile skipping (default); 0: raster order */
 } tsnet_corr_desc;
 
-int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
-                        const uint16_t* src_hi, const uint16_t* src_lo,
-                        const float* const* src_fea, const void* tar_bbox, const void* const* src_bbox,
-                        const float* coord_table, float* out_mean, float* out_grids, void* workspace,
-                        size_t workspace_bytes, void* stream);
-size_t tsnet_corr_warp_workspace_bytes(const tsnet_corr_desc* d);
-/* out_mean may be NULL (then out_grids is required and src_fea is not read): the gather then runs in
- * tsnet_warp_mean_taps below, which is the faster split on B200 -- inside the correlation kernel almost no L1 is left
- * (224 KB of shared memory) and the 4-tap gather costs 191 of 445 us at bs=32. */
+size_t tsnet_corr_workspace_bytes(const tsnet_corr_desc* d);
+int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox, const void* const* src_bbox,
+                       const float* coord_table, void* workspace, size_t workspace_bytes, void* stream);
+/* position -> sorted-rank tables inside a prepared workspace, for tsnet_l2norm_split:
+ * which = 0: target [B, hw]; which = 1: sources [n_src * B, hw] (source-major, like the source features) */
+const uint16_t* tsnet_corr_rank_table(const tsnet_corr_desc* d, const void* workspace, int which);
 
-/* ---- warp + source mean written as the decoder's operand ---------------------------------------
- * F.grid_sample(src_fea_i, G_i, bilinear, zeros, align_corners=False) (model/TSNet.py:366), the mean over sources
- * (:392) and the first half of torch.cat([pg, sg]) feeding Decoder.map_conv (:163), in one pass:
- *   grids [n_src, B, h, w, 2] (from tsnet_corr_warp_fwd) -> out_mean fp32 [B, hw, C] (optional) and/or the hi/lo
- *   tap source [B, h, w, Cp_total] channel window [c_off, c_off + C) of the 1x1 conv that consumes it. */
+/* F.normalize(fea, p=2, dim=1) (model/TSNet.py:319, :339; eps = 1e-12) of an fp32 NHWC feature map [B, HW, C],
+ * written as 16-bit hi/lo K-major operands [B*HW, C] (scaled by `scale`).  rank (optional, [B, HW] uint16):
+ * row p of sample b goes to row b*HW + rank[b*HW + p]. */
+int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, const uint16_t* rank,
+                       uint16_t* out_hi, uint16_t* out_lo, void* stream);
+
+/*   tar_hi/lo   [B*hw, C]          normalised target operands, sorted rows
+ *   src_hi/lo   [n_src, B*hw, C]   normalised operands of all sources (ONE buffer, source-major), sorted rows
+ *   src_fea     n_src pointers (host array) to fp32 NHWC un-normalised source features (sampled by grid_sample)
+ *   out_mean    NULL or fp32 NHWC [B, hw, C] = mean_i grid_sample(src_fea_i, G_i)
+ *   out_grids   NULL or [n_src, B, h, w, 2] (x, y) -- the reference's warp_grid2d_list (:369-370)
+ *   taps_hi/lo  NULL or the hi/lo tap source [B, h, w, Cp_total] of the 1x1 conv that consumes the mean: channel
+ *               window [c_off, c_off + C), values scaled by taps_scale ("grid_sample fused with the next conv's load") */
+int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
+                        const uint16_t* src_hi, const uint16_t* src_lo, const float* const* src_fea, float* out_mean,
+                        float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off,
+                        float taps_scale, void* workspace, size_t workspace_bytes, void* stream);
+/* the two halves of tsnet_corr_warp_fwd, separately launchable (profiling, grids-only use) */
+int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo, const uint16_t* src_hi,
+                     const uint16_t* src_lo, void* workspace, size_t workspace_bytes, void* stream);
+int tsnet_corr_finish(const tsnet_corr_desc* d, const float* const* src_fea, float* out_mean, float* out_grids,
+                      uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off, float taps_scale, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- warp + source mean from given grids ---------------------------------------------------------------------
+ * F.grid_sample(src_fea_i, G_i, bilinear, zeros, align_corners=False) (model/TSNet.py:366) + mean over sources
+ * (:392) for caller-supplied grids [n_src, B, h, w, 2]; outputs as in tsnet_corr_warp_fwd. */
 int tsnet_warp_mean_taps(const float* const* src_fea, int n_src, const float* grids, int B, int h, int w, int C,
                          float* out_mean, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off, int fmt,
                          float scale, void* stream);

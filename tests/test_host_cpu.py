@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(h, name), f"{name} declared in include/tsnet_b200.h but not exported"
     assert declared == set(built.EXPORTED_SYMBOLS), declared ^ set(built.EXPORTED_SYMBOLS)
-    assert built.load().tsnet_abi_version() == 1
+    assert built.load().tsnet_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built):

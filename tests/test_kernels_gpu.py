@@ -181,6 +181,12 @@ def test_l2norm_and_head():
     f[0, 3] = 0  # all-zero vector: F.normalize gives 0 (eps clamp)
     hi, lo = ops.l2norm_split(f, m)
     assert _relerr(_recon(hi, lo, m.fmt).view(2, 64, 512), F.normalize(f, dim=2) * m.corr_scale) < 1e-6
+    perm = torch.stack([torch.randperm(64) for _ in range(2)]).to(torch.int16).cuda()   # row p of sample b -> rank
+    hi2, lo2 = ops.l2norm_split(f, m, rank=perm.data_ptr())
+    torch.cuda.synchronize()
+    idx = perm.long().view(2, 64, 1).expand(2, 64, 512)
+    assert torch.equal(hi2.view(2, 64, 512).gather(1, idx), hi.view(2, 64, 512))
+    assert torch.equal(lo2.view(2, 64, 512).gather(1, idx), lo.view(2, 64, 512))
     a = torch.randn(2, 64, 64, 64, device="cuda")
     wh = torch.randn(3, 64, 7, 7, device="cuda") * 0.02
     bh = torch.randn(3, device="cuda") * 0.1
@@ -207,6 +213,19 @@ def _corr_inputs(B, n, kind, seed):
             sb = torch.zeros(B, 1, 256, 256, dtype=torch.uint8)
             sb[:, :, 20 + 10 * i:180, 50:230 - 10 * i] = 1
             sbs.append(sb)
+    elif kind == "mixed_u8":  # sample 0: rectangles, sample 1: all ones / all zeros, sample 2+: random bits
+        g2 = torch.Generator().manual_seed(seed + 100)
+        tb = torch.randint(0, 2, (B, 1, 256, 256), generator=g2).to(torch.uint8)
+        sbs = [torch.randint(0, 2, (B, 1, 256, 256), generator=g2).to(torch.uint8) for _ in range(n)]
+        tb[0] = 0
+        tb[0, :, 64:200, 16:140] = 1
+        for i, sb in enumerate(sbs):
+            sb[0] = 0
+            sb[0, :, 30 + 20 * i:220, 40:250 - 30 * i] = 1
+        if B > 1:
+            tb[1] = 1
+            for i, sb in enumerate(sbs):
+                sb[1] = i % 2
     elif kind == "random_f32":
         tb = torch.randint(0, 2, (B, 1, 256, 256), generator=g).float()
         sbs = [torch.randint(0, 2, (B, 1, 256, 256), generator=g).float() for _ in range(n)]
@@ -222,8 +241,21 @@ def _corr_inputs(B, n, kind, seed):
     return tar, srcs, tb, sbs
 
 
+def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True):
+    from wacv23_tsnet_b200 import ops
+    B, n = tar.shape[0], len(srcs)
+    tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda().view(B, 1024, 512)
+    src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).cuda().view(n, B, 1024, 512)
+    coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
+    out, grids = ops.corr_chain(tar_d, src_d, tb.squeeze(1).contiguous().cuda(),
+                                [s.squeeze(1).contiguous().cuda() for s in sbs], coord, m, want_grids=True,
+                                want_mean=want_mean, sort=sort)
+    torch.cuda.synchronize()
+    return out, grids
+
+
 @pytest.mark.parametrize("B,n,kind", [(1, 1, "random_f32"), (2, 3, "rect_u8"), (1, 5, "random_f32"), (1, 8, "rect_u8"),
-                                      (1, 2, "all_one"), (1, 2, "all_zero_tar"), (1, 2, "soft")])
+                                      (1, 2, "all_one"), (1, 2, "all_zero_tar"), (1, 2, "soft"), (3, 2, "mixed_u8")])
 def test_corr_warp_vs_oracle(B, n, kind):
     from oracle import tsnet_oracle as O
     from wacv23_tsnet_b200 import ops
@@ -231,15 +263,7 @@ def test_corr_warp_vs_oracle(B, n, kind):
     tar, srcs, tb, sbs = _corr_inputs(B, n, kind, seed=10 + n)
     ref_mean, ref_grids = O.corr_warp(tar, srcs, tb, sbs)                        # the reference's fp32 arithmetic
     tru_mean, tru_grids = O.corr_warp(tar.double(), [s.double() for s in srcs], tb, sbs)  # fp64 "truth"
-    tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda()
-    src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).cuda()
-    tar_ops = ops.l2norm_split(tar_d.view(B, 1024, 512), m)
-    src_ops = ops.l2norm_split(src_d.view(n * B, 1024, 512), m)
-    coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
-    out, grids = ops.corr_warp(tar_ops, src_ops, [src_d[i].view(B, 1024, 512) for i in range(n)],
-                               tb.squeeze(1).contiguous().cuda(), [s.squeeze(1).contiguous().cuda() for s in sbs], coord,
-                               B, 512, 32, 32, m, want_grids=True)
-    torch.cuda.synchronize()
+    out, grids = _run_corr(tar, srcs, tb, sbs, m)
     gerr = max(float((grids[i].cpu() - ref_grids[i]).abs().max()) for i in range(n))
     assert gerr < 5e-5, gerr          # vs the fp32 reference, [-1, 1] units; 5e-5 = 8e-4 feature pixels
     assert _relerr(out.view(B, 32, 32, 512).permute(0, 3, 1, 2).cpu(), ref_mean) < 1e-3
@@ -251,13 +275,60 @@ def test_corr_warp_vs_oracle(B, n, kind):
     assert k_err < max(4.0 * r_err, 1.5e-5), (k_err, r_err)
     if kind == "all_zero_tar":
         assert float(torch.stack([g for g in grids]).abs().max()) < 1e-5
+    # the class-sorted order with tile skipping and the raster order (every tile computed) are the same function
+    out_r, grids_r = _run_corr(tar, srcs, tb, sbs, m, sort=False)
+    assert float((grids - grids_r).abs().max()) < 5e-6   # summation order only
+    assert _relerr(out, out_r) < 2e-4   # 3e-6 grid units x the feature gradient
     # uint8 and float masks with the same {0,1} content must give identical bits (integer-exact mask path)
-    if kind == "rect_u8":
-        out2, grids2 = ops.corr_warp(tar_ops, src_ops, [src_d[i].view(B, 1024, 512) for i in range(n)],
-                                     tb.squeeze(1).float().contiguous().cuda(),
-                                     [s.squeeze(1).float().contiguous().cuda() for s in sbs], coord, B, 512, 32, 32, m,
-                                     want_grids=True)
+    if kind in ("rect_u8", "mixed_u8"):
+        out2, grids2 = _run_corr(tar, srcs, tb.float(), [s.float() for s in sbs], m)
         assert torch.equal(out, out2) and torch.equal(grids, grids2)
+
+
+def test_corr_strongly_correlated_features():
+    """Peaked softmax rows (cos ~ 0.95 at the true match, logits near 100) -- the regime of a trained network; the
+    random-feature cases above have row maxima near 20."""
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    g = torch.Generator().manual_seed(5)
+    B, n = 2, 3
+    tar = torch.randn(B, 512, 32, 32, generator=g)
+    srcs = [torch.roll(tar, shifts=(2 * i + 1, -(i + 2)), dims=(2, 3)) + 0.3 * torch.randn(B, 512, 32, 32, generator=g)
+            for i in range(n)]
+    _, _, tb, sbs = _corr_inputs(B, n, "rect_u8", seed=3)
+    _, ref = O.corr_warp(tar, srcs, tb, sbs)
+    _, tru = O.corr_warp(tar.double(), [s.double() for s in srcs], tb, sbs)
+    _, grids = _run_corr(tar, srcs, tb, sbs, m, want_mean=False)
+    k_err = max(float((grids[i].cpu().double() - tru[i]).abs().max()) for i in range(n))
+    r_err = max(float((ref[i].double() - tru[i]).abs().max()) for i in range(n))
+    assert k_err < max(4.0 * r_err, 1.5e-5), (k_err, r_err)
+
+
+def test_corr_prepare_plan_is_integer_exact():
+    """tsnet_corr_prepare: nearest down-sampling, stable class sort (ones, soft, zeros), rank tables and tile classes
+    against a numpy restatement (bit-exact integer work)."""
+    import numpy as np
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    B, n = 3, 2
+    _, _, tb, sbs = _corr_inputs(B, n, "mixed_u8", seed=1)
+    coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
+    plan = ops.corr_prepare(tb.squeeze(1).contiguous().cuda(), [s.squeeze(1).contiguous().cuda() for s in sbs], coord,
+                            B, 512, 32, 32, m)
+    torch.cuda.synchronize()
+    NM = (n + 1) * B
+    rank = plan.ws[:NM * 1024 * 2].view(torch.int16).view(NM, 1024).cpu().numpy().astype(np.int64)
+    masks = [O.nearest_downsample_mask(tb.numpy(), 32, 32)] + [O.nearest_downsample_mask(s.numpy(), 32, 32) for s in sbs]
+    for q in range(n + 1):
+        for b in range(B):
+            mv = masks[q][b].reshape(-1)
+            key = np.where(mv == 1, 0, np.where(mv == 0, 2, 1))
+            order = np.argsort(key, kind="stable")
+            want = np.empty(1024, np.int64)
+            want[order] = np.arange(1024)
+            assert (rank[(0 if q == 0 else B + (q - 1) * B) + b] == want).all()
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -218,12 +218,10 @@ def stage_corr():
         tru_mean, tru_grids = O.corr_warp(tar.double(), [s.double() for s in srcs], tb, sbs)
         tar_d = tar.permute(0, 2, 3, 1).contiguous().to(dev)
         src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).to(dev)  # [n,B,h,w,C]
-        tar_ops = ops.l2norm_split(tar_d.view(B, 1024, 512), m)
-        src_ops = ops.l2norm_split(src_d.view(n * B, 1024, 512), m)
         coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).to(dev)
-        out, grids = ops.corr_warp(tar_ops, src_ops, [src_d[i].view(B, 1024, 512) for i in range(n)],
-                                   tb.squeeze(1).contiguous().to(dev), [s.squeeze(1).contiguous().to(dev) for s in sbs],
-                                   coord, B, 512, 32, 32, m, want_grids=True)
+        out, grids = ops.corr_chain(tar_d.view(B, 1024, 512), src_d.view(n, B, 1024, 512),
+                                    tb.squeeze(1).contiguous().to(dev), [s.squeeze(1).contiguous().to(dev) for s in sbs],
+                                    coord, m, want_grids=True, want_mean=True)
         torch.cuda.synchronize()
         gerr = max((grids[i].cpu() - ref_grids[i]).abs().max().item() for i in range(n))
         kerr = max((grids[i].cpu().double() - tru_grids[i]).abs().max().item() for i in range(n))

@@ -318,9 +318,11 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // F.normalize(dim = channel) + hi/lo split. One warp = one pixel; C % 128 == 0, C <= 1024.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restrict__ fea, size_t npix, int C, int fmt,
-                                                           float scale, uint16_t* __restrict__ hi,
-                                                           uint16_t* __restrict__ lo) {
+// rank (optional, [B, HW] uint16): row `pix` of sample b is written to row b*HW + rank[pix] -- the class-sorted
+// operand order of the correlation kernel (tsnet_corr_prepare).
+__global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restrict__ fea, size_t npix, int HW, int C,
+                                                           int fmt, float scale, const uint16_t* __restrict__ rank,
+                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
   const size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x / 32) + (threadIdx.x >> 5);
   if (pix >= npix) return;
   const int lane = threadIdx.x & 31;
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restri
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float denom = fmaxf(__fsqrt_rn(ss), 1e-12f);  // F.normalize eps
+  const size_t drow = rank ? (pix / HW) * HW + rank[pix] : pix;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (k < nk) {
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restri
       uint16_t h[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) split16(__fdiv_rn(e[j], denom) * scale, fmt, h[j], l[j]);
-      const size_t d = pix * C + k * 128 + lane * 4;
+      const size_t d = drow * C + k * 128 + lane * 4;
       *reinterpret_cast<uint2*>(hi + d) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
       *reinterpret_cast<uint2*>(lo + d) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
     }
@@ -619,13 +622,13 @@ extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, c
   return 0;
 }
 
-extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, uint16_t* out_hi,
-                                  uint16_t* out_lo, void* stream) {
+extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, const uint16_t* rank,
+                                  uint16_t* out_hi, uint16_t* out_lo, void* stream) {
   TSNET_ARG_CHECK(fea && out_hi && out_lo, "l2norm_split: null argument");
   TSNET_ARG_CHECK(C % 128 == 0 && C <= 1024, "l2norm_split: C %d must be a multiple of 128, <= 1024", C);
   const size_t npix = static_cast<size_t>(B) * HW;
   l2norm_split_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      fea, npix, C, fmt, scale == 0.f ? 1.f : scale, out_hi, out_lo);
+      fea, npix, HW, C, fmt, scale == 0.f ? 1.f : scale, rank, out_hi, out_lo);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

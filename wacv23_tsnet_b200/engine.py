@@ -150,18 +150,19 @@ class ForwardEngine:
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
         # ---- transformation branch (model/TSNet.py:319-366, 392)
-        tar_ops = ops.l2norm_split(tar_fea.view(B, hw, Cf), m)
-        src_ops = ops.l2norm_split(src_fea.view(n * B, hw, Cf), m)
+        # prepare: masks -> class-sorted order + work list; operands are written in that order; the tensor-core tiles
+        # emit partial softmax states; the finish kernel merges them, gathers the 4 bilinear taps, averages the sources
+        # and writes the decoder's map_conv operand directly (torch.cat([pg, sg]) channels [0, 512), model/TSNet.py:163)
+        plan = ops.corr_prepare(tar_bbox.contiguous(), [bb.contiguous() for bb in src_bboxes],
+                                self._coord_table(h, w, dev), B, Cf, h, w, m)
+        tar_ops = ops.l2norm_split(tar_fea.view(B, hw, Cf), m, rank=plan.rank_t)
+        src_ops = ops.l2norm_split(src_fea.view(n * B, hw, Cf), m, rank=plan.rank_s)
         src_fea_v = src_fea.view(n, B, hw, Cf)
-        # K1 emits the warp grids only; the 4-tap gather + source mean run in K2 (warp_mean_taps), which writes the
-        # decoder's map_conv operand directly (torch.cat([pg, sg]) channels [0, 512), model/TSNet.py:163)
-        _, grids = ops.corr_warp(tar_ops, src_ops, [src_fea_v[i] for i in range(n)], tar_bbox.contiguous(),
-                                 [bb.contiguous() for bb in src_bboxes], self._coord_table(h, w, dev), B, Cf, h, w, m,
-                                 want_grids=True, want_mean=False)
         dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
         dec_lo = torch.empty_like(dec_hi)
-        pg_mean = ops.warp_mean_taps([src_fea_v[i] for i in range(n)], grids, B, h, w, Cf, m, taps=(dec_hi, dec_lo),
-                                     c_off=0, want_mean=collect is not None)
+        pg_mean, grids = ops.corr_warp(plan, tar_ops, src_ops, [src_fea_v[i] for i in range(n)], m,
+                                       want_grids=return_flow, want_mean=collect is not None, taps=(dec_hi, dec_lo),
+                                       c_off=0)
 
         # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400).
         # conv1(reflpad(cat[s_i, t])) = W[:, :512] * reflpad(s_i) + W[:, 512:] * reflpad(t): pad and conv are linear, so

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("TSNET_LIB_PATH", os.path.join(_HERE, "libtsnet_sm100.
 FMT_FP16, FMT_BF16 = 0, 1
 TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1 = 0, 1, 2, 3
 MAX_TAPS = 49
+ABI_VERSION = 2
 
 vp = C.c_void_p
 
@@ -39,7 +40,7 @@ class TapsDesc(C.Structure):
 class CorrDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("n_src", C.c_int), ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("bbox_h", C.c_int), ("bbox_w", C.c_int), ("bbox_dtype", C.c_int), ("temperature", C.c_float),
-                ("split", C.c_int), ("fmt", C.c_int), ("operand_scale", C.c_float)]
+                ("split", C.c_int), ("fmt", C.c_int), ("operand_scale", C.c_float), ("sort", C.c_int)]
 
 
 _SIGNATURES = {
@@ -53,10 +54,15 @@ _SIGNATURES = {
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_float, vp, vp, vp]),
-    "tsnet_l2norm_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
-    "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, C.POINTER(vp), vp, vp,
-                                      vp, vp, C.c_size_t, vp]),
-    "tsnet_corr_warp_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
+    "tsnet_l2norm_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp]),
+    "tsnet_corr_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
+    "tsnet_corr_prepare": (C.c_int, [C.POINTER(CorrDesc), vp, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
+    "tsnet_corr_rank_table": (vp, [C.POINTER(CorrDesc), vp, C.c_int]),
+    "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, C.c_int,
+                                      C.c_int, C.c_float, vp, C.c_size_t, vp]),
+    "tsnet_corr_tiles": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "tsnet_corr_finish": (C.c_int, [C.POINTER(CorrDesc), C.POINTER(vp), vp, vp, vp, vp, C.c_int, C.c_int, C.c_float,
+                                    vp, C.c_size_t, vp]),
     "tsnet_warp_mean_taps": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                        C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
@@ -86,7 +92,7 @@ def load():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.tsnet_abi_version() != 1:
+        if lib.tsnet_abi_version() != ABI_VERSION:
             raise TSNetLibraryError("libtsnet_sm100.so ABI version mismatch")
         _lib = lib
     return _lib

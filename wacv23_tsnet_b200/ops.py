@@ -270,26 +270,19 @@ def stem_taps(img, img_div, lbl, Cp, mode, label_nc=None):
     return hi, lo, (1, H + 6, W)
 
 
-def l2norm_split(fea, mode, out=None):
-    """fea fp32 [B, hw, C] (NHWC flattened) -> (hi, lo) int16 [B*hw, C] of F.normalize(dim=C) * corr_scale."""
-    B, HW, Cch = fea.shape
-    if out is None:
-        hi = torch.empty((B * HW, Cch), dtype=torch.int16, device=fea.device)
-        lo = torch.empty_like(hi)
-    else:
-        hi, lo = out
-    with _Prof(("l2norm_split",)):
-        L.check(L.load().tsnet_l2norm_split(_ptr(_f32(fea)), B, HW, Cch, mode.fmt, C.c_float(mode.corr_scale),
-                                            _ptr(hi), _ptr(lo), _stream()))
-    _count()
-    return hi, lo
+class CorrPlan:
+    """Prepared correlation workspace of one forward (tsnet_corr_prepare): class-sorted order of every mask,
+    tile classes, work list.  `rank_t` / `rank_s` are the position -> sorted-rank tables l2norm_split needs."""
+
+    def __init__(self, desc, ws, rank_t, rank_s, B, n, Cch, h, w):
+        self.desc, self.ws, self.rank_t, self.rank_s = desc, ws, rank_t, rank_s
+        self.B, self.n, self.C, self.h, self.w = B, n, Cch, h, w
 
 
-def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode,
-              temperature=100.0, want_grids=False, want_mean=True):
-    """tar_ops = (hi, lo) [B*hw, C]; src_ops = (hi, lo) [n*B*hw, C]; src_fea_list n x fp32 [B, hw, C];
-    bboxes [B, Hb, Wb] uint8 or fp32 (full resolution).  Returns (out_mean fp32 [B, hw, C], grids or None)."""
-    n = len(src_fea_list)
+def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=100.0, sort=True):
+    """model/TSNet.py:322-323, :347-348 (nearest down-sampling of the bbox masks) + the class-sorted work plan of the
+    correlation kernel.  bboxes [B, Hb, Wb] uint8 or fp32 (full resolution)."""
+    n = len(src_bbox_list)
     assert tar_bbox.dtype in (torch.uint8, torch.float32)
     assert all(bb.dtype == tar_bbox.dtype and bb.is_contiguous() for bb in src_bbox_list) and tar_bbox.is_contiguous()
     d = L.CorrDesc()
@@ -298,17 +291,82 @@ def corr_warp(tar_ops, src_ops, src_fea_list, tar_bbox, src_bbox_list, coord_tab
     d.bbox_dtype = 0 if tar_bbox.dtype == torch.uint8 else 1
     d.temperature, d.split, d.fmt = temperature, mode.split, mode.fmt
     d.operand_scale = mode.corr_scale * mode.corr_scale
+    d.sort = 1 if sort else 0
+    lib = L.load()
+    nbytes = lib.tsnet_corr_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise L.TSNetLibraryError(f"corr_prepare: {lib.tsnet_last_error().decode()}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=tar_bbox.device)
+    bb_ptrs = (C.c_void_p * n)(*[bb.data_ptr() for bb in src_bbox_list])
+    with _Prof(("corr_prepare",)):
+        L.check(lib.tsnet_corr_prepare(C.byref(d), _ptr(tar_bbox), bb_ptrs, _ptr(_f32(coord_table)), _ptr(ws), nbytes,
+                                       _stream()))
+    _count()
+    rank_t = lib.tsnet_corr_rank_table(C.byref(d), _ptr(ws), 0)
+    rank_s = lib.tsnet_corr_rank_table(C.byref(d), _ptr(ws), 1)
+    plan = CorrPlan(d, ws, rank_t, rank_s, B, n, Cch, h, w)
+    plan._keep = (tar_bbox, src_bbox_list, coord_table)
+    return plan
+
+
+def l2norm_split(fea, mode, out=None, rank=None):
+    """fea fp32 [B, hw, C] (NHWC flattened) -> (hi, lo) int16 [B*hw, C] of F.normalize(dim=C) * corr_scale.
+    rank: device pointer (int) of a [B, hw] uint16 position -> row table (CorrPlan.rank_t / rank_s) or None."""
+    B, HW, Cch = fea.shape
+    if out is None:
+        hi = torch.empty((B * HW, Cch), dtype=torch.int16, device=fea.device)
+        lo = torch.empty_like(hi)
+    else:
+        hi, lo = out
+    with _Prof(("l2norm_split",)):
+        L.check(L.load().tsnet_l2norm_split(_ptr(_f32(fea)), B, HW, Cch, mode.fmt, C.c_float(mode.corr_scale),
+                                            C.c_void_p(rank) if rank else None, _ptr(hi), _ptr(lo), _stream()))
+    _count()
+    return hi, lo
+
+
+def corr_warp(plan, tar_ops, src_ops, src_fea_list, mode, want_grids=False, want_mean=True, taps=None, c_off=0):
+    """plan = corr_prepare(...); tar_ops = (hi, lo) [B*hw, C] and src_ops = (hi, lo) [n*B*hw, C] from l2norm_split with
+    the plan's rank tables; src_fea_list n x fp32 [B, hw, C].  Returns (out_mean fp32 [B, hw, C] or None,
+    grids [n, B, h, w, 2] or None); `taps` = (hi, lo) [B, h, w, Cp]: the mean is also written as hi/lo operands into
+    the channel window [c_off, c_off + C)."""
+    n, B, h, w, Cch = plan.n, plan.B, plan.h, plan.w, plan.C
     dev = tar_ops[0].device
     out = torch.empty((B, h * w, Cch), dtype=torch.float32, device=dev) if want_mean else None
-    grids = torch.empty((n, B, h, w, 2), dtype=torch.float32, device=dev) if (want_grids or not want_mean) else None
-    fea_ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in src_fea_list])
-    bb_ptrs = (C.c_void_p * n)(*[bb.data_ptr() for bb in src_bbox_list])
-    with _Prof(("corr_warp",)):
-        L.check(L.load().tsnet_corr_warp_fwd(C.byref(d), _ptr(tar_ops[0]), _ptr(tar_ops[1]), _ptr(src_ops[0]),
-                                             _ptr(src_ops[1]), fea_ptrs, _ptr(tar_bbox), bb_ptrs, _ptr(coord_table),
-                                             _ptr(out), _ptr(grids), None, 0, _stream()))
+    grids = torch.empty((n, B, h, w, 2), dtype=torch.float32, device=dev) if want_grids else None
+    assert out is not None or grids is not None or taps is not None
+    hi, lo = taps if taps is not None else (None, None)
+    need_fea = want_mean or taps is not None
+    fea_ptrs = (C.c_void_p * n)(*[_f32(f).data_ptr() for f in src_fea_list]) if need_fea else None
+    lib = L.load()
+    with _Prof(("corr_tiles",)):
+        L.check(lib.tsnet_corr_tiles(C.byref(plan.desc), _ptr(tar_ops[0]), _ptr(tar_ops[1]), _ptr(src_ops[0]),
+                                     _ptr(src_ops[1]), _ptr(plan.ws), plan.ws.numel(), _stream()))
+    _count()
+    with _Prof(("corr_finish",)):
+        L.check(lib.tsnet_corr_finish(C.byref(plan.desc), fea_ptrs, _ptr(out), _ptr(grids), _ptr(hi), _ptr(lo),
+                                      0 if hi is None else hi.shape[-1], c_off, C.c_float(mode.act_scale),
+                                      _ptr(plan.ws), plan.ws.numel(), _stream()))
     _count()
     return out, grids
+
+
+def corr_chain(tar_fea, src_fea, tar_bbox, src_bbox_list, coord_table, mode, temperature=100.0, want_grids=True,
+               want_mean=False, taps=None, c_off=0, sort=True):
+    """The whole transformation branch on raw features (model/TSNet.py:319-366, :392): tar_fea fp32 [B, hw, C],
+    src_fea fp32 [n, B, hw, C] -> (mean of the warped sources [B, hw, C] or None, warp grids [n, B, h, w, 2] or None)."""
+    n, B, hw, Cch = src_fea.shape
+    h = w = int(round(hw ** 0.5))
+    plan = corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=temperature, sort=sort)
+    tar_ops = l2norm_split(tar_fea, mode, rank=plan.rank_t)
+    src_ops = l2norm_split(src_fea.view(n * B, hw, Cch), mode, rank=plan.rank_s)
+    return corr_warp(plan, tar_ops, src_ops, [src_fea[i] for i in range(n)], mode, want_grids=want_grids,
+                     want_mean=want_mean, taps=taps, c_off=c_off)
+
+
+def corr_grids(tar_fea, src_fea, tar_bbox, src_bbox_list, coord_table, mode, temperature=100.0, sort=True):
+    return corr_chain(tar_fea, src_fea, tar_bbox, src_bbox_list, coord_table, mode, temperature=temperature,
+                      sort=sort)[1]
 
 
 def warp_mean_taps(src_fea_list, grids, B, h, w, Cch, mode, taps=None, c_off=0, want_mean=False):
