@@ -24,6 +24,7 @@
 #include "../../include/tsnet_b200.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace tsnet {
 
@@ -43,6 +44,7 @@ struct alignas(64) ConvGemmArgs {
   float out_scale;
   int addend_rows;
   int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
+  int m_tile_begin;  // this launch covers pixel tiles [m_tile_begin, m_tile_begin + num_m_tiles) (tail-wave split)
   int Cout, num_taps, kc_per_tap, planes, split, fmt, chunk_kb;
   // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
   const float* f_residual;   // fp32 [B, H, W, Cout] or null
@@ -148,8 +150,9 @@ __device__ __forceinline__ bool tile_at(const ConvGemmArgs& args, int k, int& m_
   } else {
     const int tile = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
     if (tile >= args.num_m_tiles * args.num_n_tiles) return false;
-    m_tile = tile / args.num_n_tiles;
-    n_tile = tile - m_tile * args.num_n_tiles;
+    const int mt = tile / args.num_n_tiles;
+    n_tile = tile - mt * args.num_n_tiles;
+    m_tile = args.m_tile_begin + mt;
     return true;
   }
 }
@@ -654,6 +657,40 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
       case 64: return launch_conv_gemm_fused<64>(a, s);
       case 128: return launch_conv_gemm_fused<128>(a, s);
       default: return launch_conv_gemm_fused<256>(a, s);
+    }
+  }
+  // ---- tail-wave split.  The persistent grid runs ceil(tiles / SMs) waves; when the last wave is mostly empty
+  // (e.g. 1536 tiles on 148 SMs = 10.4 waves -> 11), the whole waves keep BLOCK_N and the remaining pixel tiles are
+  // computed by a second launch with BLOCK_N / 2 (twice as many half-cost tiles): 10.5 waves instead of 11.
+  const int sms = num_sms();
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  static const bool tail_split = getenv("TSNET_NO_TAIL_SPLIT") == nullptr;
+  if (tail_split && d->block_n >= 128 && tiles > sms && tiles % sms != 0 && d->Cout_pad % (d->block_n / 2) == 0) {
+    const int full_waves = tiles / sms;
+    const int main_m = full_waves * sms / a.num_n_tiles;
+    const int tail_m = a.num_m_tiles - main_m;
+    const int tail_tiles = tail_m * a.num_n_tiles * 2;
+    const float split_cost = static_cast<float>((main_m * a.num_n_tiles + sms - 1) / sms) +
+                             0.525f * static_cast<float>((tail_tiles + sms - 1) / sms) + 0.05f;
+    if (main_m > 0 && tail_m > 0 && split_cost < static_cast<float>((tiles + sms - 1) / sms)) {
+      ConvGemmArgs t = a;
+      const int bn2 = d->block_n / 2;
+      {
+        const uint64_t K = (uint64_t)d->num_taps * d->Cp;
+        const uint64_t dims[2] = {K, (uint64_t)d->Cout_pad};
+        const uint64_t str[1] = {K * 2};
+        const uint32_t box[2] = {64, (uint32_t)bn2};
+        int r = encode_tmap_u16_sw128(&t.b_hi, w_hi, 2, dims, str, box);
+        if (r) return r;
+        if (d->split && (r = encode_tmap_u16_sw128(&t.b_lo, w_lo, 2, dims, str, box))) return r;
+      }
+      t.m_tile_begin = main_m;
+      t.num_m_tiles = tail_m;
+      t.num_n_tiles = d->Cout_pad / bn2;
+      a.num_m_tiles = main_m;
+      int r = d->block_n == 256 ? launch_conv_gemm<256>(a, s) : launch_conv_gemm<128>(a, s);
+      if (r) return r;
+      return bn2 == 128 ? launch_conv_gemm<128>(t, s) : launch_conv_gemm<64>(t, s);
     }
   }
   switch (d->block_n) {

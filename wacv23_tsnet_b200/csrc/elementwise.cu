@@ -49,41 +49,43 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 // ------------------------------------------------------------------------------------------------
 // InstanceNorm statistics: [B*nsub, C, 2] (sum, centred M2 of 32 pixels) -> [B, C, 2] (mean, rstd)
 // block = (32 channels) x (8 segments).  All partials cover 32 pixels, so the merge is
-//   mean = (sum_k sum_k) / N ;  M2 = sum_k [ M2_k + 32 (sum_k/32 - mean)^2 ]
-// evaluated in fp64 with a fixed summation order (bit-reproducible), one division and one sqrt per (b, c).
+//   mean = (sum_k sum_k) / N ;  M2 = sum_k [ M2_k + sum_k^2 / 32 ] - N mean^2
+// evaluated in fp64 in ONE pass with a fixed summation order (bit-reproducible), one sqrt per (b, c).
 // ------------------------------------------------------------------------------------------------
-__global__ void instnorm_reduce_kernel(const float* __restrict__ part, int nsub, int C, float eps,
-                                       float* __restrict__ out) {
+constexpr int kInSegs = 16;
+__global__ void __launch_bounds__(32 * kInSegs) instnorm_reduce_kernel(const float* __restrict__ part, int nsub, int C,
+                                                                       float eps, float* __restrict__ out) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int seg = threadIdx.y;
-  __shared__ double s_acc[8][32];
-  const int per = (nsub + 7) / 8;
+  __shared__ double s_sum[kInSegs][32], s_q[kInSegs][32];
+  const int per = (nsub + kInSegs - 1) / kInSegs;
   const int k0 = seg * per, k1 = min(nsub, k0 + per);
   const float* p = part + (static_cast<size_t>(b) * nsub) * C * 2 + static_cast<size_t>(min(c, C - 1)) * 2;
-  double acc = 0.0;
-  for (int k = k0; k < k1; ++k) acc += static_cast<double>(p[static_cast<size_t>(k) * C * 2]);
-  s_acc[seg][threadIdx.x] = acc;
-  __syncthreads();
-  double total = 0.0;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) total += s_acc[s][threadIdx.x];
-  const double n = 32.0 * nsub;
-  const double mean = total / n;
-  __syncthreads();
-  acc = 0.0;
+  // single pass: S = sum_k sum_k,  Q = sum_k (M2_k + sum_k^2 / 32) = sum of squares;  M2 = Q - S^2 / N.
+  // The subtraction is done in fp64 on fp32-precision inputs: exact to ~1e-16 Q, i.e. far below fp32 resolution
+  // of the variance even when mean^2 >> var.
+  double acc_s = 0.0, acc_q = 0.0;
+#pragma unroll 4
   for (int k = k0; k < k1; ++k) {
     const float2 sm = *reinterpret_cast<const float2*>(p + static_cast<size_t>(k) * C * 2);
-    const double d = static_cast<double>(sm.x) * (1.0 / 32.0) - mean;
-    acc += static_cast<double>(sm.y) + 32.0 * d * d;
+    const double sk = static_cast<double>(sm.x);
+    acc_s += sk;
+    acc_q += static_cast<double>(sm.y) + sk * sk * (1.0 / 32.0);
   }
-  s_acc[seg][threadIdx.x] = acc;
+  s_sum[seg][threadIdx.x] = acc_s;
+  s_q[seg][threadIdx.x] = acc_q;
   __syncthreads();
   if (seg == 0 && c < C) {
-    double m2 = 0.0;
+    double total = 0.0, q = 0.0;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) m2 += s_acc[s][threadIdx.x];
-    const double var = m2 / n;  // biased, as nn.InstanceNorm2d
+    for (int s = 0; s < kInSegs; ++s) {
+      total += s_sum[s][threadIdx.x];
+      q += s_q[s][threadIdx.x];
+    }
+    const double n = 32.0 * nsub;
+    const double mean = total / n;
+    const double var = fmax(q / n - mean * mean, 0.0);  // biased, as nn.InstanceNorm2d
     float2 r;
     r.x = static_cast<float>(mean);
     r.y = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -560,7 +562,7 @@ extern "C" int tsnet_instnorm_reduce(const float* stats_partial, int B, int HW, 
                                      void* stream) {
   TSNET_ARG_CHECK(stats_partial && mean_rstd, "instnorm_reduce: null argument");
   TSNET_ARG_CHECK(HW % 32 == 0, "instnorm_reduce: HW %d", HW);
-  dim3 grid((C + 31) / 32, B), block(32, 8);
+  dim3 grid((C + 31) / 32, B), block(32, kInSegs);
   instnorm_reduce_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(stats_partial, HW / 32, C, eps,
                                                                                 mean_rstd);
   TSNET_CUDA_CHECK(cudaGetLastError());
