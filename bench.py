@@ -134,6 +134,57 @@ def cpu_forward_fps(sds_np, label_nc, n_blocks, n_source, bs, steps, warmup):
     return bs * steps / dt, torch.get_num_threads(), dt / steps
 
 
+def torch_cuda_eager_fps(sds_np, label_nc, n_blocks, n_source, bs, steps=5, warmup=2):
+    """The reference's stock op sequence (oracle port of model/TSNet.py:309-407: F.conv2d / instance_norm / bmm / softmax
+    / grid_sample ...) executed EAGERLY ON THE GPU by PyTorch + cuDNN/cuBLAS -- what running the unmodified reference
+    on this B200 costs (north star: 'the reference PyTorch-CUDA forward').  cudnn.benchmark = True as the reference's
+    demo scripts set it (demo/demo_face.py:113-114).  Two variants: PyTorch's default (cuDNN convolutions may use
+    TF32 -- NOT the fp32 function) and allow_tf32 = False (true fp32)."""
+    from oracle import tsnet_oracle as O
+    dev = torch.device("cuda")
+    inp = make_inputs(bs, label_nc, n_source, seed=4321)
+    sds = {net: {k: v.to(dev) for k, v in sd.items()} for net, sd in O.to_torch_sd(sds_np).items()}
+    src_img = [torch.from_numpy(x).to(dev) / 255.0 for x in inp["src_img"]]
+    src_lbl = [torch.from_numpy(x).to(dev) for x in inp["src_lbl"]]
+    src_bbox = [torch.from_numpy(x).to(dev).float().unsqueeze(1) for x in inp["src_bbox"]]
+    tar_lbl = torch.from_numpy(inp["tar_lbl"]).to(dev)
+    tar_bbox = torch.from_numpy(inp["tar_bbox"]).to(dev).float().unsqueeze(1)
+
+    @torch.no_grad()
+    def fwd():
+        src_fea = [O.encoder_forward(torch.cat([src_img[i], src_lbl[i]], dim=1), sds["img_enc"], 9)
+                   for i in range(n_source)]
+        tar_fea = O.encoder_forward(tar_lbl, sds["lbl_enc"], 0)
+        pg_mean, _ = O.corr_warp(tar_fea, src_fea, tar_bbox, src_bbox)
+        sg = [O.fuse_forward(src_fea[i], tar_fea, sds["fuse_net"]) for i in range(n_source)]
+        sg_mean = torch.stack(sg, dim=1).mean(dim=1)
+        return O.decoder_forward(pg_mean, sg_mean, sds["dec"], n_blocks)
+
+    out = {}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for tag, tf32 in (("default_tf32_convs", True), ("fp32_no_tf32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(warmup):
+                fwd()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"frames_per_s": bs / (ms * 1e-3), "ms_per_step": ms}
+            log(f"torch-cuda eager port ({tag}): {ms:.1f} ms / step of bs={bs}")
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    del sds, src_img, src_lbl
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -268,7 +319,7 @@ def run_b200(args):
     total_ms = sum(v[0] for v in kern.values()) or 1.0
     roof, roof_corr, shares = None, None, {}
     if kern:
-        for key, (t, c) in sorted(kern.items(), key=lambda kv: -kv[1][0])[:6]:
+        for key, (t, c) in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]:
             shares[str(key)] = {"ms_per_step": t / args.steps, "launches_per_step": c / args.steps,
                                 "share_of_kernel_time": t / total_ms}
         conv_keys = [k for k in kern if k[0] == "conv_gemm"]
@@ -317,6 +368,18 @@ def run_b200(args):
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "5 forwards of bs=1 of the same config (oracle/tsnet_oracle.py = bit-exact CPU "
                              "restatement of the reference forward), 1 warm-up"}
+        eager = None
+        if world == 1 and args.torch_cuda_baseline:
+            sds_np = {k: {kk: vv.detach().cpu().numpy() for kk, vv in getattr(net, k).state_dict().items()}
+                      for k in D.GENERATOR_NETS}
+            try:
+                eager = torch_cuda_eager_fps(sds_np, L, nb, n, bs)
+                eager["what"] = ("oracle port of the reference's torch ops run eagerly on this GPU (cuDNN / cuBLAS), "
+                                 "same config and batch; informational -- the reference arm of this tier is the CPU run")
+                eager["speedup_of_value_vs_fp32"] = value / world / eager["fp32_no_tf32"]["frames_per_s"]
+                eager["speedup_of_value_vs_default_tf32"] = value / world / eager["default_tf32_convs"]["frames_per_s"]
+            except Exception as e:  # never let the informational leg break the bench line
+                eager = {"error": repr(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
@@ -332,7 +395,7 @@ def run_b200(args):
                         "api": "FramePipeline.run (H2D / forward / D2H of consecutive batches overlapped)"
                         if args.e2e_mode == "pipelined" else "set_test_input + forward + rec_tar_img.cpu()"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_corr_warp": roof_corr,
-                "kernel_shares": shares, "cpu_baseline": cpu}
+                "kernel_shares": shares, "cpu_baseline": cpu, "torch_cuda_eager_port": eager}
         print(json.dumps(line), flush=True)
     if world > 1:
         tdist.barrier()
@@ -352,6 +415,8 @@ def main():
                     help="fp16x3 is the parity-grade default; single-pass modes are non-parity speed points")
     ap.add_argument("--pose", action="store_true", help="TSNet_pose, label_nc=25 (BASELINE.json config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-cuda-baseline", dest="torch_cuda_baseline", action="store_true",
+                    help="also time the reference's torch op sequence eagerly on the GPU (cuDNN), bs = --batch")
     ap.add_argument("--e2e-mode", dest="e2e_mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined: wacv23_tsnet_b200.pipeline.FramePipeline; sync: set_test_input + forward + .cpu()")
     args = ap.parse_args()

@@ -56,8 +56,8 @@ def linspace_table(n):
 def coord_channels(x):
     """Encoder.coord_conv, model/TSNet.py:107-125: append x, y in [-1,1] and r = sqrt(x^2+y^2)."""
     bs, _, h, w = x.shape
-    xx = torch.arange(w, dtype=x.dtype).view(1, 1, 1, w).expand(bs, 1, h, w)
-    yy = torch.arange(h, dtype=x.dtype).view(1, 1, h, 1).expand(bs, 1, h, w)
+    xx = torch.arange(w, dtype=x.dtype, device=x.device).view(1, 1, 1, w).expand(bs, 1, h, w)
+    yy = torch.arange(h, dtype=x.dtype, device=x.device).view(1, 1, h, 1).expand(bs, 1, h, w)
     xx = 2 * (xx.float() / (w - 1)) - 1
     yy = 2 * (yy.float() / (h - 1)) - 1
     rr = torch.sqrt(torch.pow(xx, 2) + torch.pow(yy, 2))
@@ -127,6 +127,14 @@ def get_grid(b, H, W):
     return torch.stack([gx, gy], -1).unsqueeze(0).repeat(b, 1, 1, 1).float()
 
 
+def _down_mask(bbox, h, w):
+    """CPU: the numpy restatement above (pinned against the reference).  CUDA tensors (bench.py's PyTorch-CUDA eager
+    timing of this port only): the reference's own call, F.interpolate(mode='nearest') (model/TSNet.py:322, :347)."""
+    if bbox.is_cuda:
+        return F.interpolate(bbox, size=(h, w), mode="nearest")
+    return torch.from_numpy(nearest_downsample_mask(bbox.numpy(), h, w))
+
+
 def corr_warp(tar_fea, src_fea_list, tar_bbox, src_bbox_list, temperature=100.0):
     """model/TSNet.py:319-323, 336-366, 392.
 
@@ -137,14 +145,14 @@ def corr_warp(tar_fea, src_fea_list, tar_bbox, src_bbox_list, temperature=100.0)
     b, c, h, w = tar_fea.shape
     dt = tar_fea.dtype  # fp32 = the reference; tests also evaluate this in fp64 as the "truth"
     t = F.normalize(tar_fea, p=2, dim=1).view(b, c, h * w).transpose(1, 2)
-    mt = torch.from_numpy(nearest_downsample_mask(tar_bbox.numpy(), h, w)).view(b, 1, h * w).transpose(1, 2)
-    grid2d = get_grid(b, h, w).view(b, h * w, 2).to(dt)
+    mt = _down_mask(tar_bbox, h, w).view(b, 1, h * w).transpose(1, 2)
+    grid2d = get_grid(b, h, w).view(b, h * w, 2).to(dt).to(tar_fea.device)
     if dt == torch.float64:
         mt = mt.to(dt)
     warped, grids = [], []
     for src_fea, src_bbox in zip(src_fea_list, src_bbox_list):
         s = F.normalize(src_fea, p=2, dim=1).view(b, c, h * w)
-        ms = torch.from_numpy(nearest_downsample_mask(src_bbox.numpy(), h, w)).view(b, 1, h * w)
+        ms = _down_mask(src_bbox, h, w).view(b, 1, h * w)
         if dt == torch.float64:
             ms = ms.to(dt)
         a = torch.bmm(t * mt, s * ms) + torch.bmm(t * (1.0 - mt), s * (1.0 - ms))

@@ -168,9 +168,21 @@ def test_stem_taps_and_stem_conv(label_nc):
     for s in range(7):
         assert _relerr(got[..., s * cin:(s + 1) * cin], fp[:, :, :, s:s + 128].permute(0, 2, 3, 1) * m.act_scale) < 2e-6
     assert float(got[..., 7 * cin:].abs().max()) == 0.0
-    y, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)
+    y, st = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)   # vertical-reuse stem kernel
     ref = F.conv2d(fp.double(), w.double(), b.double()).permute(0, 2, 3, 1).float()
     assert _relerr(y, ref) < CONV_TOL["fp16x3"]
+    import os
+    os.environ["TSNET_NO_VR"] = "1"                                             # plain implicit-GEMM kernel
+    try:
+        y2, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)
+    finally:
+        del os.environ["TSNET_NO_VR"]
+    assert torch.equal(y, y2)   # same accumulation order per element -> bit-identical
+    # InstanceNorm statistics from its partials (different 32-pixel grouping than the plain kernel: 2 rows x 16 px)
+    mr = ops.instnorm_reduce(st, 2, 128 * 128, 64)
+    y64 = y.double().view(2, -1, 64)
+    assert float((mr[..., 0] - y64.mean(1).float()).abs().max()) < 1e-5
+    assert _relerr(mr[..., 1], (1.0 / torch.sqrt(y64.var(1, unbiased=False) + 1e-5)).float()) < 1e-5
 
 
 def test_l2norm_and_head():

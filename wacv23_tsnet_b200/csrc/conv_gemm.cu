@@ -62,7 +62,10 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo of both operands
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 6 ? 6 : (kSmemBudget / kStageBytes);
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // all 512 TMEM columns as chunk accumulators (2 / 4 / 8 for BLOCK_N 256 / 128 / 64): with narrow tiles the MMA pipe
+  // runs several chunks ahead, so the accumulate warps' per-tile epilogue overlaps tensor work
+  static constexpr int kTmemBufs = 512 / BLOCK_N;
+  static constexpr int kTmemCols = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   // fused-IN variant: + per-warp partials [4][N] float2, per-CTA partials [2][N] double2 (read by peers over DSMEM),
   // (mean, rstd) [N] float2
@@ -165,9 +168,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* stats_ready = tmem_empty + 3;  // fused variant: 8 arrivals (one per CTA of the cluster) per item
+  uint64_t* tmem_empty = tmem_full + Cfg::kTmemBufs;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::kTmemBufs);
+  uint64_t* stats_ready = tmem_empty + Cfg::kTmemBufs + 1;  // fused variant: 8 arrivals (one per CTA of the cluster) per item
   // fused-variant scratch behind the barrier block
   uint8_t* fx = smem + Cfg::kStages * Cfg::kStageBytes + 256;
   float2* s_part = reinterpret_cast<float2*>(fx);                                  // [4][BLOCK_N]
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < Cfg::kTmemBufs; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kAccWarps);  // one arrive per accumulate warp
     }
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane_id() == 0) {
+    {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
       const uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, args.fmt);
       int stage = 0;
       uint32_t phase = 0;
@@ -251,8 +254,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       int m_tile, n_tile;
       for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile); ++kt) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
-          const int buf = cc & 1;
-          const uint32_t buf_phase = (cc >> 1) & 1;
+          const int buf = cc % Cfg::kTmemBufs;
+          const uint32_t buf_phase = (cc / Cfg::kTmemBufs) & 1;
           mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
@@ -268,16 +271,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint32_t off = k * kUmmaK * 2;
-              umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+              umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
               if (args.split) {
-                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
               }
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[buf]);
+          umma_commit_elect(&tmem_full[buf]);
         }
       }
     }
@@ -296,8 +299,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < NC; ++j) acc[j] = 0.f;
       for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
-        const int buf = cc & 1;
-        const uint32_t buf_phase = (cc >> 1) & 1;
+        const int buf = cc % Cfg::kTmemBufs;
+        const uint32_t buf_phase = (cc / Cfg::kTmemBufs) & 1;
         mbar_wait(&tmem_full[buf], buf_phase);
         tc_fence_after();
         const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * NC;
@@ -501,6 +504,233 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Vertical-reuse variant for the kw-folded 7x7 stems (Cout = 64, one 64-channel K block per vertical tap).
+// In the plain kernel every tap re-fetches its own 128-pixel A tile and the weights are re-fetched per tile: 338 KB from
+// L2 for 84 MMAs of N = 64 (2688 tensor cycles) -- L2-bound at a third of the tensor rate (1.97 ms for 96 samples).
+// Here the tile is 8 rows x 16 pixels: ONE TMA box of (8 + taps - 1) rows x 16 px x 64 ch is the halo of all vertical
+// taps -- tap dy is the same shared-memory tile shifted by dy rows = dy * 2048 B, a multiple of the 1024 B swizzle
+// atom, so it is just a different UMMA descriptor start address -- and the packed weights of all taps (16 KB per tap)
+// stay resident in shared memory for the whole kernel.  L2 traffic per tile: 56 KB.
+// Accumulation order per output element is identical to the plain kernel (chunks of chunk_kb taps promoted to
+// registers), so the two kernels are bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int kVrRows = 8, kVrW = 16, kVrN = 64;
+constexpr int kVrBTap = kVrN * kBlockK * 2;  // 8 KB: one tap of the packed weight (hi or lo)
+// all 512 TMEM columns as 8 chunk accumulators: the MMA pipe runs up to two tiles ahead of the accumulate warps, so
+// their per-tile epilogue (store + statistics) overlaps tensor work instead of stalling it after 2 chunks
+constexpr int kVrTmemBufs = 8;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __grid_constant__ ConvGemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int taps = args.num_taps;
+  const int a_bytes = (kVrRows + taps - 1) * kVrW * 128;  // one halo tile (hi or lo); multiple of 2048
+  uint8_t* b_sm = smem;                                  // [hi: taps x 8 KB][lo: taps x 8 KB]
+  uint8_t* a_sm = smem + 2 * taps * kVrBTap;             // 2 buffers x [hi][lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_sm + 4 * a_bytes);
+  uint64_t* b_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = bars + 3;
+  uint64_t* tmem_full = bars + 5;
+  uint64_t* tmem_empty = bars + 5 + kVrTmemBufs;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kVrTmemBufs);
+
+  const int warp = threadIdx.x >> 5;
+  const int num_tiles = args.num_m_tiles;
+  const int tiles_x = args.wtiles_per_row;  // W / 16
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&args.a_hi);
+    tma_prefetch_desc(&args.b_hi);
+    if (args.split) {
+      tma_prefetch_desc(&args.a_lo);
+      tma_prefetch_desc(&args.b_lo);
+    }
+  }
+  if (warp == 1 && lane_id() == 0) {
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kVrTmemBufs; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kAccWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, kVrTmemBufs * kVrN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane_id() == 0) {
+        mbar_arrive_expect_tx(b_full, (args.split ? 2u : 1u) * taps * kVrBTap);
+        for (int t = 0; t < taps; ++t) {
+          tma_load_2d(b_sm + t * kVrBTap, &args.b_hi, b_full, t * kBlockK, 0);
+          if (args.split) tma_load_2d(b_sm + (taps + t) * kVrBTap, &args.b_lo, b_full, t * kBlockK, 0);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          const int buf = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          const int m_tile = args.m_tile_begin + tile;
+          const int img = m_tile / args.tiles_per_img;
+          const int t = m_tile - img * args.tiles_per_img;
+          const int ty = t / tiles_x, tx = t - ty * tiles_x;
+          mbar_wait(&a_empty[buf], ph ^ 1);
+          uint8_t* st = a_sm + buf * 2 * a_bytes;
+          mbar_arrive_expect_tx(&a_full[buf], (args.split ? 2u : 1u) * a_bytes);
+          const int cn = img * args.planes + args.tap_plane[0];
+          tma_load_4d(st, &args.a_hi, &a_full[buf], 0, tx * kVrW + args.tap_dx[0], ty * kVrRows + args.tap_dy[0], cn);
+          if (args.split)
+            tma_load_4d(st + a_bytes, &args.a_lo, &a_full[buf], 0, tx * kVrW + args.tap_dx[0],
+                        ty * kVrRows + args.tap_dy[0], cn);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
+        const uint32_t idesc = make_idesc_f16(kBlockM, kVrN, args.fmt);
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(b_sm);
+        int it = 0, cc = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+          const int buf = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(&a_full[buf], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_sm + buf * 2 * a_bytes);
+          for (int t0 = 0; t0 < taps; t0 += args.chunk_kb, ++cc) {
+            const int tb = cc % kVrTmemBufs;
+            const uint32_t tb_phase = (cc / kVrTmemBufs) & 1;
+            mbar_wait(&tmem_empty[tb], tb_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + tb * kVrN;
+            const int t1 = min(taps, t0 + args.chunk_kb);
+            for (int t = t0; t < t1; ++t) {
+              const uint32_t a_off = static_cast<uint32_t>(args.tap_dy[t] - args.tap_dy[0]) * (kVrW * 128);
+              const uint64_t a_hi = make_desc_kmajor_sw128(a_base + a_off);
+              const uint64_t a_lo = make_desc_kmajor_sw128(a_base + a_bytes + a_off);
+              const uint64_t b_hi = make_desc_kmajor_sw128(b_base + t * kVrBTap);
+              const uint64_t b_lo = make_desc_kmajor_sw128(b_base + (taps + t) * kVrBTap);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint32_t off = k * kUmmaK * 2;
+                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((t - t0) | k) != 0);
+                if (args.split) {
+                  umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                  umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                }
+              }
+            }
+            umma_commit_elect(&tmem_full[tb]);
+          }
+          umma_commit_elect(&a_empty[buf]);  // the halo tile may be overwritten once these MMAs have read it
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== accumulate + epilogue =====================
+    constexpr int NC = kVrN / 2;
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane_id();
+    int cc = 0;
+    // the single channel slab never changes: keep its bias in registers (a per-tile __ldg was 20 % of the warps' time)
+    float bias_r[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) bias_r[j] = (args.bias && half * NC + j < args.Cout) ? __ldg(args.bias + half * NC + j) : 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float acc[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+      for (int t0 = 0; t0 < taps; t0 += args.chunk_kb, ++cc) {
+        const int tb = cc % kVrTmemBufs;
+        const uint32_t tb_phase = (cc / kVrTmemBufs) & 1;
+        mbar_wait(&tmem_full[tb], tb_phase);
+        tc_fence_after();
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tb * kVrN + half * NC, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += v[j];  // fp32 round-to-nearest promotion
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&tmem_empty[tb]);
+      }
+      const int m_tile = args.m_tile_begin + tile;
+      const int img = m_tile / args.tiles_per_img;
+      const int t = m_tile - img * args.tiles_per_img;
+      const int ty = t / tiles_x, tx = t - ty * tiles_x;
+      const int y = ty * kVrRows + (row >> 4), x = tx * kVrW + (row & 15);
+      const size_t gm = (static_cast<size_t>(img) * args.f_H + y) * args.f_W + x;
+      const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
+      float* yrow = args.y + gm * args.Cout;
+      float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
+      const int n0 = half * NC;
+      if (n0 < args.Cout) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(acc[j], args.out_scale, bias_r[j]);
+        if (arow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow + n0 + j));
+            v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (srow) {
+          float tt[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tt[j] = v[j];
+          const float colsum = warp_col_sums(tt);
+          const float mean_l = colsum * (1.f / 32.f);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float mj = __shfl_sync(0xffffffffu, mean_l, j);
+            const float dlt = v[j] - mj;
+            tt[j] = dlt * dlt;
+          }
+          const float m2 = warp_col_sums(tt);
+          *reinterpret_cast<float2*>(srow + (n0 + lane_id()) * 2) = make_float2(colsum, m2);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kVrTmemBufs * kVrN);
+  }
+}
+
+static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream) {
+  const int a_bytes = (kVrRows + a.num_taps - 1) * kVrW * 128;
+  const int smem_bytes = 2 * a.num_taps * kVrBTap + 4 * a_bytes + 1024 + 256;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_vr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes = smem_bytes;
+  }
+  const int grid = a.num_m_tiles < num_sms() ? a.num_m_tiles : num_sms();
+  conv_gemm_vr_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(a);
+  TSNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 template <int BLOCK_N>
 static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -657,6 +887,28 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
       case 64: return launch_conv_gemm_fused<64>(a, s);
       case 128: return launch_conv_gemm_fused<128>(a, s);
       default: return launch_conv_gemm_fused<256>(a, s);
+    }
+  }
+  // ---- vertical-reuse kernel for the kw-folded stems (see conv_gemm_vr_kernel)
+  {
+    const bool vr_enabled = getenv("TSNET_NO_VR") == nullptr;  // (tests compare the two kernels)
+    bool vr = vr_enabled && !d->fuse_in && d->block_n == 64 && d->Cout_pad == 64 && d->Cp == 64 && d->num_taps > 1 &&
+              d->W % kVrW == 0 && d->H % kVrRows == 0;
+    for (int t = 0; vr && t < d->num_taps; ++t)
+      vr = d->tap_dx[t] == d->tap_dx[0] && d->tap_plane[t] == d->tap_plane[0] && d->tap_dy[t] == d->tap_dy[0] + t;
+    const int a_bytes = (kVrRows + d->num_taps - 1) * kVrW * 128;
+    if (vr && 2 * d->num_taps * kVrBTap + 4 * a_bytes + 1280 <= 227 * 1024) {
+      const uint64_t dims[4] = {(uint64_t)d->Cp, (uint64_t)d->Wp, (uint64_t)d->Hp, (uint64_t)d->B * d->planes};
+      const uint64_t str[3] = {(uint64_t)d->Cp * 2, (uint64_t)d->Wp * d->Cp * 2, (uint64_t)d->Hp * d->Wp * d->Cp * 2};
+      const uint32_t box[4] = {64, (uint32_t)kVrW, (uint32_t)(kVrRows + d->num_taps - 1), 1};
+      int r = encode_tmap_u16_sw128(&a.a_hi, taps_hi, 4, dims, str, box);
+      if (r) return r;
+      if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, taps_lo, 4, dims, str, box))) return r;
+      a.wtiles_per_row = d->W / kVrW;
+      if (const char* e = getenv("TSNET_VR_CHUNK")) a.chunk_kb = atoi(e) > 0 ? atoi(e) : a.chunk_kb;  // experiments only
+      a.f_H = d->H;
+      a.f_W = d->W;
+      return launch_conv_gemm_vr(a, s);
     }
   }
   // ---- tail-wave split.  The persistent grid runs ceil(tiles / SMs) waves; when the last wave is mostly empty

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane_id() == 0) {
+      {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
         const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
         int stage = 0;
         uint32_t phase = 0;
@@ -390,16 +390,16 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
 #pragma unroll
               for (int k = 0; k < kCorrK / 16; ++k) {
                 const uint32_t off = k * 32;
-                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
                 if (args.split) {
-                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                  umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
                 }
               }
-              umma_commit(&tl.empty_bar[stage]);
+              umma_commit_elect(&tl.empty_bar[stage]);
               if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tl.tmem_full[buf]);
+            umma_commit_elect(&tl.tmem_full[buf]);
           }
         }
       }

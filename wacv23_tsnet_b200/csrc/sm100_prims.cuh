@@ -132,6 +132,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The MMA issuer warp runs CONVERGED and one elected lane issues (CUTLASS's pattern).  Issuing from inside an
+// `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop with per-lane predicate
+// shuffling: ~12 SASS instructions = ~60 issue cycles per MMA, more than the 32 (N = 64) or 64 (N = 128) tensor
+// cycles the instruction takes -- measured 28 % tensor-pipe utilisation on the N = 64 stem kernel.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (elect_one()) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -154,6 +162,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
 }
 
 // ------------------------------------------------------------------------------------------------
