@@ -238,6 +238,27 @@ int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, co
 int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* ref_mean3, const float* ref_std3,
                          const float* img_mean3_host, uint8_t* out_hwc_rgb, void* stream);
 
+/* ---- train-mode branches inside forward() (forward only) ---------------------------------
+ * model/TSNet.py:327-331 (target image statistics), :372-390 (image-space warp: F.unfold(src_img, 8, 8) ->
+ * grid_sample with the warp grid -> F.fold; per-image re-normalisation to the target's mean / unbiased std; warp loss
+ * 10 * L1), :402-405 (alignment loss 1 - mean cosine similarity of the two branch means; pass NULL means for the pose
+ * variant, which has no such loss) and model/TSNet_pose.py:395-396 (foreground compositing, fore = columns
+ * [fore_x0, fore_x1), fill = -mean/255; pass fore_x1 <= fore_x0 to disable).
+ *   src_img    n_src host-array pointers to RAW NCHW images [B,3,H,W]; src_div[i] = 255 or 1 (use_prev), host array
+ *   tar_img    raw NCHW target image, divided by tar_div
+ *   grids      [n_src, B, h, w, 2] from tsnet_corr_warp_fwd
+ *   pg_mean / sg_mean  fp32 NHWC [B, h*w, C] branch means (or both NULL)
+ *   warp_out   [n_src, B, 3, H, W]  = the reference's warp_src_img_list
+ *   losses2    device float[2] = (loss_warp, loss_align)
+ * All reductions are fp64 with a fixed order (bit-reproducible). */
+size_t tsnet_train_extras_workspace_bytes(int B, int n_src, int h, int w);
+int tsnet_train_extras_fwd(const float* const* src_img, const float* src_div, int n_src, const float* tar_img,
+                           float tar_div, const float* grids, int B, int H, int W, int h, int w, const float* pg_mean,
+                           const float* sg_mean, int C, int fore_x0, int fore_x1, const float* fill3, float* warp_out,
+                           float* losses2, void* workspace, size_t workspace_bytes, void* stream);
+/* (mean, unbiased std) of x / div over each of `planes` contiguous runs of n floats -> mean_std [planes, 2] */
+int tsnet_plane_stats(const float* x, int planes, int n, float div, float* mean_std, void* stream);
+
 /* ---- reference-style direct convolution (validation kernel, fp32 SIMT) ----------------------------
  * Plain NHWC direct convolution with zero or reflect padding; used by the tests to cross-check the
  * tensor-core path on device and by nothing on the hot path. */

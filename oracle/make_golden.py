@@ -50,7 +50,50 @@ def case_checksums(sds, inputs):
     return np.array([fold(ws), fold(xs)], np.int64)
 
 
+# train-mode forward branches: name -> (base config, use_prev)
+TRAIN_CONFIGS = {
+    "train_quickstart_bs1": ("quickstart_bs1", None),
+    "train_pose_bs1_nb4": ("pose_bs1_nb4", None),
+    "train_face_bs2_n1_useprev": ("face_bs2_n1", [True]),
+}
+
+
+def make_train_goldens():
+    """Reference forward with the is_train branches active (see ref_harness.reference_forward) vs the restatement:
+    bit-exact warp_src_img_list / loss_warp / loss_align required; fixtures store the warped images at half
+    resolution plus the losses."""
+    for name, (base, use_prev) in TRAIN_CONFIGS.items():
+        t0 = time.time()
+        cfg = CONFIGS[base]
+        sds, inputs = build_case(cfg)
+        mean = synth.IMG_MEAN if cfg["pose"] else None
+        ref = ref_harness.reference_forward(sds, inputs, cfg["label_nc"], cfg["n_blocks"], pose=cfg["pose"],
+                                            pose_mean=mean, n_source=cfg["n_source"], train=True, use_prev=use_prev)
+        ora = tsnet_oracle.tsnet_forward(sds, inputs, cfg["n_blocks"], pose_mean=mean, train=True, use_prev=use_prev)
+        ok = torch.equal(ref["rec_tar_img"], ora["rec_tar_img"])
+        ok &= all(torch.equal(a, b) for a, b in zip(ref["warp_src_img_list"], ora["warp_src_img_list"]))
+        ok &= torch.equal(ref["loss_warp"], ora["loss_warp"])
+        if not cfg["pose"]:
+            ok &= torch.equal(ref["loss_align"], ora["loss_align"])
+        print(f"{name}: oracle==reference (image, warped sources, losses) {ok}  [{time.time()-t0:.1f}s]")
+        if not ok:
+            sys.exit(f"oracle restatement of the train-mode branches is NOT bit-exact with the reference on {name}")
+        np.savez_compressed(
+            os.path.join(GOLDEN_DIR, name + ".npz"),
+            rec_tar_img_s2=ref["rec_tar_img"][..., ::2, ::2].numpy(),
+            warp_s2=torch.stack(ref["warp_src_img_list"])[..., ::2, ::2].numpy(),
+            loss_warp=ref["loss_warp"].numpy(),
+            loss_align=(ref["loss_align"].numpy() if not cfg["pose"] else np.float32(0)),
+            checks=case_checksums(sds, inputs),
+        )
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        if not ref_harness.available():
+            sys.exit("reference not found: goldens can only be (re)generated in the build container")
+        torch.set_num_threads(os.cpu_count())
+        return make_train_goldens()
     if not ref_harness.available():
         sys.exit("reference not found: goldens can only be (re)generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)

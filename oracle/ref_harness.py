@@ -52,9 +52,13 @@ def _cuda_is_identity():
 
 
 @torch.no_grad()
-def reference_forward(sds, inputs, label_nc, n_blocks, pose=False, pose_mean=None, n_source=3):
+def reference_forward(sds, inputs, label_nc, n_blocks, pose=False, pose_mean=None, n_source=3, train=False,
+                      use_prev=None):
     """Build reference TSNet(is_train=False, ...), load `sds` (numpy state dicts), run set_test_input +
-    forward() on CPU.  Returns dict with rec_tar_img (+ warp grids for the face variant)."""
+    forward() on CPU.  Returns dict with rec_tar_img (+ warp grids for the face variant).
+    train=True: the is_train=True branches of forward() are exercised.  Constructing the reference with is_train=True
+    needs a VGG19 download (model/TSNet.py:545), so the generator-only model is built and its `is_train` attribute is
+    flipped before set_train_input + forward(): forward() itself reads nothing else that is_train=True would create."""
     with _reference_on_path(), _cuda_is_identity(), contextlib.redirect_stdout(io.StringIO()):
         if pose:
             from model.TSNet_pose import TSNet
@@ -67,12 +71,25 @@ def reference_forward(sds, inputs, label_nc, n_blocks, pose=False, pose_mean=Non
         for name in ("img_enc", "lbl_enc", "fuse_net", "dec"):
             getattr(net, name).load_state_dict({k: torch.from_numpy(v) for k, v in sds[name].items()})
         net.eval()
-        net.set_test_input([torch.from_numpy(x) for x in inputs["src_img"]],
-                           [torch.from_numpy(x) for x in inputs["src_lbl"]],
-                           [torch.from_numpy(x) for x in inputs["src_bbox"]],
-                           torch.from_numpy(inputs["tar_lbl"]), torch.from_numpy(inputs["tar_bbox"]))
+        if train:
+            net.is_train = True
+            net.set_train_input([torch.from_numpy(x) for x in inputs["src_img"]],
+                                [torch.from_numpy(x) for x in inputs["src_lbl"]],
+                                [torch.from_numpy(x) for x in inputs["src_bbox"]],
+                                torch.from_numpy(inputs["tar_img"]), torch.from_numpy(inputs["tar_lbl"]),
+                                torch.from_numpy(inputs["tar_bbox"]), use_prev=use_prev)
+        else:
+            net.set_test_input([torch.from_numpy(x) for x in inputs["src_img"]],
+                               [torch.from_numpy(x) for x in inputs["src_lbl"]],
+                               [torch.from_numpy(x) for x in inputs["src_bbox"]],
+                               torch.from_numpy(inputs["tar_lbl"]), torch.from_numpy(inputs["tar_bbox"]))
         net.forward()
         out = {"rec_tar_img": net.rec_tar_img.clone()}
         if not pose:
             out["grids"] = [g.clone() for g in net.warp_grid2d_list]
+        if train:
+            out["warp_src_img_list"] = [x.clone() for x in net.warp_src_img_list]
+            out["loss_warp"] = net.loss_warp.clone()
+            if not pose:
+                out["loss_align"] = net.loss_align.clone()
         return out

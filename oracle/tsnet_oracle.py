@@ -194,8 +194,40 @@ def stage_inputs(inputs, use_prev=None):
     return st
 
 
+def train_extras(src_img_list, tar_img, grids, pg_mean, sg_mean, pose_mean=None):
+    """The train-only branches INSIDE forward(), restated op by op:
+    model/TSNet.py:327-331 (reference statistics of the target image), :372-390 (image-space warp through
+    unfold -> grid_sample -> fold, per-image re-normalisation, 10 * L1 warp loss), :402-405 (cosine alignment loss of the
+    two branch means; face variant only) and model/TSNet_pose.py:395-396 (foreground compositing of the warped image).
+    src_img_list / tar_img are the STAGED images (already /255 unless use_prev).  Returns (warp_src_img_list,
+    loss_warp, loss_align or None)."""
+    b = tar_img.shape[0]
+    h, w = grids[0].shape[1:3]
+    ref_mean = tar_img.view(b, 3, -1).mean(dim=2).view(b, 3, 1, 1)
+    ref_std = tar_img.view(b, 3, -1).std(dim=2).view(b, 3, 1, 1)
+    warp_list, losses = [], []
+    for src_img, g in zip(src_img_list, grids):
+        ori_h = src_img.shape[2]
+        down = ori_h // h
+        src_down = F.unfold(src_img, down, stride=down).view(b, -1, h, w)
+        rec_down = F.grid_sample(src_down, g, align_corners=False).view(b, -1, h * w)
+        warp = F.fold(rec_down, 256, down, stride=down)
+        gen_mean = warp.view(b, 3, -1).mean(dim=2).view(b, 3, 1, 1)
+        gen_std = warp.view(b, 3, -1).std(dim=2).view(b, 3, 1, 1)
+        warp = (warp - gen_mean) / gen_std * ref_std + ref_mean
+        if pose_mean is not None:
+            warp = pose_composite(warp, pose_mean)
+        warp_list.append(warp)
+        losses.append(10 * F.l1_loss(warp, tar_img))
+    loss_warp = sum(losses)
+    loss_align = None
+    if pose_mean is None:
+        loss_align = 1 - (F.cosine_similarity(pg_mean, sg_mean, dim=1)).mean()
+    return warp_list, loss_warp, loss_align
+
+
 @torch.no_grad()
-def tsnet_forward(sds, inputs, n_blocks, pose_mean=None, n_source=None, use_prev=None):
+def tsnet_forward(sds, inputs, n_blocks, pose_mean=None, n_source=None, use_prev=None, train=False):
     """TSNet.forward for is_train=False, model/TSNet.py:309-407 (+ TSNet_pose.py:416-417 when pose_mean
     is given).  sds: dict of four state dicts (numpy or torch); inputs: synth dict (numpy).
     Returns dict of intermediates (torch CPU tensors)."""
@@ -212,5 +244,10 @@ def tsnet_forward(sds, inputs, n_blocks, pose_mean=None, n_source=None, use_prev
     rec = decoder_forward(pg_mean, sg_mean, sds["dec"], n_blocks)
     if pose_mean is not None:
         rec = pose_composite(rec, pose_mean)
-    return {"src_fea": src_fea, "tar_fea": tar_fea, "grids": grids, "pg_mean": pg_mean,
-            "sg_mean": sg_mean, "rec_tar_img": rec}
+    out = {"src_fea": src_fea, "tar_fea": tar_fea, "grids": grids, "pg_mean": pg_mean,
+           "sg_mean": sg_mean, "rec_tar_img": rec}
+    if train:  # is_train=True branches of forward(); needs inputs["tar_img"]
+        tar_img = torch.from_numpy(inputs["tar_img"]) / 255.0
+        warp_list, loss_warp, loss_align = train_extras(st["src_img"][:n], tar_img, grids, pg_mean, sg_mean, pose_mean)
+        out.update(warp_src_img_list=warp_list, loss_warp=loss_warp, loss_align=loss_align)
+    return out

@@ -80,8 +80,13 @@ def test_rejects_impossible_geometry_and_training(cuda_off_shim):
     from wacv23_tsnet_b200.model.TSNet import TSNet
     with pytest.raises(ValueError):
         TSNet(is_train=False, label_nc=2, n_downsampling=4)  # FuseNet(1024) only fits ngf*2^n = 512
-    with pytest.raises(NotImplementedError):
-        TSNet(is_train=True, label_nc=2, n_downsampling=3)  # needs VGG19 download; training is out of scope
+    # is_train=True is forward-only here: the generator is built (no VGG19 download, no discriminators) and everything
+    # that needs a backward pass raises
+    net = TSNet(is_train=True, label_nc=2, n_downsampling=3)
+    assert net.is_train and not hasattr(net, "netD")
+    for fn in (net.optimize_parameters, net.setup, net.print_learning_rate, net.get_current_losses):
+        with pytest.raises(NotImplementedError):
+            fn()
 
 
 def test_input_staging_matches_reference_semantics(cuda_off_shim):

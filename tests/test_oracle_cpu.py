@@ -68,6 +68,23 @@ def test_oracle_reproduces_golden(name, golden_dir):
         assert torch.equal(out["rec_tar_img"][..., :64], fill.expand(cfg["bs"], 3, 256, 64))
 
 
+@pytest.mark.parametrize("name", ["train_quickstart_bs1"])
+def test_oracle_train_branches_reproduce_golden(name, golden_dir):
+    """is_train=True branches of forward() (model/TSNet.py:327-331, 372-390, 402-405) against the reference fixture."""
+    base, use_prev = MG.TRAIN_CONFIGS[name]
+    cfg = MG.CONFIGS[base]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    sds, inputs = MG.build_case(cfg)
+    assert (MG.case_checksums(sds, inputs) == gold["checks"]).all()
+    out = O.tsnet_forward(sds, inputs, cfg["n_blocks"], pose_mean=synth.IMG_MEAN if cfg["pose"] else None, train=True,
+                          use_prev=use_prev)
+    ref = torch.from_numpy(gold["warp_s2"])
+    got = torch.stack(out["warp_src_img_list"])[..., ::2, ::2]
+    assert (got - ref).abs().max() <= 2e-3 * ref.abs().max()
+    assert abs(float(out["loss_warp"]) - float(gold["loss_warp"])) <= 1e-3 * abs(float(gold["loss_warp"]))
+    assert abs(float(out["loss_align"]) - float(gold["loss_align"])) <= 1e-4
+
+
 @pytest.mark.skipif(not ref_harness.available(), reason="reference checkout only exists in the build container")
 def test_oracle_is_bit_exact_with_live_reference():
     cfg = dict(kind="qs", bs=1, label_nc=2, n_blocks=1, n_source=2, pose=False, bias_std=0.03)

@@ -121,12 +121,15 @@ class ForwardEngine:
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
     def forward(self, src_imgs, img_divs, src_lbls, src_bboxes, tar_lbl, tar_bbox, return_flow=False,
-                pose_fill=None, collect=None):
+                pose_fill=None, collect=None, train=None):
         """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (labels may instead be
         uint8 class-index maps [B,256,256]: vl2ch is then evaluated inside the stem loader; images NOT yet /255:
         img_divs[i] is the divisor set_*_input would have applied: 255, or 1 for use_prev sources); src_bboxes / tar_bbox: [B,256,256] uint8|fp32.
         Returns (rec_tar_img NCHW fp32, list of warp grids [B,h,w,2] or None).
-        `collect`: optional dict receiving intermediates (tests)."""
+        `collect`: optional dict receiving intermediates (tests).
+        `train`: optional dict {"tar_img": raw NCHW target image, "align": bool}: the is_train=True branches of the
+        reference forward (image-space warp, warp / alignment losses) are evaluated and returned in it as
+        "warp" [n,B,3,H,W] and "losses" (device float[2])."""
         L.require_device()
         m = self.mode
         n = len(src_imgs)
@@ -160,9 +163,10 @@ class ForwardEngine:
         src_fea_v = src_fea.view(n, B, hw, Cf)
         dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
         dec_lo = torch.empty_like(dec_hi)
+        want_align = train is not None and train.get("align", True)
         pg_mean, grids = ops.corr_warp(plan, tar_ops, src_ops, [src_fea_v[i] for i in range(n)], m,
-                                       want_grids=return_flow, want_mean=collect is not None, taps=(dec_hi, dec_lo),
-                                       c_off=0)
+                                       want_grids=return_flow or train is not None,
+                                       want_mean=collect is not None or want_align, taps=(dec_hi, dec_lo), c_off=0)
 
         # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400).
         # conv1(reflpad(cat[s_i, t])) = W[:, :512] * reflpad(s_i) + W[:, 512:] * reflpad(t): pad and conv are linear, so
@@ -183,7 +187,8 @@ class ForwardEngine:
         sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
 
         # ---- decoder (model/TSNet.py:128-174): map_conv on cat[pg_mean, mean_i sg_i]
-        sg_mean = torch.empty((B, h, w, Cf), dtype=torch.float32, device=dev) if collect is not None else None
+        sg_mean = (torch.empty((B, h, w, Cf), dtype=torch.float32, device=dev)
+                   if (collect is not None or want_align) else None)
         ops.build_taps(sg, m, L.TAPS_SAME, taps=(dec_hi, dec_lo), c_off=Cf, avg_n=n, act_out=sg_mean)
         pcm = self._pack("dec", "map_conv")
         x, _ = self._conv((dec_hi, dec_lo, (1, h, w)), pcm, "1x1", B, h, w, norm=False)
@@ -211,6 +216,15 @@ class ForwardEngine:
         fore, fill = (None, None) if pose_fill is None else ((64, 192), pose_fill)
         rec = ops.head_conv_tanh(act, sd[hw_key + ".weight"], sd[hw_key + ".bias"], fore=fore, fill=fill)
 
+        if train is not None:
+            # train-only branches of the reference forward (model/TSNet.py:327-331, 372-390, 402-405)
+            src_raw = train.get("src_img_raw", src_imgs)
+            src_div = train.get("src_img_div", img_divs)
+            fore, fill = (None, None) if pose_fill is None else ((64, 192), pose_fill)
+            warp, losses = ops.train_extras(src_raw, src_div, train["tar_img"], 255.0, grids,
+                                            pg_mean if want_align else None,
+                                            sg_mean.view(B, hw, Cf) if want_align else None, fore=fore, fill=fill)
+            train.update(warp=warp, losses=losses)
         if collect is not None:
             collect.update(src_fea=src_fea_v, tar_fea=tar_fea, pg_mean=pg_mean.view(B, h, w, Cf), sg_mean=sg_mean)
         grid_list = [grids[i] for i in range(n)] if return_flow else None

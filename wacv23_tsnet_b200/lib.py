@@ -65,6 +65,11 @@ _SIGNATURES = {
                                     vp, C.c_size_t, vp]),
     "tsnet_warp_mean_taps": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                        C.c_int, C.c_int, C.c_int, C.c_float, vp]),
+    "tsnet_train_extras_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tsnet_train_extras_fwd": (C.c_int, [C.POINTER(vp), C.POINTER(C.c_float), C.c_int, vp, C.c_float, vp, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_float), vp, vp, vp, C.c_size_t, vp]),
+    "tsnet_plane_stats": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                        C.POINTER(C.c_float), vp, vp]),
     "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_float), vp, vp]),

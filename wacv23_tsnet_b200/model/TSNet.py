@@ -79,8 +79,9 @@ class FuseNet(_EngineOnly):
 
 
 _TRAIN_MSG = ("training (discriminators, VGG loss, backward, optimizers: reference model/TSNet.py:229-255, 409-524) is "
-              "outside the B200 forward hot path; build with is_train=False and use set_test_input / "
-              "set_train_input + forward()")
+              "outside the B200 forward hot path: is_train=True builds the generator only and forward() evaluates the "
+              "train-mode forward branches (warp_src_img_list, loss_warp, loss_align); nothing that needs a backward "
+              "pass exists here")
 
 
 class TSNet(nn.Module):
@@ -92,8 +93,9 @@ class TSNet(nn.Module):
                  addcoords=True,
                  ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False):
         super().__init__()
-        if is_train:
-            raise NotImplementedError(_TRAIN_MSG)
+        # is_train=True: forward-only.  The generator is built exactly as for is_train=False (no discriminators, VGG,
+        # optimizers -- SURVEY section 8f row 3); forward() then also runs the reference's train-mode branches
+        # (model/TSNet.py:327-331, 372-390, 402-405) on the device.
         if not addcoords:
             raise NotImplementedError("the sm_100a stem kernel generates the CoordConv channels; addcoords=False is "
                                       "never used by the reference's callers")
@@ -118,6 +120,9 @@ class TSNet(nn.Module):
         self._use_graph = bool(cuda_graph)
         self._graphs = {}
         self._src_img_raw, self._src_img_div = None, None
+        self._tar_img_raw = None
+        self.loss_warp = 0.0
+        self.loss_align = 0.0
         self.src_lbl_list = None
         self.src_bbox_list = None
         self.warp_src_img_list = None
@@ -164,7 +169,8 @@ class TSNet(nn.Module):
                              for i in range(len(self._src_img_raw))]
         self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
         self.src_bbox_list = [self._mask(x).unsqueeze(dim=1) for x in src_bbox_list]
-        self.tar_img = self._f32(tar_img) / 255.0
+        self._tar_img_raw = self._f32(tar_img).contiguous()
+        self.tar_img = self._tar_img_raw / 255.0
         self.tar_lbl = self._lbl(tar_lbl)
         self.tar_bbox = self._mask(tar_bbox).unsqueeze(dim=1)
 
@@ -245,7 +251,17 @@ class TSNet(nn.Module):
 
     def forward(self, _collect=None):
         imgs, divs, lbls, bbs, tar_lbl, tar_bbox = self._staged()
-        if self._use_graph and _collect is None:
+        if self.is_train:
+            if self._tar_img_raw is None:
+                raise RuntimeError("is_train=True forward needs set_train_input (the target image)")
+            train = {"tar_img": self._tar_img_raw, "align": self._pose_fill is None}
+            rec, grids = self._engine.forward(imgs, divs, lbls, bbs, tar_lbl, tar_bbox, return_flow=True,
+                                              pose_fill=self._pose_fill, collect=_collect, train=train)
+            self.warp_src_img_list = [train["warp"][i] for i in range(len(imgs))]
+            self.loss_warp = train["losses"][0]
+            if self._pose_fill is None:
+                self.loss_align = train["losses"][1]
+        elif self._use_graph and _collect is None:
             with torch.no_grad():
                 rec, grids = self._forward_graph(imgs, divs, lbls, bbs, tar_lbl, tar_bbox)
         else:

@@ -384,6 +384,35 @@ def warp_mean_taps(src_fea_list, grids, B, h, w, Cch, mode, taps=None, c_off=0, 
     return out
 
 
+def train_extras(src_imgs, src_divs, tar_img_raw, tar_div, grids, pg_mean, sg_mean, fore=None, fill=None):
+    """Train-mode branches of forward() (model/TSNet.py:327-331, 372-390, 402-405; TSNet_pose.py:395-396).
+    src_imgs: n raw NCHW [B,3,H,W]; grids [n,B,h,w,2]; pg_mean / sg_mean fp32 [B,hw,C] or None (pose).
+    Returns (warp [n,B,3,H,W], losses float[2] = (loss_warp, loss_align))."""
+    n = len(src_imgs)
+    B, _, H, W = src_imgs[0].shape
+    h, w = grids.shape[2], grids.shape[3]
+    dev = grids.device
+    warp = torch.empty((n, B, 3, H, W), dtype=torch.float32, device=dev)
+    losses = torch.empty(2, dtype=torch.float32, device=dev)
+    lib = L.load()
+    nbytes = lib.tsnet_train_extras_workspace_bytes(B, n, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    img_ptrs = (C.c_void_p * n)(*[_f32(x).data_ptr() for x in src_imgs])
+    divs = (C.c_float * n)(*[float(d) for d in src_divs])
+    fx0, fx1 = fore if fore is not None else (0, 0)
+    fill3 = (C.c_float * 3)(*fill) if fill is not None else None
+    Cch = pg_mean.shape[-1] if pg_mean is not None else 0
+    with _Prof(("train_extras",)):
+        L.check(lib.tsnet_train_extras_fwd(img_ptrs, divs, n, _ptr(_f32(tar_img_raw)), C.c_float(tar_div),
+                                           _ptr(_f32(grids)), B, H, W, h, w,
+                                           _ptr(None if pg_mean is None else _f32(pg_mean)),
+                                           _ptr(None if sg_mean is None else _f32(sg_mean)), Cch, fx0, fx1, fill3,
+                                           _ptr(warp), _ptr(losses), _ptr(ws), nbytes, _stream()))
+    for _ in range(6):
+        _count()
+    return warp, losses
+
+
 def head_conv_tanh(act, weight, bias, fore=None, fill=None):
     """act fp32 NHWC [B,H,W,Cin] -> NCHW [B,3,H,W] = tanh(conv7x7(reflectpad3(act))) (+ pose compositing)."""
     B, H, W, Cin = act.shape
