@@ -138,7 +138,10 @@ __device__ __forceinline__ void fetch_act8(const TapsArgs& a, int b, int y, int 
 // grid.x = destination rows (b, plane, yd); the 256 threads of a block sweep (xd, channel group) of that row, so the
 // per-thread index math is 32-bit and, whenever 256 % (C/8) == 0, every thread keeps ONE channel group for the whole
 // row and loads its InstanceNorm statistics once.
-__global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
+// MODE is a template parameter so that the simple modes are not compiled with the register budget of the 4-tap
+// bilinear one (80 registers, 37 % occupancy for every mode when it was a run-time switch).
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == TSNET_TAPS_UP2REFLECT1 ? 3 : (MODE == TSNET_TAPS_SAME ? 4 : 5)) build_taps_kernel(const TapsArgs a) {
   const int cg = a.C / 8;
   int rowid = blockIdx.x;
   const int yd = rowid % a.Hd;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
     }
     float v[8];
     bool interior = false;  // destination pixel that owns the (unique) act_out write of its source pixel
-    if (a.mode == TSNET_TAPS_SAME) {
+    if constexpr (MODE == TSNET_TAPS_SAME) {
       fetch_act8(a, b, yd, xd, c, mean, rstd, v);
       if (a.avg_n > 1) {  // mean over sources: samples b, B + b, 2B + b, ...
         for (int i = 1; i < a.avg_n; ++i) {
@@ -188,11 +191,11 @@ __global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
         for (int j = 0; j < 8; ++j) v[j] = __fdiv_rn(v[j], nf);
       }
       interior = true;
-    } else if (a.mode == TSNET_TAPS_REFLECT1) {
+    } else if constexpr (MODE == TSNET_TAPS_REFLECT1) {
       const int y = reflect_idx(yd - 1, a.H), x = reflect_idx(xd - 1, a.W);
       fetch_act8(a, b, y, x, c, mean, rstd, v);
       interior = (yd >= 1 && yd <= a.H && xd >= 1 && xd <= a.W);
-    } else if (a.mode == TSNET_TAPS_S2ZERO) {
+    } else if constexpr (MODE == TSNET_TAPS_S2ZERO) {
       const int y = 2 * yd + (plane >> 1) - 1, x = 2 * xd + (plane & 1) - 1;
       if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
         fetch_act8(a, b, y, x, c, mean, rstd, v);
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256, 3) build_taps_kernel(const TapsArgs a) {
       }
     }
     if (a.act_out && interior) {
-      const int y = a.mode == TSNET_TAPS_SAME ? yd : yd - 1, x = a.mode == TSNET_TAPS_SAME ? xd : xd - 1;
+      const int y = MODE == TSNET_TAPS_SAME ? yd : yd - 1, x = MODE == TSNET_TAPS_SAME ? xd : xd - 1;
       float* o = a.act_out + ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.act_C_total + a.act_c_off + c;
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -601,7 +604,13 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
     default: return set_error(-1, "build_taps: unknown mode %d", d->mode);
   }
   const unsigned rows = static_cast<unsigned>(a.B) * a.planes * a.Hd;
-  build_taps_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->mode) {
+    case TSNET_TAPS_SAME: build_taps_kernel<TSNET_TAPS_SAME><<<rows, 256, 0, st>>>(a); break;
+    case TSNET_TAPS_REFLECT1: build_taps_kernel<TSNET_TAPS_REFLECT1><<<rows, 256, 0, st>>>(a); break;
+    case TSNET_TAPS_S2ZERO: build_taps_kernel<TSNET_TAPS_S2ZERO><<<rows, 256, 0, st>>>(a); break;
+    default: build_taps_kernel<TSNET_TAPS_UP2REFLECT1><<<rows, 256, 0, st>>>(a); break;
+  }
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
