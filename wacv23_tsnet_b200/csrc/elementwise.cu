@@ -248,9 +248,9 @@ __global__ void __launch_bounds__(256, MODE == TSNET_TAPS_UP2REFLECT1 ? 3 : (MOD
 // ------------------------------------------------------------------------------------------------
 // stem tap source: [B, H+6, W, Cp], kw folded into channels.
 // block = one destination row (b, yd) x 64 pixels.  Phase 1 stages the Cin input channels of the 70 source pixels
-// (64 + 6 halo, reflect-indexed) in shared memory with coalesced plane reads (CoordConv channels are generated, the
-// /255 is applied).  Phase 2: thread = destination pixel x 8 folded channels, consecutive threads write consecutive
-// 16-byte pieces (fully coalesced hi / lo stores); (column tap, channel) of a folded channel comes from a table.
+// (64 + 6 halo, reflect-indexed) in shared memory, pixel-major, with coalesced plane reads (CoordConv channels are
+// generated, the /255 is applied).  Phase 2: thread = destination pixel x 8 folded channels = 8 consecutive floats of
+// the staging buffer; consecutive threads write consecutive 16-byte pieces (fully coalesced hi / lo stores).
 // lbl_kind: 0 = fp32 one-hot planes [B, Clbl, H, W]; 1 = uint8 class-index map [B, H, W] (utils/misc.py:50-67 vl2ch).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemTW = 64;
@@ -259,14 +259,11 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
                                                         const void* __restrict__ lbl, int Clbl, int lbl_kind, int B,
                                                         int H, int W, int Cp, int fmt, float scale,
                                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  extern __shared__ float s_src[];  // [Cin][kStemTW + 6]
-  __shared__ int8_t s_tap[1024], s_chan[1024];
+  // pixel-major staging buffer [kStemTW + 6 source pixels][Cin]: folded channel j = s * Cin + c of destination pixel
+  // px is source pixel px + s, channel c, i.e. element px * Cin + j -- the folded row of a pixel is a contiguous
+  // window of 7 * Cin floats, no (tap, channel) tables needed
+  extern __shared__ float s_src[];
   const int Cin = Cimg + Clbl + 3;
-  for (int j = threadIdx.x; j < Cp; j += blockDim.x) {
-    const int s = j / Cin;
-    s_tap[j] = static_cast<int8_t>(s < 7 ? s : -1);
-    s_chan[j] = static_cast<int8_t>(j - s * Cin);
-  }
   const int Hd = H + 6;
   const int xt = blockIdx.x * kStemTW;
   const int yd = blockIdx.y;
@@ -277,7 +274,7 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
   const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
   constexpr int SW = kStemTW + 6;
   for (int i = threadIdx.x; i < Cin * SW; i += blockDim.x) {
-    const int c = i / SW, k = i - c * SW;
+    const int c = i / SW, k = i - c * SW;  // consecutive threads read consecutive pixels of one input plane
     const int xs = reflect_idx(xt + k - 3, W);
     float v;
     if (c < Cimg) {
@@ -294,20 +291,20 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
       const int kk = c - Cimg - Clbl;
       v = kk == 0 ? xx : (kk == 1 ? yy : __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy))));
     }
-    s_src[i] = v;
+    s_src[k * Cin + c] = v;
   }
   __syncthreads();
   const int cg = Cp / 8;
+  const int jmax = 7 * Cin;
   const size_t row_base = ((static_cast<size_t>(b) * Hd + yd) * W + xt) * Cp;
   for (int i = threadIdx.x; i < kStemTW * cg; i += blockDim.x) {
     const int px = i / cg, g = i - px * cg;
     if (xt + px >= W) break;
+    const float* src = s_src + px * Cin + g * 8;
     uint16_t h[8], l[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const int j = g * 8 + jj;
-      const int s = s_tap[j];
-      const float v = s >= 0 ? s_src[s_chan[j] * SW + px + s] : 0.f;
+      const float v = g * 8 + jj < jmax ? src[jj] : 0.f;
       split16(v * scale, fmt, h[jj], l[jj]);
     }
     uint4 ph, pl;
