@@ -224,9 +224,12 @@ int tsnet_warp_mean_taps(const float* const* src_fea, int n_src, const float* gr
  * out = out * fore + fill_c * (1 - fore), fore = columns [fore_x0, fore_x1) (model/TSNet_pose.py:276-280,
  * :416-417; fill = -mean/255).  Pass fore_x1 <= fore_x0 to disable.  SIMT fp32 (Cout = 3 is not a
  * tensor-core shape). */
-int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
-                         const float* bias, int fore_x0, int fore_x1, const float* fill3, float* out_nchw,
-                         void* stream);
+int tsnet_head_conv_tanh(const float* act_nhwc, const float* mean_rstd, int relu, int B, int H, int W, int Cin,
+                         const float* w_oihw, const float* bias, int fore_x0, int fore_x1, const float* fill3,
+                         float* out_nchw, void* stream);
+/* mean_rstd (optional, [B, Cin, 2] from tsnet_instnorm_reduce) and relu: act_nhwc is then the RAW output of the last
+ * up-conv and InstanceNorm + ReLU (model/TSNet.py:149-150) are applied while the tile is staged -- no separate
+ * normalisation pass over the 256 x 256 x 64 activation. */
 
 /* ---- demo post-processing -------------------------------------------------------
  * demo/demo_face.py:194-199 + sample_img :96-105 (demo_pose.py analogous): per image and channel

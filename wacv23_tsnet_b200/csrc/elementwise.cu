@@ -365,8 +365,10 @@ __global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 constexpr int kHeadTW = 32, kHeadTH = 16, kHeadCC = 8, kHeadPS = 12, kHeadPPT = 4;
 
-__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ act, int B, int H, int W, int Cin,
-                                                        const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ act,
+                                                        const float* __restrict__ mean_rstd, int relu, int B, int H,
+                                                        int W, int Cin, const float* __restrict__ w,
+                                                        const float* __restrict__ bias,
                                                         int fore_x0, int fore_x1, float fill0, float fill1,
                                                         float fill2, float* __restrict__ out) {
   __shared__ __align__(16) float s_in[(kHeadTH + 6) * (kHeadTW + 6) * kHeadPS];
@@ -384,8 +386,14 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
       const int p = i / (kHeadCC / 4);
       const int px = p % (kHeadTW + 6), py = p / (kHeadTW + 6);
       const int ys = reflect_idx(y0 + py - 3, H), xs = reflect_idx(x0 + px - 3, W);
-      const float4 v =
+      float4 v =
           *reinterpret_cast<const float4*>(act + ((static_cast<size_t>(b) * H + ys) * W + xs) * Cin + cc + c4 * 4);
+      if (mean_rstd) {  // InstanceNorm (+ ReLU) of the raw conv output applied while staging (model/TSNet.py:149-150)
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean_rstd + (static_cast<size_t>(b) * Cin + cc + c4 * 4) * 2));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(mean_rstd + (static_cast<size_t>(b) * Cin + cc + c4 * 4) * 2 + 4));
+        v.x = (v.x - m0.x) * m0.y; v.y = (v.y - m0.z) * m0.w; v.z = (v.z - m1.x) * m1.y; v.w = (v.w - m1.z) * m1.w;
+      }
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       *reinterpret_cast<float4*>(&s_in[p * kHeadPS + c4 * 4]) = v;
     }
     for (int i = threadIdx.x; i < 49 * kHeadCC; i += blockDim.x) {
@@ -641,17 +649,18 @@ extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fm
   return 0;
 }
 
-extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, int B, int H, int W, int Cin, const float* w_oihw,
-                                    const float* bias, int fore_x0, int fore_x1, const float* fill3, float* out_nchw,
-                                    void* stream) {
+extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, const float* mean_rstd, int relu, int B, int H, int W,
+                                    int Cin, const float* w_oihw, const float* bias, int fore_x0, int fore_x1,
+                                    const float* fill3, float* out_nchw, void* stream) {
   TSNET_ARG_CHECK(act_nhwc && w_oihw && bias && out_nchw, "head_conv: null argument");
   TSNET_ARG_CHECK(Cin % kHeadCC == 0, "head_conv: Cin %d must be a multiple of %d", Cin, kHeadCC);
   TSNET_ARG_CHECK(H >= 4 && W >= 4, "head_conv: image too small for reflect pad 3");
   TSNET_ARG_CHECK(fore_x1 <= fore_x0 || fill3, "head_conv: compositing needs fill3 (host pointer to 3 floats)");
   dim3 grid((W + kHeadTW - 1) / kHeadTW, (H + kHeadTH - 1) / kHeadTH, B);
   const float f0 = fill3 ? fill3[0] : 0.f, f1 = fill3 ? fill3[1] : 0.f, f2 = fill3 ? fill3[2] : 0.f;
-  head_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, B, H, W, Cin, w_oihw, bias, fore_x0,
-                                                                          fore_x1, f0, f1, f2, out_nchw);
+  head_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, mean_rstd, relu, B, H, W, Cin,
+                                                                          w_oihw, bias, fore_x0, fore_x1, f0, f1, f2,
+                                                                          out_nchw);
   TSNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

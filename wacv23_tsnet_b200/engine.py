@@ -209,12 +209,12 @@ class ForwardEngine:
             y, mr = self._conv(t, pc, "3x3", B, Hc, Wc)
             if i < 2:
                 t = ops.build_taps(y, m, L.TAPS_UP2REFLECT1, mean_rstd=mr, relu=True)
-        act = torch.empty_like(y)
-        ops.build_taps(y, m, L.TAPS_SAME, mean_rstd=mr, relu=True, act_out=act, want_taps=False)
+        # last IN + ReLU (model/TSNet.py:149-150) is applied inside the head kernel's tile loader
         sd = self.nets["dec"].state_dict(keep_vars=True)
         hw_key = f"model{nb + 3}.1"
         fore, fill = (None, None) if pose_fill is None else ((64, 192), pose_fill)
-        rec = ops.head_conv_tanh(act, sd[hw_key + ".weight"], sd[hw_key + ".bias"], fore=fore, fill=fill)
+        rec = ops.head_conv_tanh(y, sd[hw_key + ".weight"], sd[hw_key + ".bias"], fore=fore, fill=fill, mean_rstd=mr,
+                                 relu=True)
 
         if train is not None:
             # train-only branches of the reference forward (model/TSNet.py:327-331, 372-390, 402-405)

@@ -70,7 +70,7 @@ _SIGNATURES = {
                                          C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_float), vp, vp, vp, C.c_size_t, vp]),
     "tsnet_plane_stats": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, vp, vp]),
-    "tsnet_head_conv_tanh": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
+    "tsnet_head_conv_tanh": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                        C.POINTER(C.c_float), vp, vp]),
     "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_float), vp, vp]),
     "tsnet_direct_conv_fp32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,

@@ -413,14 +413,16 @@ def train_extras(src_imgs, src_divs, tar_img_raw, tar_div, grids, pg_mean, sg_me
     return warp, losses
 
 
-def head_conv_tanh(act, weight, bias, fore=None, fill=None):
-    """act fp32 NHWC [B,H,W,Cin] -> NCHW [B,3,H,W] = tanh(conv7x7(reflectpad3(act))) (+ pose compositing)."""
+def head_conv_tanh(act, weight, bias, fore=None, fill=None, mean_rstd=None, relu=False):
+    """act fp32 NHWC [B,H,W,Cin] -> NCHW [B,3,H,W] = tanh(conv7x7(reflectpad3(act))) (+ pose compositing).
+    mean_rstd [B,Cin,2] / relu: `act` is a raw conv output, InstanceNorm (+ ReLU) is applied inside the loader."""
     B, H, W, Cin = act.shape
     out = torch.empty((B, 3, H, W), dtype=torch.float32, device=act.device)
     x0, x1 = fore if fore is not None else (0, 0)
     fill_arr = (C.c_float * 3)(*(fill if fill is not None else (0.0, 0.0, 0.0)))
     with _Prof(("head_conv_tanh",)):
-        L.check(L.load().tsnet_head_conv_tanh(_ptr(_f32(act)), B, H, W, Cin, _ptr(_f32(weight.detach())),
+        L.check(L.load().tsnet_head_conv_tanh(_ptr(_f32(act)), _ptr(None if mean_rstd is None else _f32(mean_rstd)),
+                                              int(relu), B, H, W, Cin, _ptr(_f32(weight.detach())),
                                               _ptr(_f32(bias.detach())), x0, x1, fill_arr, _ptr(out), _stream()))
     _count()
     return out
