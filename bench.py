@@ -261,7 +261,7 @@ def run_b200(args):
     def timed(fn, steps, profile=False):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ops.LAUNCHES
+        l0 = ops.kernel_launches()
         if profile:
             ops.PROFILE = {}
         ev0.record()
@@ -271,7 +271,7 @@ def run_b200(args):
         barrier()
         prof, ops.PROFILE = ops.PROFILE, None
         ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev)
-        return ms, ops.LAUNCHES - l0, prof
+        return ms, ops.kernel_launches() - l0, prof
 
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):

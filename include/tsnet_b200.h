@@ -52,6 +52,8 @@ int tsnet_abi_version(void);
 const char* tsnet_last_error(void);
 /* 1 if the current device is compute capability 10.x, else 0 */
 int tsnet_device_ok(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
+long long tsnet_launch_count(void);
 
 /* ---- weights --------------------------------------------------------------------------------
  * nn.Conv2d weight [Cout, Cin, KH, KW] fp32 (state_dict layout) -> packed K-major hi/lo.

@@ -727,7 +727,7 @@ static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   const int grid = a.num_m_tiles < num_sms() ? a.num_m_tiles : num_sms();
   conv_gemm_vr_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -743,7 +743,7 @@ static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_gemm_kernel<BLOCK_N, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -781,6 +781,7 @@ static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
   }
   const int clusters = items < max_clusters ? items : max_clusters;
   cfg.gridDim = dim3(clusters * 8);
+  ++launch_counter();
   TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, true>, a));
   return 0;
 }

@@ -694,9 +694,9 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
   a.sort = d->sort;
   if (const char* e = getenv("TSNET_K1_SORT")) a.sort = atoi(e);  // experiments only
   corr_sort_kernel<<<dim3(d->B, d->n_src + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   corr_plan_kernel<<<d->B, 384, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -753,7 +753,7 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
   const int max_items = d->B * a.ncand;
   const int grid = max_items < num_sms() ? max_items : num_sms();
   corr_tile_kernel<<<grid, kCorrThreads, kCorrSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -764,7 +764,7 @@ static int launch_warp_taps(WarpTapsArgs& a, bool from_states, void* stream) {
     warp_mean_taps_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else
     warp_mean_taps_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 

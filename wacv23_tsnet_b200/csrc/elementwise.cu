@@ -544,7 +544,15 @@ static inline int grid_for(size_t total, int block, int max_blocks = 148 * 16) {
 
 using namespace tsnet;
 
+namespace tsnet {
+long long& launch_counter() {
+  static long long n = 0;  // host-side bookkeeping of one process; launches are enqueued from one thread at a time
+  return n;
+}
+}  // namespace tsnet
+
 extern "C" int tsnet_abi_version(void) { return TSNET_ABI_VERSION; }
+extern "C" long long tsnet_launch_count(void) { return tsnet::launch_counter(); }
 extern "C" const char* tsnet_last_error(void) { return last_error_buf(); }
 extern "C" int tsnet_device_ok(void) {
   int dev = 0, major = 0;
@@ -562,7 +570,7 @@ extern "C" int tsnet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, in
   const size_t total = static_cast<size_t>(Cout_pad) * (fold_kw ? KH : KH * KW) * Cp;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w_oihw, Cout, Cin, KH, KW, fold_kw, Cp, Cout_pad, scale, fmt, w_hi, w_lo);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -573,7 +581,7 @@ extern "C" int tsnet_instnorm_reduce(const float* stats_partial, int B, int HW, 
   dim3 grid((C + 31) / 32, B), block(32, kInSegs);
   instnorm_reduce_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(stats_partial, HW / 32, C, eps,
                                                                                 mean_rstd);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -616,7 +624,7 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
     case TSNET_TAPS_S2ZERO: build_taps_kernel<TSNET_TAPS_S2ZERO><<<rows, 256, 0, st>>>(a); break;
     default: build_taps_kernel<TSNET_TAPS_UP2REFLECT1><<<rows, 256, 0, st>>>(a); break;
   }
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -634,7 +642,7 @@ extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, c
   stem_taps_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl, Clbl, lbl_kind, B, H, W, Cp, fmt,
       scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -645,7 +653,7 @@ extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fm
   const size_t npix = static_cast<size_t>(B) * HW;
   l2norm_split_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       fea, npix, HW, C, fmt, scale == 0.f ? 1.f : scale, rank, out_hi, out_lo);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -661,7 +669,7 @@ extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, const float* mean_rst
   head_conv_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(act_nhwc, mean_rstd, relu, B, H, W, Cin,
                                                                           w_oihw, bias, fore_x0, fore_x1, f0, f1, f2,
                                                                           out_nchw);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -673,7 +681,7 @@ extern "C" int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, 
   dim3 grid(3, B);
   postprocess_u8_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
       rec_nchw, H * W, ref_mean3, ref_std3, img_mean3_host[0], img_mean3_host[1], img_mean3_host[2], out_hwc_rgb);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -685,6 +693,6 @@ extern "C" int tsnet_direct_conv_fp32(const float* x_nhwc, int B, int H, int W, 
   const size_t total = static_cast<size_t>(B) * Ho * Wo * Cout;
   direct_conv_kernel<<<grid_for(total, 256, 148 * 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nhwc, B, H, W, Cin, w_oihw, bias, Cout, K, stride, pad, reflect, Ho, Wo, y_nhwc);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }

@@ -32,6 +32,15 @@ inline int set_error(int code, const char* fmt, ...) {
       return ::tsnet::set_error(static_cast<int>(_e), "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// every kernel launch of the library goes through this check: it also counts the launch (tsnet_launch_count(),
+// reported by bench.py as gpu_launches)
+long long& launch_counter();
+#define TSNET_LAUNCH_CHECK()            \
+  do {                                  \
+    ++::tsnet::launch_counter();        \
+    TSNET_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -217,7 +217,7 @@ extern "C" int tsnet_plane_stats(const float* x, int planes, int n, float div, f
   TSNET_ARG_CHECK(x && mean_std && planes > 0 && n > 1, "plane_stats: bad argument");
   plane_stats_kernel<<<planes, kPlaneThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, div == 0.f ? 1.f : div,
                                                                                      mean_std);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }
 
@@ -262,23 +262,23 @@ extern "C" int tsnet_train_extras_fwd(const float* const* src_img, const float* 
   }
   a.grids = grids; a.out = warp_out; a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.n_src = n_src;
   image_warp_kernel<<<dim3(h, B, n_src), 256, 0, s>>>(a);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   plane_stats_kernel<<<planes, kPlaneThreads, 0, s>>>(warp_out, H * W, 1.f, gen_stats);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   plane_stats_kernel<<<B * 3, kPlaneThreads, 0, s>>>(tar_img, H * W, tar_div == 0.f ? 1.f : tar_div, ref_stats);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   const float f0 = fill3 ? fill3[0] : 0.f, f1 = fill3 ? fill3[1] : 0.f, f2 = fill3 ? fill3[2] : 0.f;
   warp_renorm_l1_kernel<<<planes, kPlaneThreads, 0, s>>>(warp_out, gen_stats, ref_stats, tar_img,
                                                          tar_div == 0.f ? 1.f : tar_div, B, H, W, fore_x0, fore_x1, f0,
                                                          f1, f2, l1);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   if (pg_mean) {
     cosine_partial_kernel<<<cos_blocks, 256, 0, s>>>(pg_mean, sg_mean, B * h * w, C, cosp);
-    TSNET_CUDA_CHECK(cudaGetLastError());
+    TSNET_LAUNCH_CHECK();
   }
   finalize_losses_kernel<<<1, kPlaneThreads, 0, s>>>(l1, n_src, B * 3, static_cast<double>(B) * 3 * H * W, cosp,
                                                      cos_blocks, pg_mean ? static_cast<double>(B) * h * w : 0.0,
                                                      losses2);
-  TSNET_CUDA_CHECK(cudaGetLastError());
+  TSNET_LAUNCH_CHECK();
   return 0;
 }

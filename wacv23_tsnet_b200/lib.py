@@ -47,6 +47,7 @@ _SIGNATURES = {
     "tsnet_abi_version": (C.c_int, []),
     "tsnet_last_error": (C.c_char_p, []),
     "tsnet_device_ok": (C.c_int, []),
+    "tsnet_launch_count": (C.c_longlong, []),
     "tsnet_pack_conv_weight": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_int, vp, vp, vp]),
     "tsnet_conv_gemm_fwd": (C.c_int, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),

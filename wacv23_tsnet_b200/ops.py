@@ -1,7 +1,8 @@
 """Thin tensor-level wrappers over the C ABI (include/tsnet_b200.h).
 
-torch is used only for device memory and the current stream; every function enqueues exactly one
-kernel of libtsnet_sm100.so.  `LAUNCHES` counts them (bench.py reports it as gpu_launches).
+torch is used only for device memory and the current stream; every function enqueues the kernels of one C-ABI call
+of libtsnet_sm100.so.  `LAUNCHES` counts the calls; `kernel_launches()` is the library's own count of CUDA kernel
+launches (bench.py reports it as gpu_launches).
 """
 import ctypes as C
 import math
@@ -41,6 +42,10 @@ def _ptr(t):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def kernel_launches():
+    return int(L.load().tsnet_launch_count())
 
 
 def _count():
