@@ -268,15 +268,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint64_t a_lo = make_desc_kmajor_sw128(st + Cfg::kABytes);
             const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes);
             const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+            if (elect_one()) {  // one election per K block: the 12 MMAs are issued back to back by the leader
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint32_t off = k * kUmmaK * 2;
-              umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
-              if (args.split) {
-                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint32_t off = k * kUmmaK * 2;
+                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                if (args.split) {
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                  umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                }
               }
             }
+            __syncwarp();
             umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
@@ -621,15 +624,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
               const uint64_t a_lo = make_desc_kmajor_sw128(a_base + a_bytes + a_off);
               const uint64_t b_hi = make_desc_kmajor_sw128(b_base + t * kVrBTap);
               const uint64_t b_lo = make_desc_kmajor_sw128(b_base + (taps + t) * kVrBTap);
+              if (elect_one()) {  // one election per K block: the 12 MMAs are issued back to back by the leader
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint32_t off = k * kUmmaK * 2;
-                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((t - t0) | k) != 0);
-                if (args.split) {
-                  umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  const uint32_t off = k * kUmmaK * 2;
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((t - t0) | k) != 0);
+                  if (args.split) {
+                    umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
                 }
               }
+              __syncwarp();
             }
             umma_commit_elect(&tmem_full[tb]);
           }

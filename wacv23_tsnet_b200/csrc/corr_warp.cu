@@ -387,15 +387,18 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
               const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
               const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
               const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kCorrABytes + kCorrBBytes);
+              if (elect_one()) {  // one election per K block: the 12 MMAs are issued back to back by the leader
 #pragma unroll
-              for (int k = 0; k < kCorrK / 16; ++k) {
-                const uint32_t off = k * 32;
-                umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
-                if (args.split) {
-                  umma_f16_elect(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16_elect(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                for (int k = 0; k < kCorrK / 16; ++k) {
+                  const uint32_t off = k * 32;
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                  if (args.split) {
+                    umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
                 }
               }
+              __syncwarp();
               umma_commit_elect(&tl.empty_bar[stage]);
               if (++stage == kCorrStages) { stage = 0; phase ^= 1; }
             }

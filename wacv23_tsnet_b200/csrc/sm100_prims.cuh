@@ -132,10 +132,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// The MMA issuer warp runs CONVERGED and one elected lane issues (CUTLASS's pattern).  Issuing from inside an
-// `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop with per-lane predicate
-// shuffling: ~12 SASS instructions = ~60 issue cycles per MMA, more than the 32 (N = 64) or 64 (N = 128) tensor
-// cycles the instruction takes -- measured 28 % tensor-pipe utilisation on the N = 64 stem kernel.
+// The MMA issuer warp runs CONVERGED and one elected lane issues a whole K block (12 MMAs) per election:
+//   if (elect_one()) { umma_f16 x 12 }  __syncwarp();
+// with the descriptors computed in converged code, ptxas emits the UTCHMMAs back to back from uniform registers.
+// Issuing from inside an `if (lane == 0)` role branch made it wrap EVERY UTCHMMA in an ELECT / BRA.U.ANY loop, and
+// electing per MMA still left ~9 dependent uniform-datapath instructions per MMA: ~94 issue cycles per MMA measured,
+// i.e. issue-bound for every tile narrower than N = 256 (32 / 64 tensor cycles per MMA at N = 64 / 128).
 __device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate) {
   if (elect_one()) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
