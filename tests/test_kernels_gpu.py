@@ -92,6 +92,29 @@ def test_conv_gemm_network_shapes(B, H, W, Cin, Cout, kind, bn):
     assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
 
 
+def test_conv_gemm_tail_wave_split_is_bit_exact():
+    """512 -> 512 3x3 over 24 samples = 384 tiles of N = 256 on 148 SMs (2.6 waves): the launcher recomputes the last
+    partial wave with N = 128 tiles; per-element accumulation order does not depend on the tile width."""
+    import os
+    from wacv23_tsnet_b200 import ops
+    from wacv23_tsnet_b200 import lib as L
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(11)
+    x = torch.randn(24, 32, 32, 512, device="cuda")
+    w = torch.randn(512, 512, 3, 3, device="cuda") * 0.02
+    b = torch.randn(512, device="cuda") * 0.1
+    pc = ops.PackedConv(w, b, m)
+    hi, lo, g = ops.build_taps(x, m, L.TAPS_REFLECT1)
+    y1, s1 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
+    os.environ["TSNET_NO_TAIL_SPLIT"] = "1"
+    try:
+        y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
+    finally:
+        del os.environ["TSNET_NO_TAIL_SPLIT"]
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(s1, s2)
+
+
 def test_conv_gemm_is_deterministic_and_batch_invariant():
     """Same sample -> same bits, whatever the batch it rides in (required for shard == single-GPU equality)."""
     from wacv23_tsnet_b200 import lib as L, ops

@@ -923,7 +923,7 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   // computed by a second launch with BLOCK_N / 2 (twice as many half-cost tiles): 10.5 waves instead of 11.
   const int sms = num_sms();
   const int tiles = a.num_m_tiles * a.num_n_tiles;
-  static const bool tail_split = getenv("TSNET_NO_TAIL_SPLIT") == nullptr;
+  const bool tail_split = getenv("TSNET_NO_TAIL_SPLIT") == nullptr;  // (tests compare the two launch plans)
   if (tail_split && d->block_n >= 128 && tiles > sms && tiles % sms != 0 && d->Cout_pad % (d->block_n / 2) == 0) {
     const int full_waves = tiles / sms;
     const int main_m = full_waves * sms / a.num_n_tiles;
