@@ -143,9 +143,21 @@ def test_build_taps_modes(mode):
     xn = x.permute(0, 3, 1, 2)
     hi, lo, _ = ops.build_taps(x, m, L.TAPS_REFLECT1)
     assert _relerr(_recon(hi, lo, m.fmt), F.pad(xn, (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1) * m.act_scale) < tol
-    hi, lo, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)
+    hi, lo, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)          # quad kernel: 3x3 neighbourhood -> 2x2 outputs
     up = F.pad(F.interpolate(xn, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
     assert _relerr(_recon(hi, lo, m.fmt), up.permute(0, 2, 3, 1) * m.act_scale) < tol
+    import os
+    mr0 = torch.stack([x.mean((1, 2)), 1.0 / torch.sqrt(x.var((1, 2), unbiased=False) + 1e-5)], -1).contiguous()
+    hq, lq, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, mean_rstd=mr0, relu=True)
+    os.environ["TSNET_UP2_GENERIC"] = "1"                            # one destination pixel per thread
+    try:
+        hg, lg, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, mean_rstd=mr0, relu=True)
+        hg0, lg0, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)
+    finally:
+        del os.environ["TSNET_UP2_GENERIC"]
+    torch.cuda.synchronize()
+    assert torch.equal(hq, hg) and torch.equal(lq, lg)             # same expression per output value
+    assert _relerr(_recon(hg0, lg0, m.fmt), _recon(hi, lo, m.fmt)) == 0.0
     hi, lo, _ = ops.build_taps(x, m, L.TAPS_S2ZERO)
     xp = F.pad(xn, (1, 1, 1, 1)).permute(0, 2, 3, 1)
     got = _recon(hi, lo, m.fmt).view(2, 4, 9, 9, 64)

@@ -5,6 +5,7 @@
 #include "sm100_prims.cuh"
 #include "host_util.h"
 #include "../../include/tsnet_b200.h"
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -241,6 +242,105 @@ __global__ void __launch_bounds__(256, MODE == TSNET_TAPS_UP2REFLECT1 ? 3 : (MOD
       pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
       *reinterpret_cast<uint4*>(a.hi + d) = ph;
       *reinterpret_cast<uint4*>(a.lo + d) = pl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// UP2REFLECT1 specialisation: thread = one SOURCE pixel x 4 channels -> the 2 x 2 block of up-sampled pixels around it
+// (and their reflect-pad duplicates on the border).  The generic kernel fetches + normalises 4 source values per
+// destination pixel (16 per 2 x 2 block); here the 3 x 3 neighbourhood is fetched + normalised once (9 per block).
+// Every destination value is computed with exactly the generic kernel's expression (ATen's source index / weights,
+// same operation order), so the two are bit-identical.  grid.x = (b, source row); threads sweep (source column, c4).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fetch_act4(const TapsArgs& a, int b, int y, int x, int c, const float4& mean,
+                                           const float4& rstd, float (&v)[4]) {
+  const size_t off = ((static_cast<size_t>(b) * a.H + y) * a.W + x) * a.C + c;
+  const float4 t = *reinterpret_cast<const float4*>(a.raw + off);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  if (a.mean_rstd) {
+    v[0] = (v[0] - mean.x) * rstd.x; v[1] = (v[1] - mean.y) * rstd.y;
+    v[2] = (v[2] - mean.z) * rstd.z; v[3] = (v[3] - mean.w) * rstd.w;
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.residual) {
+    const float4 r = *reinterpret_cast<const float4*>(a.residual + off);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) build_taps_up2_kernel(const TapsArgs a) {
+  const int cg = a.C / 4;
+  const int ys = blockIdx.x % a.H;
+  const int b = blockIdx.x / a.H;
+  const int per_row = a.W * cg;
+  const int H2 = 2 * a.H, W2 = 2 * a.W;
+  const int yr[3] = {max(ys - 1, 0), ys, min(ys + 1, a.H - 1)};
+  for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+    const int xs = idx / cg;
+    const int c = (idx - xs * cg) * 4;
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), rstd = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (a.mean_rstd) {
+      const float* mr = a.mean_rstd + (static_cast<size_t>(b) * a.C + c) * 2;
+      const float4 t0 = *reinterpret_cast<const float4*>(mr), t1 = *reinterpret_cast<const float4*>(mr + 4);
+      mean = make_float4(t0.x, t0.z, t1.x, t1.z);
+      rstd = make_float4(t0.y, t0.w, t1.y, t1.w);
+    }
+    const int xr[3] = {max(xs - 1, 0), xs, min(xs + 1, a.W - 1)};
+    float nb[3][3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) fetch_act4(a, b, yr[i], xr[j], c, mean, rstd, nb[i][j]);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int uy = 2 * ys + dy;
+      // ATen area_pixel_compute_source_index(scale = 0.5, align_corners = false): max(0.5*(d+0.5)-0.5, 0)
+      const float sy = fmaxf(0.5f * (uy + 0.5f) - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy), y1 = min(y0 + 1, a.H - 1);
+      const float ly = sy - y0, hy = 1.f - ly;
+      (void)y1;
+      // ATen's (y0, y1) are rows (ys-1, ys) for the even and (ys, ys+1) for the odd up-sampled row, i.e. nb rows
+      // (dy, dy+1); on the border the clamped neighbour differs from ATen's y1 only where its weight ly is exactly 0
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ux = 2 * xs + dx;
+        const float sx = fmaxf(0.5f * (ux + 0.5f) - 0.5f, 0.f);
+        const int x0 = static_cast<int>(sx);
+        const float lx = sx - x0, hx = 1.f - lx;
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v00 = nb[dy][dx][j], v01 = nb[dy][dx + 1][j], v10 = nb[dy + 1][dx][j], v11 = nb[dy + 1][dx + 1][j];
+          const float t0 = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
+          const float t1 = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
+          const float v = __fadd_rn(__fmul_rn(hy, t0), __fmul_rn(ly, t1));
+          split16(v * a.scale, a.fmt, h[j], l[j]);
+        }
+        const uint2 ph = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+        const uint2 pl = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+        // destination rows / columns holding up-sampled pixel (uy, ux): uy + 1, plus the reflect-pad duplicates
+        // (row 0 <- uy = 1, row 2H+1 <- uy = 2H-2; same for columns)
+        int yd[2] = {uy + 1, -1}, xd[2] = {ux + 1, -1};
+        if (uy == 1) yd[1] = 0;
+        if (uy == H2 - 2) yd[1] = H2 + 1;
+        if (ux == 1) xd[1] = 0;
+        if (ux == W2 - 2) xd[1] = W2 + 1;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (yd[p] < 0) continue;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (xd[r] < 0) continue;
+            const size_t d = ((static_cast<size_t>(b) * a.Hd + yd[p]) * a.Wd + xd[r]) * a.Cp_total + a.c_off + c;
+            *reinterpret_cast<uint2*>(a.hi + d) = ph;
+            *reinterpret_cast<uint2*>(a.lo + d) = pl;
+          }
+        }
+      }
     }
   }
 }
@@ -622,7 +722,13 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
     case TSNET_TAPS_SAME: build_taps_kernel<TSNET_TAPS_SAME><<<rows, 256, 0, st>>>(a); break;
     case TSNET_TAPS_REFLECT1: build_taps_kernel<TSNET_TAPS_REFLECT1><<<rows, 256, 0, st>>>(a); break;
     case TSNET_TAPS_S2ZERO: build_taps_kernel<TSNET_TAPS_S2ZERO><<<rows, 256, 0, st>>>(a); break;
-    default: build_taps_kernel<TSNET_TAPS_UP2REFLECT1><<<rows, 256, 0, st>>>(a); break;
+    default:
+      // quad kernel (9 instead of 16 normalised fetches per 2 x 2 block); the generic one stays for odd shapes / tests
+      if (a.hi && !act_out && a.avg_n == 1 && d->C % 4 == 0 && d->H >= 2 && d->W >= 2 && getenv("TSNET_UP2_GENERIC") == nullptr)
+        build_taps_up2_kernel<<<static_cast<unsigned>(a.B) * a.H, 256, 0, st>>>(a);
+      else
+        build_taps_kernel<TSNET_TAPS_UP2REFLECT1><<<rows, 256, 0, st>>>(a);
+      break;
   }
   TSNET_LAUNCH_CHECK();
   return 0;
