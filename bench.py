@@ -203,7 +203,7 @@ def run_reference(args):
                              "sample": f"{args.steps} forwards of bs={bs} (oracle/tsnet_oracle.py, torch CPU fp32, "
                                        "bit-exact restatement of the reference forward)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -396,13 +396,31 @@ def run_b200(args):
                         if args.e2e_mode == "pipelined" else "set_test_input + forward + rec_tar_img.cpu()"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_corr_warp": roof_corr,
                 "kernel_shares": shares, "cpu_baseline": cpu, "torch_cuda_eager_port": eager}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Rank 0's single JSON line goes to the process's ORIGINAL stdout; everything else that prints to fd 1 (e.g. the
+    NCCL version banner under NCCL_DEBUG=VERSION) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # stdout of this process and of the libraries it loads -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

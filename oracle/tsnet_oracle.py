@@ -5,12 +5,14 @@ bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may 
 product path (wacv23_tsnet_b200/) never does and fails loudly without its CUDA library.
 
 It restates, function by function, /root/reference/model/TSNet.py (face) and
-/root/reference/model/TSNet_pose.py (pose) for `is_train=False` in plain fp32 torch-CPU /
-numpy ops.  Each function cites the reference lines it follows.
+/root/reference/model/TSNet_pose.py (pose) in plain fp32 torch-CPU / numpy ops: the whole
+`is_train=False` forward plus the forward-only `is_train=True` branches (`train_extras`).
+Each function cites the reference lines it follows.
 
 Parity pin: the reference publishes no golden vectors.  The pin is the
 reference itself, imported unmodified in the build container by oracle/make_golden.py, which
-(1) checks this restatement bit-for-bit against reference `TSNet.forward()` on CPU and
+(1) checks this restatement bit-for-bit against reference `TSNet.forward()` on CPU (five inference
+    configs + three train-mode configs: `python -m oracle.make_golden [train]`) and
 (2) writes the fixtures in tests/golden/ that travel to the GPU box.
 """
 import math
