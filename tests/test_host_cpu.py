@@ -170,3 +170,27 @@ def test_two_rank_gloo_plumbing(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
+
+
+def test_corr_host_side_validation_and_workspace(built):
+    """Host-side parts of the correlation ABI that need no device: workspace sizing and argument checks."""
+    import ctypes as C
+    lib = built.load()
+    d = built.CorrDesc()
+    d.B, d.n_src, d.C, d.h, d.w = 32, 3, 512, 32, 32
+    d.bbox_h = d.bbox_w = 256
+    d.temperature, d.split, d.fmt, d.operand_scale, d.sort = 100.0, 1, 0, 4096.0 ** 2, 1
+    n32 = lib.tsnet_corr_workspace_bytes(C.byref(d))
+    # rank u16 + mask f32 per map, coordinates per source map, 8 float4 states per (source, row)
+    assert n32 >= 128 * 1024 * 6 + 96 * 1024 * 8 + 3 * 32 * 1024 * 8 * 16
+    d.B = 64
+    assert lib.tsnet_corr_workspace_bytes(C.byref(d)) > n32
+    for field, bad in (("n_src", 13), ("h", 30), ("C", 520), ("bbox_dtype", 2), ("B", 0)):
+        e = built.CorrDesc()
+        for f, _ in built.CorrDesc._fields_:
+            setattr(e, f, getattr(d, f))
+        setattr(e, field, bad)
+        assert lib.tsnet_corr_workspace_bytes(C.byref(e)) == 0
+        assert lib.tsnet_corr_prepare(C.byref(e), None, None, None, None, 0, None) < 0
+        assert len(lib.tsnet_last_error()) > 0
+    assert lib.tsnet_launch_count() >= 0

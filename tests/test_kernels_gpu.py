@@ -352,6 +352,34 @@ def test_corr_strongly_correlated_features():
     assert k_err < max(4.0 * r_err, 1.5e-5), (k_err, r_err)
 
 
+def test_corr_chain_other_geometry():
+    """16 x 16 feature maps with 256 channels (hw = 256: one column chunk, two row tiles; C = 256: four K blocks):
+    the correlation chain is not tied to the 32 x 32 x 512 geometry of the reference network."""
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    g = torch.Generator().manual_seed(21)
+    B, n, Cc, hh = 3, 2, 256, 16
+    tar = torch.relu(torch.randn(B, Cc, hh, hh, generator=g))
+    srcs = [torch.randn(B, Cc, hh, hh, generator=g) * 2 for _ in range(n)]
+    tb = torch.zeros(B, 1, 128, 128, dtype=torch.uint8)
+    tb[:, :, 20:100, 10:90] = 1
+    tb[2] = 1
+    sbs = [torch.randint(0, 2, (B, 1, 128, 128), generator=g).to(torch.uint8) for _ in range(n)]
+    sbs[1][2] = 0                                   # sample 2, source 1: every pair mismatched -> closed form only
+    ref_mean, ref_grids = O.corr_warp(tar, srcs, tb, sbs)
+    tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda().view(B, hh * hh, Cc)
+    src_d = torch.stack([s.permute(0, 2, 3, 1).contiguous() for s in srcs]).cuda().view(n, B, hh * hh, Cc)
+    coord = torch.cat([torch.linspace(-1, 1, hh), torch.linspace(-1, 1, hh)]).cuda()
+    out, grids = ops.corr_chain(tar_d, src_d, tb.squeeze(1).contiguous().cuda(),
+                                [s.squeeze(1).contiguous().cuda() for s in sbs], coord, m, want_grids=True, want_mean=True)
+    torch.cuda.synchronize()
+    gerr = max(float((grids[i].cpu() - ref_grids[i]).abs().max()) for i in range(n))
+    assert gerr < 5e-5, gerr
+    assert _relerr(out.view(B, hh, hh, Cc).permute(0, 3, 1, 2).cpu(), ref_mean) < 1e-3
+    assert float(grids[1, 2].abs().max()) < 1e-5    # all logits 0 -> uniform softmax -> mean coordinate (0, 0)
+
+
 def test_corr_prepare_plan_is_integer_exact():
     """tsnet_corr_prepare: nearest down-sampling, stable class sort (ones, soft, zeros), rank tables and tile classes
     against a numpy restatement (bit-exact integer work)."""

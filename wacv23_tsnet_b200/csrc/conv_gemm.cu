@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
+    {  // whole warp, converged; one elected lane issues (see sm100_prims.cuh)
       const uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N, args.fmt);
       int stage = 0;
       uint32_t phase = 0;
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
+      {  // whole warp, converged; one elected lane issues (see sm100_prims.cuh)
         const uint32_t idesc = make_idesc_f16(kBlockM, kVrN, args.fmt);
         mbar_wait(b_full, 0);
         tc_fence_after();

@@ -37,7 +37,6 @@ constexpr int kCorrN = 256;       // source columns per work item
 constexpr int kCorrNC = 128;      // columns owned by one thread
 constexpr int kCorrK = 64;        // K block (one 128 B swizzle row)
 constexpr int kCorrThreads = 384;
-constexpr int kCorrEpiThreads = 256;
 constexpr int kCorrMaxSrc = 12;
 constexpr int kCorrMaxHW = 1024;
 constexpr int kCorrMaxB = 1024;
@@ -366,7 +365,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      {  // whole warp, converged; one elected lane issues (see umma_f16_elect)
+      {  // whole warp, converged; one elected lane issues (see sm100_prims.cuh)
         const uint32_t idesc = make_idesc_f16(kCorrM, kCorrN, args.fmt);
         int stage = 0;
         uint32_t phase = 0;

@@ -138,10 +138,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // Issuing from inside an `if (lane == 0)` role branch made it wrap EVERY UTCHMMA in an ELECT / BRA.U.ANY loop, and
 // electing per MMA still left ~9 dependent uniform-datapath instructions per MMA: ~94 issue cycles per MMA measured,
 // i.e. issue-bound for every tile narrower than N = 256 (32 / 64 tensor cycles per MMA at N = 64 / 128).
-__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  if (elect_one()) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
-}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
