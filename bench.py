@@ -56,6 +56,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.proc, self.rows = gpu_index, None, []
+        self.t0, self.t1 = None, None   # only samples taken inside [t0, t1] (the timed region) are reported
 
     def start(self):
         try:
@@ -68,16 +69,25 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        lo = self.t0 if self.t0 is not None else 0.0
+        hi = (self.t1 if self.t1 is not None else time.time()) + 0.25   # a 200 ms sample may land just after the end
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
@@ -273,14 +283,22 @@ def run_b200(args):
         ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev)
         return ms, ops.kernel_launches() - l0, prof
 
+    import gc
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step_resident()
+        # the sampler process is forked and nvidia-smi initialises BEFORE the warm-up, so that neither overlaps the
+        # timed region; only the samples taken inside the timed region are reported
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        torch.cuda.synchronize()
         log("warm-up done")
+        gc.collect()
+        gc.disable()   # no collector pauses between launches inside the timed regions
+        sampler.mark_begin()
         ms, launches, prof = timed(step_resident, args.steps, profile=True)
+        sampler.mark_end()
         log(f"timed region done: {ms / args.steps:.2f} ms/step")
         clocks = sampler.stop() if rank == 0 else None
         for _ in range(2):
@@ -306,6 +324,7 @@ def run_b200(args):
             barrier()
             ms_e2e = D.max_over_ranks(ev0.elapsed_time(ev1), dev)
         log(f"e2e region done: {ms_e2e / args.steps:.2f} ms/step")
+    gc.enable()
 
     frames = bs * world * args.steps
     value = frames / (ms * 1e-3)
