@@ -1,7 +1,8 @@
 """Forward engine: sequences the sm_100a kernels for TSNet.forward().
 
-Reference path being replaced: model/TSNet.py:309-407 (face) and model/TSNet_pose.py:325-417 (pose),
-is_train=False.  All activations stay on the device in NHWC; the only torch ops used are allocations.
+Reference path being replaced: model/TSNet.py:309-407 (face) and model/TSNet_pose.py:325-417 (pose): the
+is_train=False forward and, on request (`train=`), the forward-only is_train=True branches.  All activations stay on
+the device in NHWC; the only torch ops used are allocations.
 The n sources are run through img_enc / fuse_net as ONE batch of n*B samples (shared weights), the target
 through lbl_enc / dec as a batch of B.
 """
