@@ -187,10 +187,16 @@ __global__ void __launch_bounds__(1024) corr_sort_kernel(const PrepArgs a) {
 __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
   __shared__ uint8_t skip_sm[kCorrMaxSrc * 32];
   __shared__ int kc[12];
+  __shared__ float2 sums_sm[kCorrMaxSrc * 8];  // (sum x, sum y) of every 128-run of every source map of this sample
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int hw = a.hw, runs = hw / kCorrM, chunks = hw / kCorrN, NS = 2 * chunks;
   const uint32_t lt = (1u << lane) - 1u;
   const int per_src = runs * chunks, ncand = a.n_src * per_src;  // <= 12 * 8 * 4 = 384 candidates
+  if (t < a.n_src * runs) {  // one coalesced read instead of a dependent global load per skipped tile below
+    const int i = t / runs, u = t - i * runs;
+    const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
+    sums_sm[i * 8 + u] = *reinterpret_cast<const float2*>(a.sums + (smap * runs + u) * 2);
+  }
   bool keep = false;
   int code = 0;
   if (t < ncand) {  // candidates (source, row tile, column chunk) in lexicographic order
@@ -220,10 +226,9 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
     const int i = c / per_src, rem = c - i * per_src, mt = rem / chunks, ch = rem - mt * chunks;
     if (t < 2 * kCorrM) {
       const int row = t & (kCorrM - 1), half = t >> 7;
-      const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
-      const float* sm = a.sums + (smap * runs + 2 * ch + half) * 2;
+      const float2 sm = sums_sm[i * 8 + 2 * ch + half];
       const size_t r = (static_cast<size_t>(i) * a.B + b) * hw + mt * kCorrM + row;
-      a.state[r * NS + 2 * ch + half] = make_float4(0.f, static_cast<float>(kCorrNC), sm[0], sm[1]);
+      a.state[r * NS + 2 * ch + half] = make_float4(0.f, static_cast<float>(kCorrNC), sm.x, sm.y);
     }
   }
 }
