@@ -332,6 +332,25 @@ def test_corr_warp_vs_oracle(B, n, kind):
         assert torch.equal(out, out2) and torch.equal(grids, grids2)
 
 
+def test_corr_two_cta_and_one_cta_tile_kernels_agree():
+    """The default tile kernel is the 2-CTA one (tcgen05.mma.cta_group::2: a CTA pair computes 256 target rows, each CTA
+    loads half of the source chunk); TSNET_K1_2CTA=0 selects the 1-CTA kernel.  Same math per element, different work
+    list granularity (tile pairs) -> identical up to the summation order of the state merge."""
+    import os
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    for kind, B, n in (("rect_u8", 2, 3), ("mixed_u8", 3, 2), ("soft", 1, 2)):
+        tar, srcs, tb, sbs = _corr_inputs(B, n, kind, seed=31)
+        out2, grids2 = _run_corr(tar, srcs, tb, sbs, m)
+        os.environ["TSNET_K1_2CTA"] = "0"
+        try:
+            out1, grids1 = _run_corr(tar, srcs, tb, sbs, m)
+        finally:
+            del os.environ["TSNET_K1_2CTA"]
+        assert float((grids2 - grids1).abs().max()) < 5e-6, kind
+        assert _relerr(out2, out1) < 2e-4, kind
+
+
 def test_corr_strongly_correlated_features():
     """Peaked softmax rows (cos ~ 0.95 at the true match, logits near 100) -- the regime of a trained network; the
     random-feature cases above have row maxima near 20."""

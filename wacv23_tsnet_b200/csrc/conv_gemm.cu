@@ -74,47 +74,7 @@ struct GemmCfg {
   static_assert(kSmemBytesFused <= 227 * 1024, "fused conv shared memory budget");
 };
 
-// ---- cluster helpers (fused variant) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  long long t0 = 0;
-  for (uint32_t spins = 0;; ++spins) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    if (spins > 8) __nanosleep(32);
-    if ((spins & 0xFFF) == 0xFFF) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > TSNET_MBAR_TIMEOUT_CYCLES) __trap();
-    }
-  }
-}
+// ---- cluster helpers: sm100_prims.cuh ----
 __device__ __forceinline__ double2 ld_cluster_double2(uint32_t cluster_addr) {
   double2 v;
   asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(cluster_addr) : "memory");

@@ -10,7 +10,10 @@
 //     128-row target tile and a 256-column source chunk that are class-pure with different classes need no tensor
 //     work at all: their softmax contribution is the closed form (max 0, weight count, sum of coordinates) and is
 //     written here.  Everything else goes on the work list.  (sort = 0 keeps the raster order.)
-//  K1 corr_tile_kernel     (persistent, <= 148 CTAs)  work item = (sample, 128 target rows, source, 256 source columns)
+//  K1 corr_tile2_kernel    (persistent, 74 CTA PAIRS, default)  work item = (sample, 256 target rows, source, 256 source
+//     columns): tcgen05.mma.cta_group::2, M = 256 across the pair -- see the comment above the kernel.
+//     corr_tile_kernel     (persistent, <= 148 CTAs, TSNET_K1_2CTA=0)  work item = (sample, 128 target rows, source,
+//     256 source columns).  Common to both:
 //     S = T_hat[128 x C] . S_hat[256 x C]^T on tcgen05 (3-term hi/lo split, fp32 accumulate in TMEM, two 128 x 256
 //     accumulators so the tensor pipe runs on the next item while eight softmax warps read the finished one:
 //     thread = one row x 128 columns), mask weight as one FMA, softmax partial state (max, sum, sum p.x, sum p.y) with
@@ -44,6 +47,8 @@ constexpr int kCorrABytes = kCorrM * kCorrK * 2;                    // 16 KB
 constexpr int kCorrBBytes = kCorrN * kCorrK * 2;                    // 32 KB
 constexpr int kCorrStageBytes = 2 * kCorrABytes + 2 * kCorrBBytes;  // 96 KB
 constexpr int kCorrStages = 2;
+constexpr int kCorr2StageBytes = 4 * kCorrABytes;  // 2-CTA kernel: A hi/lo (128 rows) + B-half hi/lo (128 columns) = 64 KB
+constexpr int kCorr2Stages = 3;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -104,6 +109,7 @@ struct PrepArgs {
   int* counts;
   float4* state;
   int B, n_src, h, w, hw, bbox_h, bbox_w, bbox_dtype, sort;
+  int pair;  // 1: work items cover 256 target rows (two adjacent 128-row tiles) -- the 2-CTA tile kernel
 };
 
 // one block per (map, sample): grid = (B, n_src + 1); blockIdx.y = 0 is the target map
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int hw = a.hw, runs = hw / kCorrM, chunks = hw / kCorrN, NS = 2 * chunks;
   const uint32_t lt = (1u << lane) - 1u;
-  const int per_src = runs * chunks, ncand = a.n_src * per_src;  // <= 12 * 8 * 4 = 384 candidates
+  const int rtiles = a.pair ? runs / 2 : runs;                    // row tiles (pairs of 128-row tiles in pair mode)
+  const int per_src = rtiles * chunks, ncand = a.n_src * per_src;  // <= 12 * 8 * 4 = 384 candidates
   if (t < a.n_src * runs) {  // one coalesced read instead of a dependent global load per skipped tile below
     const int i = t / runs, u = t - i * runs;
     const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
@@ -202,7 +209,8 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
   if (t < ncand) {  // candidates (source, row tile, column chunk) in lexicographic order
     const int i = t / per_src, rem = t - i * per_src, mt = rem / chunks, ch = rem - mt * chunks;
     const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
-    const int rowc = a.cls[static_cast<size_t>(b) * runs + mt];
+    int rowc = a.cls[static_cast<size_t>(b) * runs + (a.pair ? 2 * mt : mt)];
+    if (a.pair && a.cls[static_cast<size_t>(b) * runs + 2 * mt + 1] != rowc) rowc = 2;
     const int c0 = a.cls[smap * runs + 2 * ch], c1 = a.cls[smap * runs + 2 * ch + 1];
     const int colc = c0 == c1 ? c0 : 2;
     const bool skip = (rowc == 1 && colc == 0) || (rowc == 0 && colc == 1);
@@ -221,13 +229,14 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
   if (keep) a.items[static_cast<size_t>(b) * ncand + kbefore + __popc(km & lt)] = code;
   if (t == 0) a.counts[b] = ktot;
   // ---- skipped tiles: all 256 logits are exactly 0 -> per column half: max 0, weight 128, coordinate sums
+  const int rows_per_item = a.pair ? 2 * kCorrM : kCorrM;
   for (int c = 0; c < ncand; ++c) {
     if (!skip_sm[c]) continue;
     const int i = c / per_src, rem = c - i * per_src, mt = rem / chunks, ch = rem - mt * chunks;
-    if (t < 2 * kCorrM) {
-      const int row = t & (kCorrM - 1), half = t >> 7;
+    for (int e = t; e < 2 * rows_per_item; e += blockDim.x) {
+      const int row = e % rows_per_item, half = e / rows_per_item;
       const float2 sm = sums_sm[i * 8 + 2 * ch + half];
-      const size_t r = (static_cast<size_t>(i) * a.B + b) * hw + mt * kCorrM + row;
+      const size_t r = (static_cast<size_t>(i) * a.B + b) * hw + mt * rows_per_item + row;
       a.state[r * NS + 2 * ch + half] = make_float4(0.f, static_cast<float>(kCorrNC), sm.x, sm.y);
     }
   }
@@ -250,7 +259,7 @@ struct alignas(64) CorrArgs {
 };
 
 struct CorrSmemTail {
-  uint64_t full_bar[kCorrStages], empty_bar[kCorrStages], tmem_full[2], tmem_empty[2];
+  uint64_t full_bar[3], empty_bar[3], tmem_full[2], tmem_empty[2];  // (3 = max stages of the two tile kernels)
   uint32_t tmem_base;
   uint32_t pad[15];
   alignas(16) float tab[2][3][kCorrN];  // per item (double-buffered): source mask, x, y of the 256 columns
@@ -508,8 +517,240 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
   }
 }
 
+// 2-CTA variant (cta_group::2): a CTA pair takes 256 target rows x 256 source columns; each CTA loads its own 128
+// rows of T and only HALF of the S chunk, the leader issues M = 256 MMAs that read both halves.  Operand delivery per
+// SM drops from 96 KB to 64 KB per K block (the 1-CTA kernel needs 62 B/clk/SM from L2 to keep the tensor pipe busy).
+__global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __grid_constant__ CorrArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  CorrSmemTail& tl = *reinterpret_cast<CorrSmemTail*>(smem + kCorr2Stages * kCorr2StageBytes);
+  const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the MMAs of the pair and owns the full / tmem_empty barriers
+
+  const int warp = threadIdx.x >> 5;
+  const int num_kb = args.C / kCorrK;
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&args.t_hi);
+    tma_prefetch_desc(&args.s_hi);
+    if (args.split) {
+      tma_prefetch_desc(&args.t_lo);
+      tma_prefetch_desc(&args.s_lo);
+    }
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int s = 0; s < kCorr2Stages; ++s) {
+      mbar_init(&tl.full_bar[s], 1);   // leader's copy is the one in use: its producer arrives, both CTAs' TMA add bytes
+      mbar_init(&tl.empty_bar[s], 1);  // armed in both CTAs by the leader's multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tl.tmem_full[a], 1);    // multicast commit
+      mbar_init(&tl.tmem_empty[a], 16);  // leader's copy: one arrive per softmax warp of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(&tl.tmem_base, 2 * kCorrN);  // two 128 x 256 fp32 accumulators in each CTA
+  if (warp == 3) {
+    int carry = 0;
+    if (lane_id() == 0) tl.pref[0] = 0;
+    for (int base = 0; base < args.B; base += 32) {
+      const int idx = base + lane_id();
+      int v = idx < args.B ? args.counts[idx] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (static_cast<int>(lane_id()) >= o) v += u;
+      }
+      if (idx < args.B) tl.pref[idx + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / 2-CTA MMA
+  tc_fence_after();
+  const uint32_t tmem_base = tl.tmem_base;
+  const int total = tl.pref[args.B];
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane_id() == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        // per stage and CTA: A = own 128 rows (hi, lo), B = own HALF (128 of the 256 columns) of the source chunk
+        const uint32_t stage_tx = 2u * (args.split ? kCorr2StageBytes : kCorr2StageBytes / 2);  // bytes of BOTH CTAs
+        for (int g = pair_id; g < total; g += num_pairs) {
+          int b, mt, i, ch;
+          decode_item(args, tl.pref, g, b, mt, i, ch);
+          const int trow = b * args.hw + (2 * mt + static_cast<int>(rank)) * kCorrM;
+          const int srow = (i * args.B + b) * args.hw + ch * kCorrN + static_cast<int>(rank) * (kCorrN / 2);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait_cluster(&tl.empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * kCorr2StageBytes;
+            if (rank == 0) mbar_arrive_expect_tx(&tl.full_bar[stage], stage_tx);
+            tma_load_2d_2sm(st, &args.t_hi, &tl.full_bar[stage], kb * kCorrK, trow);
+            tma_load_2d_2sm(st + 2 * kCorrABytes, &args.s_hi, &tl.full_bar[stage], kb * kCorrK, srow);
+            if (args.split) {
+              tma_load_2d_2sm(st + kCorrABytes, &args.t_lo, &tl.full_bar[stage], kb * kCorrK, trow);
+              tma_load_2d_2sm(st + 3 * kCorrABytes, &args.s_lo, &tl.full_bar[stage], kb * kCorrK, srow);
+            }
+            if (++stage == kCorr2Stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only: M = 256 across the pair) =====================
+      {  // whole warp, converged; one elected lane issues (see sm100_prims.cuh)
+        const uint32_t idesc = make_idesc_f16(2 * kCorrM, kCorrN, args.fmt);
+        int stage = 0;
+        uint32_t phase = 0;
+        int cc = 0;  // partial-accumulator counter -> TMEM buffer + phase
+        for (int g = pair_id; g < total; g += num_pairs) {
+          for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
+            const int buf = cc & 1;
+            const uint32_t buf_phase = (cc >> 1) & 1;
+            mbar_wait_cluster(&tl.tmem_empty[buf], buf_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * kCorrN;
+            const int kb1 = min(num_kb, kb0 + args.chunk_kb);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait_cluster(&tl.full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t st = smem_u32(smem + stage * kCorr2StageBytes);
+              const uint64_t a_hi = make_desc_kmajor_sw128(st);
+              const uint64_t a_lo = make_desc_kmajor_sw128(st + kCorrABytes);
+              const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kCorrABytes);
+              const uint64_t b_lo = make_desc_kmajor_sw128(st + 3 * kCorrABytes);
+              if (elect_one()) {  // one election per K block: the 12 MMAs are issued back to back by the leader
+#pragma unroll
+                for (int k = 0; k < kCorrK / 16; ++k) {
+                  const uint32_t off = k * 32;
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                  if (args.split) {
+                    umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16_2sm(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
+                }
+              }
+              __syncwarp();
+              if (elect_one()) umma_commit_2sm(&tl.empty_bar[stage]);
+              __syncwarp();
+              if (++stage == kCorr2Stages) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit_2sm(&tl.tmem_full[buf]);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== softmax =====================
+    const int q = warp & 3;            // TMEM lane quarter
+    const int half = (warp - 4) >> 2;  // column half of the 256-column chunk
+    const int row = q * 32 + lane_id();
+    const int et = threadIdx.x - 128;  // 0..255 among the softmax threads
+    int it = 0, par = 0;
+    for (int g = pair_id; g < total; g += num_pairs, par ^= 1) {
+      int b, mt, i, ch;
+      decode_item(args, tl.pref, g, b, mt, i, ch);
+      // ---- column tables of this item (the table of item k is last read before the barrier of item k+1, so
+      //      writing buffer `par` again at item k+2 is safe)
+      {
+        const size_t sb = (static_cast<size_t>(i) * args.B + b) * args.hw + ch * kCorrN + et;
+        tl.tab[par][0][et] = args.maskv[static_cast<size_t>(args.B) * args.hw + sb];
+        tl.tab[par][1][et] = args.cxs[sb];
+        tl.tab[par][2][et] = args.cys[sb];
+      }
+      const int mrow = (2 * mt + static_cast<int>(rank)) * kCorrM + row;  // this CTA's 128 of the item's 256 rows
+      const float m_t = args.maskv[static_cast<size_t>(b) * args.hw + mrow];
+      // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)) = (T.S) * (wa*ms + wb);
+      // exact for binary masks (mismatched pairs get logit 0, not -inf, as in the reference).  k2 folds the temperature,
+      // the operand scale and log2(e): logits are kept in log2 units.
+      const float wa = (2.f * m_t - 1.f) * args.k2, wb = (1.f - m_t) * args.k2;
+      epi_bar_sync();
+
+      // ---- accumulator -> registers (one TMEM read when the whole K is accumulated in TMEM)
+      float acc[kCorrNC];
+      for (int kb0 = 0, p = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++p, ++it) {
+        const int buf = it & 1;
+        const uint32_t buf_phase = (it >> 1) & 1;
+        mbar_wait_cluster(&tl.tmem_full[buf], buf_phase);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrN + half * kCorrNC;
+        if (p == 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < kCorrNC; c0 += 32) tmem_ld32_issue(t0 + c0, acc + c0);
+          tmem_ld32_wait(acc);
+#pragma unroll
+          for (int c0 = 32; c0 < kCorrNC; c0 += 32) reg_fence32(acc + c0);
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < kCorrNC; c0 += 32) {
+            float v[32];
+            tmem_ld32_issue(t0 + c0, v);
+            tmem_ld32_wait(v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += v[j];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) {
+          if (rank == 0) mbar_arrive(&tl.tmem_empty[buf]);
+          else mbar_arrive_remote(map_to_cta(smem_u32(&tl.tmem_empty[buf]), 0));
+        }
+      }
+
+      // ---- logits (log2 units) and their maximum
+      const float* tmask = &tl.tab[par][0][half * kCorrNC];
+      const float* tcx = &tl.tab[par][1][half * kCorrNC];
+      const float* tcy = &tl.tab[par][2][half * kCorrNC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kCorrNC; j += 4) {
+        const float4 mk = *reinterpret_cast<const float4*>(tmask + j);
+        acc[j + 0] *= fmaf(wa, mk.x, wb);
+        acc[j + 1] *= fmaf(wa, mk.y, wb);
+        acc[j + 2] *= fmaf(wa, mk.z, wb);
+        acc[j + 3] *= fmaf(wa, mk.w, wb);
+        mx = fmaxf(mx, fmaxf(fmaxf(acc[j], acc[j + 1]), fmaxf(acc[j + 2], acc[j + 3])));
+      }
+      // ---- softmax partial state with the source coordinates as V
+      float sum = 0.f, gx = 0.f, gy = 0.f;
+#pragma unroll
+      for (int j = 0; j < kCorrNC; j += 4) {
+        const float4 vx = *reinterpret_cast<const float4*>(tcx + j);
+        const float4 vy = *reinterpret_cast<const float4*>(tcy + j);
+        const float xs[4] = {vx.x, vx.y, vx.z, vx.w}, ys[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float p = ex2_approx(acc[j + u] - mx);  // argument <= 0
+          sum += p;
+          gx = fmaf(p, xs[u], gx);
+          gy = fmaf(p, ys[u], gy);
+        }
+      }
+      const size_t r = (static_cast<size_t>(i) * args.B + b) * args.hw + mrow;
+      args.state[r * args.NS + 2 * ch + half] = make_float4(mx, sum, gx, gy);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal its barriers / read its tile
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * kCorrN);
+  }
+}
+
 constexpr int kCorrSmemBytes = kCorrStages * kCorrStageBytes + 1024 + static_cast<int>(sizeof(CorrSmemTail));
 static_assert(kCorrSmemBytes <= 227 * 1024, "corr_tile shared memory budget");
+constexpr int kCorr2SmemBytes = kCorr2Stages * kCorr2StageBytes + 1024 + static_cast<int>(sizeof(CorrSmemTail));
+static_assert(kCorr2SmemBytes <= 227 * 1024, "corr_tile2 shared memory budget");
 
 // ---------------------------------------------------------------------------------------------------------------
 // K2: (partial states -> warp grid) -> bilinear grid_sample of the n source feature maps + mean over sources, written
@@ -642,6 +883,13 @@ __global__ void __launch_bounds__(256) warp_mean_taps_kernel(const WarpTapsArgs 
   }
 }
 
+// 2-CTA tile kernel (cta_group::2) is the default; TSNET_K1_2CTA=0 selects the 1-CTA kernel (tests compare the two).
+// tsnet_corr_prepare and tsnet_corr_tiles of one forward must see the same setting (the work list granularity differs).
+static bool corr_use_2cta() {
+  const char* e = getenv("TSNET_K1_2CTA");
+  return e == nullptr || atoi(e) != 0;
+}
+
 static int corr_desc_check(const tsnet_corr_desc* d) {
   TSNET_ARG_CHECK(d, "corr: null descriptor");
   TSNET_ARG_CHECK(d->n_src >= 1 && d->n_src <= kCorrMaxSrc, "corr: n_src %d (max %d)", d->n_src, kCorrMaxSrc);
@@ -700,6 +948,7 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
   a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
   a.sort = d->sort;
   if (const char* e = getenv("TSNET_K1_SORT")) a.sort = atoi(e);  // experiments only
+  a.pair = corr_use_2cta() ? 1 : 0;
   corr_sort_kernel<<<dim3(d->B, d->n_src + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
   corr_plan_kernel<<<d->B, 384, 0, static_cast<cudaStream_t>(stream)>>>(a);
@@ -728,10 +977,11 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
     if (r) return r;
     if (d->split && (r = encode_tmap_u16_sw128(&a.t_lo, tar_lo, 2, dims, str, box))) return r;
   }
+  const bool two_cta = corr_use_2cta();
   {
     const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->n_src * d->B * hw};
     const uint64_t str[1] = {(uint64_t)d->C * 2};
-    const uint32_t box[2] = {64, kCorrN};
+    const uint32_t box[2] = {64, two_cta ? (uint32_t)(kCorrN / 2) : (uint32_t)kCorrN};  // 2-CTA: each CTA loads half a chunk
     int r = encode_tmap_u16_sw128(&a.s_hi, src_hi, 2, dims, str, box);
     if (r) return r;
     if (d->split && (r = encode_tmap_u16_sw128(&a.s_lo, src_lo, 2, dims, str, box))) return r;
@@ -743,7 +993,7 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
   a.counts = reinterpret_cast<const int*>(ws + L.counts);
   a.state = reinterpret_cast<float4*>(ws + L.state);
   a.B = d->B; a.n_src = d->n_src; a.C = d->C; a.hw = hw;
-  a.ncand = d->n_src * (hw / kCorrM) * (hw / kCorrN);
+  a.ncand = d->n_src * (hw / kCorrM) * (hw / kCorrN) / (two_cta ? 2 : 1);
   a.NS = 2 * (hw / kCorrN);
   a.split = d->split; a.fmt = d->fmt;
   a.chunk_kb = d->C / kCorrK;  // whole K accumulated in TMEM (see the header comment)
@@ -751,13 +1001,38 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
   // operand_scale is a power of two, so folding it into the temperature is exact up to one rounding of the product
   a.k2 = d->temperature / (d->operand_scale == 0.f ? 1.f : d->operand_scale) * kLog2e;
 
+  const int max_items = d->B * a.ncand;
+  if (two_cta) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      TSNET_CUDA_CHECK(cudaFuncSetAttribute(corr_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kCorr2SmemBytes));
+      attr2_set = true;
+    }
+    const int pairs = max_items < num_sms() / 2 ? max_items : num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kCorrThreads);
+    cfg.dynamicSmemBytes = kCorr2SmemBytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ++launch_counter();
+    TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, corr_tile2_kernel, a));
+    return 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     TSNET_CUDA_CHECK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kCorrSmemBytes));
     attr_set = true;
   }
-  const int max_items = d->B * a.ncand;
   const int grid = max_items < num_sms() ? max_items : num_sms();
   corr_tile_kernel<<<grid, kCorrThreads, kCorrSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
