@@ -468,6 +468,253 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2-CTA variant of the BLOCK_N = 256 kernel (tcgen05.mma.cta_group::2; opt-in: TSNET_CONV_2CTA=1).
+// A CTA pair takes two adjacent pixel tiles (M = 256) of one 256-channel slab: each CTA TMA-loads its own A tile and only
+// HALF of the weight tile (128 of the 256 rows); the leader issues the MMAs of both SMs.  Operand delivery per SM drops
+// from 96 KB to 64 KB per K block (three 64 KB stages instead of two 96 KB ones) -- the same change took the
+// correlation tile kernel from 80 % to 92 % tensor-pipe activity.  Chunked accumulation, promotion and the epilogue
+// are those of conv_gemm_kernel<256, false>; per-element accumulation order is unchanged (bit-identical results).
+// ------------------------------------------------------------------------------------------------
+constexpr int kG2N = 256;
+constexpr int kG2ABytes = kBlockM * kBlockK * 2;        // 16 KB: one A tile (hi or lo)
+constexpr int kG2BBytes = (kG2N / 2) * kBlockK * 2;     // 16 KB: this CTA's half of the weight tile (hi or lo)
+constexpr int kG2StageBytes = 2 * kG2ABytes + 2 * kG2BBytes;  // 64 KB
+constexpr int kG2Stages = 3;
+constexpr int kG2SmemBytes = kG2Stages * kG2StageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __grid_constant__ ConvGemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kG2Stages * kG2StageBytes);
+  uint64_t* empty_bar = full_bar + kG2Stages;
+  uint64_t* tmem_full = empty_bar + kG2Stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int num_kb = args.num_taps * args.kc_per_tap;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_items = (args.num_m_tiles >> 1) * args.num_n_tiles;
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&args.a_hi);
+    tma_prefetch_desc(&args.b_hi);
+    if (args.split) {
+      tma_prefetch_desc(&args.a_lo);
+      tma_prefetch_desc(&args.b_lo);
+    }
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int s = 0; s < kG2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's copy is used: its producer arrives, both CTAs' TMA add their bytes
+      mbar_init(&empty_bar[s], 1);  // armed in both CTAs by the leader's multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);               // multicast commit
+      mbar_init(&tmem_empty[a], 2 * kAccWarps);  // leader's copy: the accumulate warps of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_base_smem, 2 * kG2N);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      if (lane_id() == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t stage_tx = 2u * (args.split ? kG2StageBytes : kG2StageBytes / 2);  // bytes of BOTH CTAs
+        for (int item = pair_id; item < num_items; item += num_pairs) {
+          const int mp = item / args.num_n_tiles, n_tile = item - mp * args.num_n_tiles;
+          const int m_tile = args.m_tile_begin + 2 * mp + static_cast<int>(rank);
+          const int img = m_tile / args.tiles_per_img;
+          const int t = m_tile - img * args.tiles_per_img;
+          const int ty = t / args.wtiles_per_row;
+          const int tx = t - ty * args.wtiles_per_row;
+          const int y0 = ty * args.rows_per_tile;
+          const int x0 = tx * args.Wt;
+          const int brow = n_tile * kG2N + static_cast<int>(rank) * (kG2N / 2);
+          for (int tap = 0; tap < args.num_taps; ++tap) {
+            const int cy = y0 + args.tap_dy[tap];
+            const int cx = x0 + args.tap_dx[tap];
+            const int cn = img * args.planes + args.tap_plane[tap];
+            for (int kc = 0; kc < args.kc_per_tap; ++kc) {
+              mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + stage * kG2StageBytes;
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+              const int kb = tap * args.kc_per_tap + kc;
+              tma_load_4d_2sm(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+              tma_load_2d_2sm(st + 2 * kG2ABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, brow);
+              if (args.split) {
+                tma_load_4d_2sm(st + kG2ABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+                tma_load_2d_2sm(st + 2 * kG2ABytes + kG2BBytes, &args.b_lo, &full_bar[stage], kb * kBlockK, brow);
+              }
+              if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (leader CTA: M = 256 across the pair) =====================
+      const uint32_t idesc = make_idesc_f16(2 * kBlockM, kG2N, args.fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int cc = 0;
+      for (int item = pair_id; item < num_items; item += num_pairs) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
+          const int buf = cc & 1;
+          const uint32_t buf_phase = (cc >> 1) & 1;
+          mbar_wait_cluster(&tmem_empty[buf], buf_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kG2N;
+          const int kb1 = min(num_kb, kb0 + args.chunk_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * kG2StageBytes);
+            const uint64_t a_hi = make_desc_kmajor_sw128(st);
+            const uint64_t a_lo = make_desc_kmajor_sw128(st + kG2ABytes);
+            const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kG2ABytes);
+            const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kG2ABytes + kG2BBytes);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint32_t off = k * kUmmaK * 2;
+                umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                if (args.split) {
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                }
+              }
+              umma_commit_2sm(&empty_bar[stage]);  // frees the stage in BOTH CTAs once these MMAs have read it
+            }
+            __syncwarp();
+            if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one()) umma_commit_2sm(&tmem_full[buf]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== accumulate + epilogue (each CTA: its own 128 pixels x 256 channels) =====================
+    constexpr int NC = kG2N / 2;
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane_id();
+    int cc = 0;
+    for (int item = pair_id; item < num_items; item += num_pairs) {
+      const int mp = item / args.num_n_tiles, n_tile = item - mp * args.num_n_tiles;
+      const int m_tile = args.m_tile_begin + 2 * mp + static_cast<int>(rank);
+      float acc[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[j] = 0.f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
+        const int buf = cc & 1;
+        const uint32_t buf_phase = (cc >> 1) & 1;
+        mbar_wait_cluster(&tmem_full[buf], buf_phase);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kG2N + half * NC;
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(t0 + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += v[j];  // fp32 round-to-nearest promotion
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) {
+          if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+          else mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[buf]), 0));
+        }
+      }
+      const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
+      const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
+      float* yrow = args.y + gm * args.Cout;
+      float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        const int n0 = n_tile * kG2N + half * NC + c0;
+        if (n0 < args.Cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = fmaf(acc[c0 + j], args.out_scale, args.bias ? __ldg(args.bias + n0 + j) : 0.f);
+          if (arow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(arow + n0 + j));
+              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (srow) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = v[j];
+            const float colsum = warp_col_sums(t);
+            const float mean_l = colsum * (1.f / 32.f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float mj = __shfl_sync(0xffffffffu, mean_l, j);
+              const float dlt = v[j] - mj;
+              t[j] = dlt * dlt;
+            }
+            const float m2 = warp_col_sums(t);
+            *reinterpret_cast<float2*>(srow + (n0 + lane_id()) * 2) = make_float2(colsum, m2);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers or read its operand tiles
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * kG2N);
+  }
+}
+
+static int launch_conv_gemm2(const ConvGemmArgs& a, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes));
+    attr_set = true;
+  }
+  const int items = (a.num_m_tiles / 2) * a.num_n_tiles;
+  const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kG2SmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ++launch_counter();
+  TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel, a));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Vertical-reuse variant for the kw-folded 7x7 stems (Cout = 64, one 64-channel K block per vertical tap).
 // In the plain kernel every tap re-fetches its own 128-pixel A tile and the weights are re-fetched per tile: 338 KB from
 // L2 for 84 MMAs of N = 64 (2688 tensor cycles) -- L2-bound at a third of the tensor rate (1.97 ms for 96 samples).
@@ -878,6 +1125,22 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
       return launch_conv_gemm_vr(a, s);
     }
   }
+  // ---- BLOCK_N = 256 launches may use the 2-CTA kernel (opt-in while it is being validated: TSNET_CONV_2CTA=1)
+  auto launch_256 = [&](ConvGemmArgs& x) -> int {
+    const char* e2 = getenv("TSNET_CONV_2CTA");
+    if (e2 != nullptr && atoi(e2) != 0 && x.num_m_tiles >= 2 && x.num_m_tiles % 2 == 0 && d->Cout_pad % kG2N == 0) {
+      ConvGemmArgs y = x;
+      const uint64_t K = (uint64_t)d->num_taps * d->Cp;
+      const uint64_t dims[2] = {K, (uint64_t)d->Cout_pad};
+      const uint64_t str[1] = {K * 2};
+      const uint32_t box[2] = {64, (uint32_t)(kG2N / 2)};  // each CTA of the pair loads half of the weight tile
+      int r = encode_tmap_u16_sw128(&y.b_hi, w_hi, 2, dims, str, box);
+      if (r) return r;
+      if (d->split && (r = encode_tmap_u16_sw128(&y.b_lo, w_lo, 2, dims, str, box))) return r;
+      return launch_conv_gemm2(y, s);
+    }
+    return launch_conv_gemm<256>(x, s);
+  };
   // ---- tail-wave split.  The persistent grid runs ceil(tiles / SMs) waves; when the last wave is mostly empty
   // (e.g. 1536 tiles on 148 SMs = 10.4 waves -> 11), the whole waves keep BLOCK_N and the remaining pixel tiles are
   // computed by a second launch with BLOCK_N / 2 (twice as many half-cost tiles): 10.5 waves instead of 11.
@@ -907,7 +1170,7 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
       t.num_m_tiles = tail_m;
       t.num_n_tiles = d->Cout_pad / bn2;
       a.num_m_tiles = main_m;
-      int r = d->block_n == 256 ? launch_conv_gemm<256>(a, s) : launch_conv_gemm<128>(a, s);
+      int r = d->block_n == 256 ? launch_256(a) : launch_conv_gemm<128>(a, s);
       if (r) return r;
       return bn2 == 128 ? launch_conv_gemm<128>(t, s) : launch_conv_gemm<64>(t, s);
     }
@@ -915,6 +1178,6 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   switch (d->block_n) {
     case 64: return launch_conv_gemm<64>(a, s);
     case 128: return launch_conv_gemm<128>(a, s);
-    default: return launch_conv_gemm<256>(a, s);
+    default: return launch_256(a);
   }
 }
