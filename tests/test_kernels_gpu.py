@@ -2,6 +2,8 @@
 op, plus edge cases of the correlation kernel against the oracle.  Convolutions are checked against an fp64 torch
 conv: cuDNN's "fp32" 3x3 algorithms (Winograd class) are themselves ~1e-5 off at C=512, ten times the error of the
 kernel under test."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -90,6 +92,29 @@ def test_conv_gemm_network_shapes(B, H, W, Cin, Cout, kind, bn):
     y, mr, ref = _conv_case(B, H, W, Cin, Cout, kind, "fp16x3", bn)
     assert _relerr(y, ref) < CONV_TOL["fp16x3"]
     assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
+
+
+@pytest.mark.skipif(os.environ.get("TSNET_TEST_CONV_2CTA") != "1",
+                    reason="opt-in 2-CTA conv kernel: set TSNET_TEST_CONV_2CTA=1 (DESIGN.md section 4, K3-2CTA)")
+def test_conv_gemm_two_cta_variant_is_bit_exact():
+    """conv_gemm2_kernel (tcgen05.mma.cta_group::2, TSNET_CONV_2CTA=1) against the default 1-CTA kernel."""
+    from wacv23_tsnet_b200 import ops
+    from wacv23_tsnet_b200 import lib as L
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(12)
+    x = torch.randn(24, 32, 32, 512, device="cuda")
+    w = torch.randn(512, 512, 3, 3, device="cuda") * 0.02
+    b = torch.randn(512, device="cuda") * 0.1
+    pc = ops.PackedConv(w, b, m)
+    hi, lo, g = ops.build_taps(x, m, L.TAPS_REFLECT1)
+    y1, s1 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
+    os.environ["TSNET_CONV_2CTA"] = "1"
+    try:
+        y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
+    finally:
+        del os.environ["TSNET_CONV_2CTA"]
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(s1, s2)
 
 
 def test_conv_gemm_tail_wave_split_is_bit_exact():
