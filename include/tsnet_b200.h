@@ -206,7 +206,9 @@ int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const 
                         const uint16_t* src_hi, const uint16_t* src_lo, const float* const* src_fea, float* out_mean,
                         float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off,
                         float taps_scale, void* workspace, size_t workspace_bytes, void* stream);
-/* the two halves of tsnet_corr_warp_fwd, separately launchable (profiling, grids-only use) */
+/* the two halves of tsnet_corr_warp_fwd, separately launchable (profiling, grids-only use).  tsnet_corr_tiles runs
+ * the 2-CTA tile kernel (tcgen05.mma.cta_group::2, work items of 256 target rows) unless the environment variable
+ * TSNET_K1_2CTA=0 selects the 1-CTA kernel; tsnet_corr_prepare of the same forward must see the same setting. */
 int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo, const uint16_t* src_hi,
                      const uint16_t* src_lo, void* workspace, size_t workspace_bytes, void* stream);
 int tsnet_corr_finish(const tsnet_corr_desc* d, const float* const* src_fea, float* out_mean, float* out_grids,
