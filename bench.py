@@ -236,9 +236,10 @@ def run_b200(args):
         if args.pose:  # BASELINE.json config 3 (Youtube-dance): label_nc=25, foreground compositing
             from oracle.synth import IMG_MEAN
             net = TSNetPose(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, use_mask=True,
-                            mean=IMG_MEAN, math_mode=args.math)
+                            mean=IMG_MEAN, math_mode=args.math, winograd=args.winograd)
         else:
-            net = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, math_mode=args.math)
+            net = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n, math_mode=args.math,
+                        winograd=args.winograd)
     D.broadcast_generator(net, src=0)
     net.eval()
     log("model built")
@@ -341,22 +342,40 @@ def run_b200(args):
         for key, (t, c) in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]:
             shares[str(key)] = {"ms_per_step": t / args.steps, "launches_per_step": c / args.steps,
                                 "share_of_kernel_time": t / total_ms}
-        conv_keys = [k for k in kern if k[0] == "conv_gemm"]
+        conv_keys = [k for k in kern if k[0] in ("conv_gemm", "wino_gemm")]
         dom = max(conv_keys, key=lambda k: kern[k][0])
         t, c = kern[dom]
-        _, kind, X, Hh, Ww, Cin_eff, Cout, taps = dom
-        flops = 2.0 * X * Hh * Ww * Cout * taps * Cin_eff  # algorithmic fp32-conv flops of one launch
+        kname, kind, X, Hh, Ww, Cin_eff, Cout, taps = dom
+        conv_flops = 2.0 * X * Hh * Ww * Cout * taps * Cin_eff  # fp32-conv flops of the layer one launch belongs to
+        # Winograd F(2x2,3x3): the launch executes 16 plane GEMMs over H/2 x W/2 tiles = 16/36 of the conv's MACs;
+        # ALGORITHMIC flops of the kernel = what the batched GEMM computes
+        flops = conv_flops * (16.0 / 36.0) if kname == "wino_gemm" else conv_flops
         ach = flops / (t / c * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
         traffic = load_traffic()
-        conv_traffic = traffic.get("conv_gemm_512x512_3x3_x96") if (kind, X, Hh, Cin_eff, Cout) == ("3x3", 96, 32, 512, 512) else None
-        roof = {"kernel": f"conv_gemm {kind} {Cin_eff}->{Cout} @{Hh}x{Ww} x{X} samples", "bound": "tensor",
+        tkey = {"conv_gemm": "conv_gemm_512x512_3x3_x96", "wino_gemm": "wino_gemm_512x512_x96"}[kname]
+        conv_traffic = traffic.get(tkey) if (kind, X, Hh, Cin_eff, Cout) == ("3x3", 96, 32, 512, 512) else None
+        roof = {"kernel": f"{kname} {kind} {Cin_eff}->{Cout} @{Hh}x{Ww} x{X} samples", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": conv_traffic,
                 "algorithmic_flops_per_launch": flops,
                 "peak_source": peaks["source"] + ", bf16 sustained",
                 "note": "fp32-faithful mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi): "
                         "frac <= 0.333 by construction; tensor-pipe utilisation = 3 x frac" if net._engine.mode.split
                 else "single-pass 16-bit operands"}
+        if kname == "wino_gemm":
+            # the whole Winograd convolution layer = input transform pass + batched GEMM + output transform pass
+            n_l = c / args.steps
+            t_in = sum(v[0] for k, v in kern.items() if k[0] == "build_taps" and k[1] == 4) / args.steps
+            n_in = sum(v[1] for k, v in kern.items() if k[0] == "build_taps" and k[1] == 4) / args.steps
+            t_out = kern.get(("wino_output",), (0.0, 1))[0] / args.steps
+            n_out = kern.get(("wino_output",), (0.0, 1))[1] / args.steps
+            layer_ms = t / c + (t_in / n_in if n_in else 0.0) + (t_out / n_out if n_out else 0.0)
+            roof["winograd_layer"] = {
+                "what": "per 3x3 conv layer of this shape: GEMM launch + mean input-transform pass + mean output-"
+                        "transform pass (the passes are averaged over all Winograd layers of the step)",
+                "ms": layer_ms, "gemm_ms": t / c, "launches_per_step": n_l,
+                "conv_equivalent_tflops": conv_flops / (layer_ms * 1e-3) / 1e12,
+                "conv_equivalent_frac_of_peak": conv_flops / (layer_ms * 1e-3) / 1e12 / peak}
         chain = ("corr_prepare", "l2norm_split", "corr_tiles", "corr_finish")
         if all((k,) in kern for k in chain):
             # the reference's corr+warp (model/TSNet.py:319-366, :392) = ALL four kernels of the chain: mask sort / work
@@ -407,7 +426,7 @@ def run_b200(args):
                 "config": {"workload": f"{'Youtube-dance (pose)' if args.pose else 'FaceForensics'} config: bs={bs}/GPU, 256x256, label_nc={L}, n_source={n}, "
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
-                           "math_mode": args.math,
+                           "math_mode": args.math, "winograd_f2x2_3x3": bool(args.winograd),
                            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
@@ -451,6 +470,8 @@ def main():
     ap.add_argument("--math", default="fp16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"],
                     help="fp16x3 is the parity-grade default; single-pass modes are non-parity speed points")
     ap.add_argument("--pose", action="store_true", help="TSNet_pose, label_nc=25 (BASELINE.json config 3)")
+    ap.add_argument("--no-winograd", dest="winograd", action="store_false",
+                    help="direct implicit GEMM for the ResnetBlock convolutions (A/B against the Winograd default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-cuda-baseline", dest="torch_cuda_baseline", action="store_true",
                     help="also time the reference's torch op sequence eagerly on the GPU (cuDNN), bs = --batch")

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TSNET_ABI_VERSION 2
+#define TSNET_ABI_VERSION 3
 
 /* 16-bit operand format of the tensor-core path */
 #define TSNET_FMT_FP16 0
@@ -45,6 +45,8 @@ extern "C" {
 #define TSNET_TAPS_REFLECT1 1 /* nn.ReflectionPad2d(1) for 3x3 stride-1 convs                       */
 #define TSNET_TAPS_S2ZERO 2   /* zero pad 1 + parity split into 4 planes for 3x3 stride-2 convs      */
 #define TSNET_TAPS_UP2REFLECT1 3 /* nn.Upsample(x2, bilinear, align_corners=False) + ReflectionPad2d(1) */
+#define TSNET_TAPS_WINO 4     /* ReflectionPad2d(1) + Winograd F(2x2,3x3) input transform B^T d B: 16 planes of
+                                 H/2 x W/2 tiles, [B, 16, H/2, W/2, Cp] (operand of tsnet_wino_gemm_fwd)       */
 
 #define TSNET_MAX_TAPS 49
 
@@ -103,11 +105,47 @@ typedef struct {
   int fuse_taps_Cp, fuse_taps_c_off;
   float fuse_act_scale;        /* power-of-two scale of the written operands */
   float fuse_eps;              /* 1e-5 */
+  int flags;                   /* TSNET_CONV_* launch-plan switches (0 = default plan); results never depend on them */
 } tsnet_conv_desc;
+
+/* launch-plan switches (tests compare the alternative plans bit for bit) */
+#define TSNET_CONV_NO_VR 1         /* kw-folded stems: plain implicit-GEMM kernel instead of the vertical-reuse one  */
+#define TSNET_CONV_NO_TAIL_SPLIT 2 /* no second launch with block_n / 2 for the last partial wave                    */
+#define TSNET_CONV_ONE_CTA 4       /* block_n = 256: 1-CTA kernel instead of the default cta_group::2 pair kernel     */
 
 int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,
                         const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
                         float* stats_partial, void* stream);
+
+/* ---- Winograd F(2x2, 3x3) path of the 32 x 32 ResnetBlock convolutions --------------------------------------------
+ * model/TSNet.py:10-49 (ReflectionPad2d(1) + Conv2d(dim, dim, 3) of ResnetBlock: img_enc x 18, FuseNet x 2,
+ * decoder x 2 n_blocks).  Same function as tsnet_conv_gemm_fwd on a REFLECT1 tap source, with 2.25 x fewer MACs:
+ *   U = G g G^T   tsnet_wino_weight_transform (fp64 arithmetic -> fp32 [16, Cout, Cin]) then
+ *                 tsnet_pack_conv_weight(U viewed as a 1x1 weight [16*Cout, Cin, 1, 1]) -> hi/lo [16*Cout, Cp]
+ *   V = B^T d B   tsnet_build_taps(mode = TSNET_TAPS_WINO) on the producer's raw output (InstanceNorm / ReLU /
+ *                 residual / reflect pad applied in the same pass) -> hi/lo [B, 16, H/2, W/2, C]
+ *   M[p] = V[p] . U[p]^T   tsnet_wino_gemm_fwd: the 16 plane GEMMs as one batched tcgen05 launch (cta_group::2 pairs,
+ *                 chunked accumulation with promotion to fp32 registers as in tsnet_conv_gemm_fwd)
+ *                 -> fp32 [16, B * H/2 * W/2, Cout]
+ *   y = A^T M A + bias (+ addend)   tsnet_wino_output -> y_raw [B, H, W, Cout] + stats_partial, exactly the outputs of
+ *                 tsnet_conv_gemm_fwd, so everything downstream is unchanged. */
+typedef struct {
+  int B, TH, TW;    /* samples, tile rows / columns per sample (H/2, W/2); TH*TW % 128 == 0 */
+  int C;            /* input channels = K of every plane GEMM (multiple of 64) */
+  int Cout;         /* output channels (multiple of 256) */
+  int split, fmt;
+  float out_scale;  /* 1 / (weight scale * activation scale) */
+  int chunk_kb;     /* 0 = default (2 K blocks per TMEM chunk in split mode) */
+  int flags;        /* TSNET_CONV_ONE_CTA */
+} tsnet_wino_gemm_desc;
+
+int tsnet_wino_weight_transform(const float* w_oihw, int Cout, int Cin, float* u_out, void* stream);
+int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t* v_hi, const uint16_t* v_lo,
+                        const uint16_t* u_hi, const uint16_t* u_lo, float* m_out, void* stream);
+/* addend (optional): fp32 [addend_rows, C] added per output pixel (row index modulo) before the statistics -- the
+ * source-independent half of FuseNet's first convolution (see tsnet_conv_desc.addend). W/2 must be a multiple of 8. */
+int tsnet_wino_output(const float* m, int B, int H, int W, int C, const float* bias, const float* addend,
+                      long long addend_rows, float* y_raw, float* stats_partial, void* stream);
 
 /* ---- InstanceNorm statistics -----------------------------------------------------------------
  * nn.InstanceNorm2d(affine=False, eps=1e-5, biased variance): model/TSNet.py:28,43,66,71,149.
@@ -134,7 +172,9 @@ typedef struct {
   int act_c_off;    /* first act_out channel */
   int avg_n;        /* > 1 (mode SAME only): v = mean over i < avg_n of f(raw[i*B + b]) -- torch.stack().mean(1)
                        of model/TSNet.py:400; raw / mean_rstd / residual then hold avg_n*B samples */
+  int flags;        /* TSNET_TAPS_GENERIC_UP2: one-destination-pixel-per-thread kernel for mode UP2REFLECT1 (tests) */
 } tsnet_taps_desc;
+#define TSNET_TAPS_GENERIC_UP2 1
 
 int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* mean_rstd, const float* residual,
                      float* act_out, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
@@ -180,6 +220,10 @@ typedef struct {
   int split, fmt;
   float operand_scale;            /* product of the two operand pre-scales (accumulators are divided by it) */
   int sort;                       /* 1: class-sorted order + tile skipping (default); 0: raster order */
+  int one_cta;                    /* 0 (default): 2-CTA tile kernel (cta_group::2, work items of 256 target rows);
+                                     1: 1-CTA kernel (128-row items).  Read by prepare AND tiles from this descriptor,
+                                     so the work-list granularity always matches the kernel that consumes it. */
+  int chunk_kb;                   /* K blocks accumulated in TMEM before promotion to registers; 0 = whole K */
 } tsnet_corr_desc;
 
 size_t tsnet_corr_workspace_bytes(const tsnet_corr_desc* d);
@@ -207,8 +251,8 @@ int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const 
                         float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off,
                         float taps_scale, void* workspace, size_t workspace_bytes, void* stream);
 /* the two halves of tsnet_corr_warp_fwd, separately launchable (profiling, grids-only use).  tsnet_corr_tiles runs
- * the 2-CTA tile kernel (tcgen05.mma.cta_group::2, work items of 256 target rows) unless the environment variable
- * TSNET_K1_2CTA=0 selects the 1-CTA kernel; tsnet_corr_prepare of the same forward must see the same setting. */
+ * the 2-CTA tile kernel (tcgen05.mma.cta_group::2, work items of 256 target rows) unless tsnet_corr_desc.one_cta
+ * selects the 1-CTA kernel. */
 int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo, const uint16_t* src_hi,
                      const uint16_t* src_lo, void* workspace, size_t workspace_bytes, void* stream);
 int tsnet_corr_finish(const tsnet_corr_desc* d, const float* const* src_fea, float* out_mean, float* out_grids,

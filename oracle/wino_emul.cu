@@ -1,0 +1,34 @@
+// TEST INFRASTRUCTURE (not part of the product path): host emulation of the Winograd transform passes.
+// The kernel bodies of wacv23_tsnet_b200/csrc/wino_passes.cuh are plain functions of (block, thread); here they are
+// executed by nested loops on the CPU so that `pytest -m "not gpu"` checks their index math, layouts and statistics
+// against torch before any GPU time is spent.  Built by oracle/Makefile into oracle/_build/libwino_emul.so.
+#include "../wacv23_tsnet_b200/csrc/wino_passes.cuh"
+
+using namespace tsnet;
+
+extern "C" void wino_emul_weight(const float* w, int Cout, int Cin, float* u) {
+  const size_t total = static_cast<size_t>(Cout) * Cin;
+  for (size_t i = 0; i < total; ++i) wino_weight_body(w, Cout, Cin, u, i);
+}
+
+extern "C" void wino_emul_input(const float* raw, const float* mean_rstd, const float* residual, float* act_out,
+                                uint16_t* hi, uint16_t* lo, int B, int H, int W, int C, int relu, int Cp_total,
+                                int c_off, int fmt, int act_C_total, int act_c_off, float scale, int nthreads) {
+  WinoInArgs a;
+  a.raw = raw; a.mean_rstd = mean_rstd; a.residual = residual; a.act_out = act_out; a.hi = hi; a.lo = lo;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.relu = relu; a.Cp_total = Cp_total; a.c_off = c_off; a.fmt = fmt;
+  a.act_C_total = act_C_total; a.act_c_off = act_c_off; a.scale = scale;
+  const int blocks = B * (H / 2);
+  for (int blk = 0; blk < blocks; ++blk)
+    for (int t = 0; t < nthreads; ++t) wino_input_body(a, blk, t, nthreads);
+}
+
+extern "C" void wino_emul_output(const float* m, const float* bias, const float* addend, long long addend_rows, float* y,
+                                 float* stats, int B, int H, int W, int C, int nthreads) {
+  WinoOutArgs a;
+  a.m = m; a.bias = bias; a.addend = addend; a.y = y; a.stats = stats; a.B = B; a.H = H; a.W = W; a.C = C;
+  a.addend_rows = addend_rows;
+  const int blocks = B * (H / 2);
+  for (int blk = 0; blk < blocks; ++blk)
+    for (int t = 0; t < nthreads; ++t) wino_output_body(a, blk, t, nthreads);
+}

@@ -94,10 +94,9 @@ def test_conv_gemm_network_shapes(B, H, W, Cin, Cout, kind, bn):
     assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
 
 
-@pytest.mark.skipif(os.environ.get("TSNET_TEST_CONV_2CTA") != "1",
-                    reason="opt-in 2-CTA conv kernel: set TSNET_TEST_CONV_2CTA=1 (DESIGN.md section 4, K3-2CTA)")
 def test_conv_gemm_two_cta_variant_is_bit_exact():
-    """conv_gemm2_kernel (tcgen05.mma.cta_group::2, TSNET_CONV_2CTA=1) against the default 1-CTA kernel."""
+    """conv_gemm2_kernel (tcgen05.mma.cta_group::2, the default for block_n = 256) against the 1-CTA kernel
+    (tsnet_conv_desc.flags = TSNET_CONV_ONE_CTA)."""
     from wacv23_tsnet_b200 import ops
     from wacv23_tsnet_b200 import lib as L
     m = ops.MathMode("fp16x3")
@@ -107,12 +106,8 @@ def test_conv_gemm_two_cta_variant_is_bit_exact():
     b = torch.randn(512, device="cuda") * 0.1
     pc = ops.PackedConv(w, b, m)
     hi, lo, g = ops.build_taps(x, m, L.TAPS_REFLECT1)
-    y1, s1 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
-    os.environ["TSNET_CONV_2CTA"] = "1"
-    try:
-        y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
-    finally:
-        del os.environ["TSNET_CONV_2CTA"]
+    y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
+    y1, s1 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale, flags=L.CONV_ONE_CTA)
     torch.cuda.synchronize()
     assert torch.equal(y1, y2) and torch.equal(s1, s2)
 
@@ -120,7 +115,6 @@ def test_conv_gemm_two_cta_variant_is_bit_exact():
 def test_conv_gemm_tail_wave_split_is_bit_exact():
     """512 -> 512 3x3 over 24 samples = 384 tiles of N = 256 on 148 SMs (2.6 waves): the launcher recomputes the last
     partial wave with N = 128 tiles; per-element accumulation order does not depend on the tile width."""
-    import os
     from wacv23_tsnet_b200 import ops
     from wacv23_tsnet_b200 import lib as L
     m = ops.MathMode("fp16x3")
@@ -131,11 +125,7 @@ def test_conv_gemm_tail_wave_split_is_bit_exact():
     pc = ops.PackedConv(w, b, m)
     hi, lo, g = ops.build_taps(x, m, L.TAPS_REFLECT1)
     y1, s1 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
-    os.environ["TSNET_NO_TAIL_SPLIT"] = "1"
-    try:
-        y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale)
-    finally:
-        del os.environ["TSNET_NO_TAIL_SPLIT"]
+    y2, s2 = ops.conv_gemm(hi, lo, g, pc, "3x3", 24, 32, 32, m, m.act_scale, flags=L.CONV_NO_TAIL_SPLIT)
     torch.cuda.synchronize()
     assert torch.equal(y1, y2) and torch.equal(s1, s2)
 
@@ -171,15 +161,11 @@ def test_build_taps_modes(mode):
     hi, lo, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)          # quad kernel: 3x3 neighbourhood -> 2x2 outputs
     up = F.pad(F.interpolate(xn, scale_factor=2, mode="bilinear", align_corners=False), (1, 1, 1, 1), mode="reflect")
     assert _relerr(_recon(hi, lo, m.fmt), up.permute(0, 2, 3, 1) * m.act_scale) < tol
-    import os
     mr0 = torch.stack([x.mean((1, 2)), 1.0 / torch.sqrt(x.var((1, 2), unbiased=False) + 1e-5)], -1).contiguous()
     hq, lq, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, mean_rstd=mr0, relu=True)
-    os.environ["TSNET_UP2_GENERIC"] = "1"                            # one destination pixel per thread
-    try:
-        hg, lg, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, mean_rstd=mr0, relu=True)
-        hg0, lg0, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)
-    finally:
-        del os.environ["TSNET_UP2_GENERIC"]
+    # one destination pixel per thread (tsnet_taps_desc.flags = TSNET_TAPS_GENERIC_UP2)
+    hg, lg, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, mean_rstd=mr0, relu=True, flags=L.TAPS_GENERIC_UP2)
+    hg0, lg0, _ = ops.build_taps(x, m, L.TAPS_UP2REFLECT1, flags=L.TAPS_GENERIC_UP2)
     torch.cuda.synchronize()
     assert torch.equal(hq, hg) and torch.equal(lq, lg)             # same expression per output value
     assert _relerr(_recon(hg0, lg0, m.fmt), _recon(hi, lo, m.fmt)) == 0.0
@@ -231,12 +217,8 @@ def test_stem_taps_and_stem_conv(label_nc):
     y, st = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)   # vertical-reuse stem kernel
     ref = F.conv2d(fp.double(), w.double(), b.double()).permute(0, 2, 3, 1).float()
     assert _relerr(y, ref) < CONV_TOL["fp16x3"]
-    import os
-    os.environ["TSNET_NO_VR"] = "1"                                             # plain implicit-GEMM kernel
-    try:
-        y2, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale)
-    finally:
-        del os.environ["TSNET_NO_VR"]
+    from wacv23_tsnet_b200 import lib as L
+    y2, _ = ops.conv_gemm(hi, lo, g, pc, "7x1", 2, 128, 128, m, m.act_scale, flags=L.CONV_NO_VR)  # plain implicit GEMM
     assert torch.equal(y, y2)   # same accumulation order per element -> bit-identical
     # InstanceNorm statistics from its partials (different 32-pixel grouping than the plain kernel: 2 rows x 16 px)
     mr = ops.instnorm_reduce(st, 2, 128 * 128, 64)
@@ -313,7 +295,7 @@ def _corr_inputs(B, n, kind, seed):
     return tar, srcs, tb, sbs
 
 
-def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True):
+def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True, one_cta=False):
     from wacv23_tsnet_b200 import ops
     B, n = tar.shape[0], len(srcs)
     tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda().view(B, 1024, 512)
@@ -321,7 +303,7 @@ def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True):
     coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
     out, grids = ops.corr_chain(tar_d, src_d, tb.squeeze(1).contiguous().cuda(),
                                 [s.squeeze(1).contiguous().cuda() for s in sbs], coord, m, want_grids=True,
-                                want_mean=want_mean, sort=sort)
+                                want_mean=want_mean, sort=sort, one_cta=one_cta)
     torch.cuda.synchronize()
     return out, grids
 
@@ -359,19 +341,14 @@ def test_corr_warp_vs_oracle(B, n, kind):
 
 def test_corr_two_cta_and_one_cta_tile_kernels_agree():
     """The default tile kernel is the 2-CTA one (tcgen05.mma.cta_group::2: a CTA pair computes 256 target rows, each CTA
-    loads half of the source chunk); TSNET_K1_2CTA=0 selects the 1-CTA kernel.  Same math per element, different work
-    list granularity (tile pairs) -> identical up to the summation order of the state merge."""
-    import os
+    loads half of the source chunk); tsnet_corr_desc.one_cta selects the 1-CTA kernel.  Same math per element, different
+    work list granularity (tile pairs) -> identical up to the summation order of the state merge."""
     from wacv23_tsnet_b200 import ops
     m = ops.MathMode("fp16x3")
     for kind, B, n in (("rect_u8", 2, 3), ("mixed_u8", 3, 2), ("soft", 1, 2)):
         tar, srcs, tb, sbs = _corr_inputs(B, n, kind, seed=31)
         out2, grids2 = _run_corr(tar, srcs, tb, sbs, m)
-        os.environ["TSNET_K1_2CTA"] = "0"
-        try:
-            out1, grids1 = _run_corr(tar, srcs, tb, sbs, m)
-        finally:
-            del os.environ["TSNET_K1_2CTA"]
+        out1, grids1 = _run_corr(tar, srcs, tb, sbs, m, one_cta=True)
         assert float((grids2 - grids1).abs().max()) < 5e-6, kind
         assert _relerr(out2, out1) < 2e-4, kind
 
@@ -593,3 +570,109 @@ def test_warp_mean_taps_vs_grid_sample(B, n):
     assert _relerr(out.view(B, 32, 32, 512), ref_nhwc) < 2e-6
     assert _relerr(_recon(hi, lo, m.fmt)[..., 512:], ref_nhwc * m.act_scale) < 2e-6
     assert int(hi[..., :512].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Winograd F(2x2, 3x3) path of the ResnetBlock convolutions (model/TSNet.py:10-49)
+# ---------------------------------------------------------------------------------------------------------------------
+# tolerance of the whole Winograd convolution against an fp64 reflect-pad conv, relative to max|ref|: the input /
+# output transforms are fp32 additions (3e-7 class), operands carry 22 bits, accumulation is promoted every 2 K blocks.
+WINO_TOL = 3e-6
+
+
+def _wino_case(B, Cin, Cout, seed=0, flags=0, with_addend=False):
+    from wacv23_tsnet_b200 import lib as L, ops
+    torch.manual_seed(seed)
+    m = ops.MathMode("fp16x3")
+    x = torch.randn(B, 32, 32, Cin, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    b = torch.randn(Cout, device="cuda")
+    ref = F.conv2d(F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect").double(), w.double(), b.double())
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    addend = None
+    if with_addend:
+        addend = torch.randn(1, 32, 32, Cout, device="cuda")
+        ref = ref + addend.double()
+    pw = ops.PackedWino(w, b, m)
+    taps = ops.build_taps(x, m, L.TAPS_WINO)
+    y, stats = ops.wino_conv(taps, pw, B, 32, 32, m, m.act_scale, addend=addend, flags=flags)
+    mr = ops.instnorm_reduce(stats, B, 1024, Cout)
+    torch.cuda.synchronize()
+    return y, mr, ref.float(), (x, w, b, taps, pw)
+
+
+@pytest.mark.parametrize("B,Cin,Cout", [
+    (3, 512, 512),       # the dominant layer: ResnetBlock(512) of img_enc / the decoder
+    (1, 1024, 1024),     # FuseNet ResnetBlock(1024), second conv
+    (2, 512, 1024),      # FuseNet first conv, one half of the channel concatenation
+    (1, 64, 256),        # one K block per plane
+    (37, 128, 256),      # 74 pixel tiles per plane: more items than CTA pairs, persistent loop across planes
+])
+def test_wino_conv_vs_fp64(B, Cin, Cout):
+    y, mr, ref, _ = _wino_case(B, Cin, Cout)
+    assert _relerr(y, ref) < WINO_TOL
+    assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
+    assert _relerr(mr[..., 1], 1.0 / torch.sqrt(ref.var((1, 2), unbiased=False) + 1e-5)) < 5e-5
+
+
+def test_wino_conv_addend_one_cta_and_batch_invariance():
+    """(a) fp32 addend per output pixel (FuseNet's target half) enters before the statistics; (b) the 1-CTA kernel
+    (TSNET_CONV_ONE_CTA) and the default 2-CTA pair kernel are bit-identical; (c) a sample gives the same bits
+    whatever batch it rides in (what makes batch sharding exact)."""
+    from wacv23_tsnet_b200 import lib as L, ops
+    y, mr, ref, (x, w, b, taps, pw) = _wino_case(3, 256, 256, seed=5, with_addend=True)
+    assert _relerr(y, ref) < WINO_TOL
+    assert _relerr(mr[..., 0], ref.mean((1, 2))) < 2e-5
+    m = ops.MathMode("fp16x3")
+    y2, s2 = ops.wino_conv(taps, pw, 3, 32, 32, m, m.act_scale)
+    y1, s1 = ops.wino_conv(taps, pw, 3, 32, 32, m, m.act_scale, flags=L.CONV_ONE_CTA)
+    t1 = ops.build_taps(x[1:2].contiguous(), m, L.TAPS_WINO)
+    ya, sa = ops.wino_conv(t1, pw, 1, 32, 32, m, m.act_scale)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(s1, s2)
+    assert torch.equal(ya, y2[1:2]) and torch.equal(sa, s2[32:64])
+
+
+def test_wino_passes_equal_host_emulation():
+    """The CUDA kernels of the transform passes and the host emulation the CPU suite runs are the same source
+    (csrc/wino_passes.cuh): operands and outputs must agree bit for bit (the statistics up to FMA contraction)."""
+    import ctypes as C
+    import subprocess
+    from wacv23_tsnet_b200 import lib as L, ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, capture_output=True)
+    emul = C.CDLL(os.path.join(root, "oracle", "_build", "libwino_emul.so"))
+    vp = C.c_void_p
+    emul.wino_emul_input.argtypes = [vp, vp, vp, vp, vp, vp] + [C.c_int] * 10 + [C.c_float, C.c_int]
+    emul.wino_emul_output.argtypes = [vp, vp, vp, C.c_longlong, vp, vp] + [C.c_int] * 5
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(6)
+    B, Cc = 2, 64
+    x = torch.randn(B, 32, 32, Cc) * 3
+    res = torch.randn(B, 32, 32, Cc)
+    mr = torch.stack([x.mean((1, 2)), 1.0 / torch.sqrt(x.var((1, 2), unbiased=False) + 1e-5)], -1).contiguous()
+    hi_c = torch.zeros(B, 16, 16, 16, Cc, dtype=torch.int16)
+    lo_c = torch.zeros_like(hi_c)
+    act_c = torch.zeros(B, 32, 32, Cc)
+    emul.wino_emul_input(p(x), p(mr), p(res), p(act_c), p(hi_c), p(lo_c), B, 32, 32, Cc, 1, Cc, 0, 0, Cc, 0,
+                         m.act_scale, 64)
+    act_g = torch.zeros(B, 32, 32, Cc, device="cuda")
+    x_g, mr_g, res_g = x.cuda(), mr.cuda(), res.cuda()
+    hi_g, lo_g, _ = ops.build_taps(x_g, m, L.TAPS_WINO, mean_rstd=mr_g, relu=True, residual=res_g, act_out=act_g)
+    torch.cuda.synchronize()
+    assert torch.equal(hi_g.cpu().view_as(hi_c), hi_c) and torch.equal(lo_g.cpu().view_as(lo_c), lo_c)
+    assert torch.equal(act_g.cpu(), act_c)
+    mm = torch.randn(16, B * 256, Cc)
+    bias = torch.randn(Cc)
+    y_c = torch.zeros(B, 32, 32, Cc)
+    st_c = torch.zeros(B * 32, Cc, 2)
+    emul.wino_emul_output(p(mm), p(bias), None, 0, p(y_c), p(st_c), B, 32, 32, Cc, 64)
+    y_g = torch.empty(B, 32, 32, Cc, device="cuda")
+    st_g = torch.empty(B * 32, Cc, 2, device="cuda")
+    mm_g, bias_g = mm.cuda(), bias.cuda()
+    L.check(L.load().tsnet_wino_output(p(mm_g), B, 32, 32, Cc, p(bias_g), None, 0, p(y_g), p(st_g),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(y_g.cpu(), y_c)
+    assert _relerr(st_g.cpu(), st_c) < 1e-6

@@ -1,0 +1,163 @@
+"""CPU suite, part 3: the Winograd F(2x2, 3x3) transform passes (wacv23_tsnet_b200/csrc/wino_passes.cuh) executed by
+the host emulation (oracle/wino_emul.cu: the SAME kernel bodies, run by loops over (block, thread)) against torch.
+
+Covers the weight transform, the input pass "T" (InstanceNorm + ReLU + residual + reflect pad + B^T d B + hi/lo split,
+act_out), the output pass "I" (A^T M A + bias + addend, InstanceNorm partial statistics) and the whole chain
+T -> 16 plane GEMMs (emulated in fp64 with the layouts tsnet_wino_gemm_fwd assumes) -> I against an fp64
+ReflectionPad2d(1) + Conv2d of the reference's ResnetBlock (model/TSNet.py:19-27)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BT = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float64)
+G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64)
+AT = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float64)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libwino_emul.so"))
+    vp = C.c_void_p
+    lib.wino_emul_weight.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.wino_emul_input.argtypes = [vp, vp, vp, vp, vp, vp] + [C.c_int] * 10 + [C.c_float, C.c_int]
+    lib.wino_emul_output.argtypes = [vp, vp, vp, C.c_longlong, vp, vp] + [C.c_int] * 5
+    return lib
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _recon(hi, lo, fmt=0):
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    return hi.view(dt).double() + lo.view(dt).double()
+
+
+def run_input(emul, x, mean_rstd=None, relu=False, residual=None, want_act=False, scale=16.0, fmt=0, nthreads=64,
+              Cp_total=None, c_off=0, act_extra=0):
+    B, H, W, Cc = x.shape
+    Cp_total = Cp_total or Cc
+    hi = torch.zeros((B, 16, H // 2, W // 2, Cp_total), dtype=torch.int16)
+    lo = torch.zeros_like(hi)
+    act = torch.zeros((B, H, W, Cc + act_extra), dtype=torch.float32) if want_act else None
+    emul.wino_emul_input(_p(x), _p(mean_rstd), _p(residual), _p(act), _p(hi), _p(lo), B, H, W, Cc, int(relu), Cp_total,
+                         c_off, fmt, Cc + act_extra, act_extra, scale, nthreads)
+    return hi, lo, act
+
+
+def run_output(emul, m, B, H, W, Cc, bias=None, addend=None, want_stats=True, nthreads=64):
+    y = torch.zeros((B, H, W, Cc), dtype=torch.float32)
+    stats = torch.zeros((B * H * W // 32, Cc, 2), dtype=torch.float32) if want_stats else None
+    rows = 0 if addend is None else addend.numel() // Cc
+    emul.wino_emul_output(_p(m), _p(bias), _p(addend), rows, _p(y), _p(stats), B, H, W, Cc, nthreads)
+    return y, stats
+
+
+def ref_input_transform(v_nhwc):
+    """B^T d B of every 4x4 tile (stride 2) of the reflect-padded activation -> [B, 16, H/2, W/2, C] (fp64)."""
+    xp = F.pad(v_nhwc.permute(0, 3, 1, 2).double(), (1, 1, 1, 1), mode="reflect")
+    d = xp.unfold(2, 4, 2).unfold(3, 4, 2)                                  # [B, C, TH, TW, 4, 4]
+    V = torch.einsum("ik,bcxykl,jl->bijxyc", BT, d, BT)                     # [B, 4, 4, TH, TW, C]
+    return V.reshape(V.shape[0], 16, *V.shape[3:])
+
+
+def test_weight_transform(emul):
+    torch.manual_seed(0)
+    w = torch.randn(8, 12, 3, 3) * 0.05
+    u = torch.zeros(16, 8, 12)
+    emul.wino_emul_weight(_p(w), 8, 12, _p(u))
+    ref = torch.einsum("ik,ockl,jl->ijoc", G, w.double(), G).reshape(16, 8, 12)
+    assert float((u.double() - ref).abs().max()) < 1e-8
+    assert torch.equal(u, ref.float())   # fp64 arithmetic, one rounding
+
+
+@pytest.mark.parametrize("H,W,Cc,nthreads", [(32, 32, 16, 64), (8, 16, 8, 3), (4, 4, 4, 1), (16, 48, 8, 256)])
+def test_input_pass(emul, H, W, Cc, nthreads):
+    torch.manual_seed(1)
+    B = 2
+    x = torch.randn(B, H, W, Cc) * 3
+    res = torch.randn(B, H, W, Cc)
+    mr = torch.stack([x.mean((1, 2)), 1.0 / torch.sqrt(x.var((1, 2), unbiased=False) + 1e-5)], -1).contiguous()
+    # plain: just pad + transform + split
+    hi, lo, _ = run_input(emul, x, nthreads=nthreads)
+    ref = ref_input_transform(x) * 16.0
+    got = _recon(hi, lo)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-6
+    # InstanceNorm + ReLU + residual + act_out (with a channel offset in a wider act_out and tap source)
+    hi, lo, act = run_input(emul, x, mean_rstd=mr, relu=True, residual=res, want_act=True, nthreads=nthreads,
+                            Cp_total=Cc + 8, c_off=8, act_extra=4)
+    v = torch.relu((x - mr[..., 0].view(B, 1, 1, Cc)) * mr[..., 1].view(B, 1, 1, Cc)) + res
+    assert torch.equal(act[..., 4:], v) and float(act[..., :4].abs().max()) == 0.0
+    ref = ref_input_transform(v) * 16.0
+    got = _recon(hi, lo)
+    assert float((got[..., 8:] - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert int(hi[..., :8].abs().max()) == 0 and int(lo[..., :8].abs().max()) == 0
+
+
+def test_input_pass_bf16_and_saturation(emul):
+    torch.manual_seed(2)
+    x = torch.randn(1, 8, 8, 4)
+    hi, lo, _ = run_input(emul, x, scale=1.0, fmt=1)
+    ref = ref_input_transform(x)
+    assert float((_recon(hi, lo, 1) - ref).abs().max() / ref.abs().max()) < 1e-4
+    x[0, 3, 3, 0] = 3.0e4                                   # 16 * 3e4 overflows fp16: must saturate, not turn into NaN
+    hi, lo, _ = run_input(emul, x)
+    assert torch.isfinite(_recon(hi, lo)).all()
+
+
+@pytest.mark.parametrize("H,W,Cc,nthreads", [(32, 32, 16, 64), (4, 16, 4, 1), (8, 32, 8, 5)])
+def test_output_pass(emul, H, W, Cc, nthreads):
+    torch.manual_seed(3)
+    B = 3
+    T = (H // 2) * (W // 2)
+    m = torch.randn(16, B * T, Cc)
+    bias = torch.randn(Cc)
+    addend = torch.randn(H * W, Cc)                          # one sample's worth of rows: broadcast over the batch
+    y, stats = run_output(emul, m, B, H, W, Cc, bias=bias, addend=addend, nthreads=nthreads)
+    M = m.double().view(4, 4, B, H // 2, W // 2, Cc)
+    Y = torch.einsum("ai,ijbxyc,ej->bxaye c".replace(" ", ""), AT, M, AT)   # [B, TH, 2, TW, 2, C]
+    ref = Y.reshape(B, H, W, Cc) + bias.double() + addend.double().view(1, H, W, Cc)
+    assert float((y.double() - ref).abs().max()) < 2e-5
+    # statistics partials -> mean / biased variance of y exactly as tsnet_instnorm_reduce merges them
+    s = stats.double().view(B, H * W // 32, Cc, 2)
+    mean = s[..., 0].sum(1) / (H * W)
+    q = (s[..., 1] + s[..., 0] ** 2 / 32.0).sum(1)
+    var = q / (H * W) - mean ** 2
+    yd = y.double().view(B, -1, Cc)
+    assert float((mean - yd.mean(1)).abs().max()) < 1e-5
+    assert float((var - yd.var(1, unbiased=False)).abs().max() / yd.var(1, unbiased=False).max()) < 1e-5
+    y2, _ = run_output(emul, m, B, H, W, Cc, want_stats=False, nthreads=nthreads)
+    assert float((y2.double() - Y.reshape(B, H, W, Cc)).abs().max()) < 2e-5
+
+
+def test_whole_chain_equals_reflect_pad_conv(emul):
+    """T -> 16 plane GEMMs over the hi/lo operands (layouts of tsnet_wino_gemm_fwd: A = V[b, p] rows = tiles, B rows
+    p * Cout + o, M = [16, B * tiles, Cout]) -> I  ==  Conv2d(ReflectionPad2d(1)(x)) in fp64."""
+    torch.manual_seed(4)
+    B, H, W, Cin, Cout = 2, 32, 32, 16, 8
+    x = torch.randn(B, H, W, Cin) * 2
+    w = torch.randn(Cout, Cin, 3, 3) * 0.05
+    bias = torch.randn(Cout)
+    u = torch.zeros(16, Cout, Cin)
+    emul.wino_emul_weight(_p(w), Cout, Cin, _p(u))
+    wscale = 2.0 ** np.floor(np.log2(8192.0 / float(u.abs().max())))
+    us = (u * wscale).view(16 * Cout, Cin)
+    u_hi = us.half()
+    u_lo = (us - u_hi.float()).half()
+    hi, lo, _ = run_input(emul, x)
+    V = _recon(hi, lo).view(B, 16, (H // 2) * (W // 2), Cin)              # [B, 16, tiles, C]
+    U = (u_hi.double() + u_lo.double()).view(16, Cout, Cin)
+    # hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative) ~ full product of the reconstructed operands
+    M = torch.einsum("bptc,poc->pbto", V, U).reshape(16, B * (H // 2) * (W // 2), Cout) / (wscale * 16.0)
+    y, _ = run_output(emul, M.float().contiguous(), B, H, W, Cout, bias=bias)
+    ref = F.conv2d(F.pad(x.permute(0, 3, 1, 2).double(), (1, 1, 1, 1), mode="reflect"), w.double(), bias.double())
+    ref = ref.permute(0, 2, 3, 1)
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-6

@@ -46,6 +46,12 @@ struct alignas(64) ConvGemmArgs {
   int num_m_tiles, num_n_tiles, tiles_per_img, wtiles_per_row, rows_per_tile, Wt;
   int m_tile_begin;  // this launch covers pixel tiles [m_tile_begin, m_tile_begin + num_m_tiles) (tail-wave split)
   int Cout, num_taps, kc_per_tap, planes, split, fmt, chunk_kb;
+  // batched GEMM over `batch_planes` independent (A plane, weight matrix, output plane) triples in ONE launch: the 16
+  // Winograd-domain contractions of a 3x3 convolution (tsnet_wino_gemm_fwd).  1 for ordinary convolutions.
+  // plane p reads tap-source plane index img * planes + tap_plane + p, weight rows [p * b_plane_rows, ...) and writes
+  // y + p * y_plane_stride.
+  int batch_planes, b_plane_rows;
+  long long y_plane_stride;
   // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
   const float* f_residual;   // fp32 [B, H, W, Cout] or null
   float* f_act_out;          // fp32, channel window [f_act_c_off, +Cout) of f_act_C_total, or null
@@ -102,22 +108,36 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[32]) {
 // 8 pixel tiles of ONE image for the same channel slab, so that the InstanceNorm statistics of that (image, slab)
 // are complete inside the cluster: item = cluster_id + k * num_clusters, (img, n_tile) = item / % num_n_tiles.
 template <bool FUSED>
-__device__ __forceinline__ bool tile_at(const ConvGemmArgs& args, int k, int& m_tile, int& n_tile) {
+__device__ __forceinline__ bool tile_at(const ConvGemmArgs& args, int k, int& m_tile, int& n_tile, int& plane) {
   if constexpr (FUSED) {
     const int item = static_cast<int>(blockIdx.x >> 3) + k * static_cast<int>(gridDim.x >> 3);
     if (item >= (args.num_m_tiles >> 3) * args.num_n_tiles) return false;
     const int img = item / args.num_n_tiles;
     n_tile = item - img * args.num_n_tiles;
     m_tile = img * 8 + static_cast<int>(cluster_ctarank());
+    plane = 0;
     return true;
   } else {
+    // order: plane, pixel tile, channel slab (fastest) -- the slabs of one A tile run concurrently, so the second read
+    // of the tile is an L2 hit, and the weights of one plane stay L2-resident while the plane is swept
     const int tile = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
-    if (tile >= args.num_m_tiles * args.num_n_tiles) return false;
+    if (tile >= args.batch_planes * args.num_m_tiles * args.num_n_tiles) return false;
     const int mt = tile / args.num_n_tiles;
     n_tile = tile - mt * args.num_n_tiles;
-    m_tile = args.m_tile_begin + mt;
+    plane = mt / args.num_m_tiles;
+    m_tile = args.m_tile_begin + (mt - plane * args.num_m_tiles);
     return true;
   }
+}
+
+// 32 consecutive fp32 of one output row as four 256-bit stores (STG.E.256): one full 32 B sector per lane and request
+// (16-byte pieces from 32 different rows touch 32 half-sectors per instruction)
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + j), "f"(v[j]), "f"(v[j + 1]),
+                 "f"(v[j + 2]), "f"(v[j + 3]), "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
+                 : "memory");
 }
 
 template <int BLOCK_N, bool FUSED>
@@ -175,29 +195,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = args.split ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes);
-      int m_tile, n_tile;
-      for (int k = 0; tile_at<FUSED>(args, k, m_tile, n_tile); ++k) {
+      int m_tile, n_tile, plane;
+      for (int k = 0; tile_at<FUSED>(args, k, m_tile, n_tile, plane); ++k) {
         const int img = m_tile / args.tiles_per_img;
         const int t = m_tile - img * args.tiles_per_img;
         const int ty = t / args.wtiles_per_row;
         const int tx = t - ty * args.wtiles_per_row;
         const int y0 = ty * args.rows_per_tile;
         const int x0 = tx * args.Wt;
+        const int brow = plane * args.b_plane_rows + n_tile * BLOCK_N;
         for (int tap = 0; tap < args.num_taps; ++tap) {
           const int cy = y0 + args.tap_dy[tap];
           const int cx = x0 + args.tap_dx[tap];
-          const int cn = img * args.planes + args.tap_plane[tap];
+          const int cn = img * args.planes + args.tap_plane[tap] + plane;
           for (int kc = 0; kc < args.kc_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
             const int kb = tap * args.kc_per_tap + kc;
             tma_load_4d(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
-            tma_load_2d(st + 2 * Cfg::kABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+            tma_load_2d(st + 2 * Cfg::kABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, brow);
             if (args.split) {
               tma_load_4d(st + Cfg::kABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
-              tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &args.b_lo, &full_bar[stage], kb * kBlockK,
-                          n_tile * BLOCK_N);
+              tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &args.b_lo, &full_bar[stage], kb * kBlockK, brow);
             }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
@@ -211,8 +231,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0;
       uint32_t phase = 0;
       int cc = 0;  // global chunk counter -> TMEM buffer + phase
-      int m_tile, n_tile;
-      for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile); ++kt) {
+      int m_tile, n_tile, plane;
+      for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile, plane); ++kt) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
           const int buf = cc % Cfg::kTmemBufs;
           const uint32_t buf_phase = (cc / Cfg::kTmemBufs) & 1;
@@ -256,8 +276,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int half = (warp - 4) >> 2;   // which half of the BLOCK_N columns
     const int row = q * 32 + lane_id();
     int cc = 0;
-    int m_tile, n_tile;
-    for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile); ++kt) {
+    int m_tile, n_tile, plane;
+    for (int kt = 0; tile_at<FUSED>(args, kt, m_tile, n_tile, plane); ++kt) {
       float acc[NC];
 #pragma unroll
       for (int j = 0; j < NC; ++j) acc[j] = 0.f;
@@ -417,7 +437,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         continue;
       }
       // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
-      float* yrow = args.y + gm * args.Cout;
+      float* yrow = args.y + static_cast<size_t>(plane) * args.y_plane_stride + gm * args.Cout;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -434,9 +454,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
               v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          store_row32(yrow + n0, v);
           if (srow) {
             // per-column (sum, centred M2) over this warp's 32 pixels
             float t[32];
@@ -495,7 +513,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const int num_kb = args.num_taps * args.kc_per_tap;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int num_items = (args.num_m_tiles >> 1) * args.num_n_tiles;
+  const int m_pairs = args.num_m_tiles >> 1;
+  const int num_items = args.batch_planes * m_pairs * args.num_n_tiles;  // order: plane, tile pair, channel slab
 
   if (warp == 0 && lane_id() == 0) {
     tma_prefetch_desc(&args.a_hi);
@@ -532,7 +551,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
         uint32_t phase = 0;
         const uint32_t stage_tx = 2u * (args.split ? kG2StageBytes : kG2StageBytes / 2);  // bytes of BOTH CTAs
         for (int item = pair_id; item < num_items; item += num_pairs) {
-          const int mp = item / args.num_n_tiles, n_tile = item - mp * args.num_n_tiles;
+          const int mpa = item / args.num_n_tiles, n_tile = item - mpa * args.num_n_tiles;
+          const int plane = mpa / m_pairs, mp = mpa - plane * m_pairs;
           const int m_tile = args.m_tile_begin + 2 * mp + static_cast<int>(rank);
           const int img = m_tile / args.tiles_per_img;
           const int t = m_tile - img * args.tiles_per_img;
@@ -540,11 +560,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
           const int tx = t - ty * args.wtiles_per_row;
           const int y0 = ty * args.rows_per_tile;
           const int x0 = tx * args.Wt;
-          const int brow = n_tile * kG2N + static_cast<int>(rank) * (kG2N / 2);
+          const int brow = plane * args.b_plane_rows + n_tile * kG2N + static_cast<int>(rank) * (kG2N / 2);
           for (int tap = 0; tap < args.num_taps; ++tap) {
             const int cy = y0 + args.tap_dy[tap];
             const int cx = x0 + args.tap_dx[tap];
-            const int cn = img * args.planes + args.tap_plane[tap];
+            const int cn = img * args.planes + args.tap_plane[tap] + plane;
             for (int kc = 0; kc < args.kc_per_tap; ++kc) {
               mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
               uint8_t* st = smem + stage * kG2StageBytes;
@@ -612,7 +632,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
     const int row = q * 32 + lane_id();
     int cc = 0;
     for (int item = pair_id; item < num_items; item += num_pairs) {
-      const int mp = item / args.num_n_tiles, n_tile = item - mp * args.num_n_tiles;
+      const int mpa = item / args.num_n_tiles, n_tile = item - mpa * args.num_n_tiles;
+      const int plane = mpa / m_pairs, mp = mpa - plane * m_pairs;
       const int m_tile = args.m_tile_begin + 2 * mp + static_cast<int>(rank);
       float acc[NC];
 #pragma unroll
@@ -639,7 +660,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
       }
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
       const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
-      float* yrow = args.y + gm * args.Cout;
+      float* yrow = args.y + static_cast<size_t>(plane) * args.y_plane_stride + gm * args.Cout;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -656,9 +677,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
               v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          store_row32(yrow + n0, v);
           if (srow) {
             float t[32];
 #pragma unroll
@@ -689,12 +708,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
 }
 
 static int launch_conv_gemm2(const ConvGemmArgs& a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes));
-    attr_set = true;
-  }
-  const int items = (a.num_m_tiles / 2) * a.num_n_tiles;
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm2_kernel, kG2SmemBytes, smem_attr));
+  const int items = a.batch_planes * (a.num_m_tiles / 2) * a.num_n_tiles;
   const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -900,9 +916,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
             v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
           }
         }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(yrow + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        store_row32(yrow + n0, v);
         if (srow) {
           float tt[32];
 #pragma unroll
@@ -933,11 +947,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
 static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream) {
   const int a_bytes = (kVrRows + a.num_taps - 1) * kVrW * 128;
   const int smem_bytes = 2 * a.num_taps * kVrBTap + 4 * a_bytes + 1024 + 256;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_vr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_vr_kernel, smem_bytes, smem_attr));
   const int grid = a.num_m_tiles < num_sms() ? a.num_m_tiles : num_sms();
   conv_gemm_vr_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(a);
   TSNET_LAUNCH_CHECK();
@@ -947,13 +958,9 @@ static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream) {
 template <int BLOCK_N>
 static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_kernel<BLOCK_N, false>, Cfg::kSmemBytes, smem_attr));
+  const int tiles = a.batch_planes * a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_gemm_kernel<BLOCK_N, false><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a);
   TSNET_LAUNCH_CHECK();
@@ -964,12 +971,8 @@ static int launch_conv_gemm(const ConvGemmArgs& a, cudaStream_t stream) {
 template <int BLOCK_N>
 static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytesFused));
-    attr_set = true;
-  }
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_kernel<BLOCK_N, true>, Cfg::kSmemBytesFused, smem_attr));
   const int items = (a.num_m_tiles / 8) * a.num_n_tiles;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -985,7 +988,8 @@ static int launch_conv_gemm_fused(const ConvGemmArgs& a, cudaStream_t stream) {
   cfg.numAttrs = 1;
   // The persistent loop needs every cluster to be CO-RESIDENT: a cluster lives inside one GPC, and GPCs of 16/18/20 SMs
   // hold two 8-CTA clusters each (16 on a B200, not 148/8 = 18).  Ask the runtime instead of guessing.
-  static int max_clusters = 0;
+  static int max_clusters_dev[kMaxDevices] = {0};
+  int& max_clusters = max_clusters_dev[current_device()];
   if (max_clusters == 0) {
     cfg.gridDim = dim3(num_sms() / 8 * 8);
     int n = 0;
@@ -1063,6 +1067,9 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   a.split = d->split;
   a.fmt = d->fmt;
   a.chunk_kb = d->split ? 2 : 6;  // <= 24 accumulating MMAs per TMEM chunk before promotion to registers
+  a.batch_planes = 1;
+  a.b_plane_rows = 0;
+  a.y_plane_stride = 0;
   for (int t = 0; t < d->num_taps; ++t) {
     a.tap_dy[t] = d->tap_dy[t];
     a.tap_dx[t] = d->tap_dx[t];
@@ -1105,7 +1112,7 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   }
   // ---- vertical-reuse kernel for the kw-folded stems (see conv_gemm_vr_kernel)
   {
-    const bool vr_enabled = getenv("TSNET_NO_VR") == nullptr;  // (tests compare the two kernels)
+    const bool vr_enabled = (d->flags & TSNET_CONV_NO_VR) == 0;  // (tests compare the two kernels)
     bool vr = vr_enabled && !d->fuse_in && d->block_n == 64 && d->Cout_pad == 64 && d->Cp == 64 && d->num_taps > 1 &&
               d->W % kVrW == 0 && d->H % kVrRows == 0;
     for (int t = 0; vr && t < d->num_taps; ++t)
@@ -1119,16 +1126,16 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
       if (r) return r;
       if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, taps_lo, 4, dims, str, box))) return r;
       a.wtiles_per_row = d->W / kVrW;
-      if (const char* e = getenv("TSNET_VR_CHUNK")) a.chunk_kb = atoi(e) > 0 ? atoi(e) : a.chunk_kb;  // experiments only
       a.f_H = d->H;
       a.f_W = d->W;
       return launch_conv_gemm_vr(a, s);
     }
   }
-  // ---- BLOCK_N = 256 launches may use the 2-CTA kernel (opt-in while it is being validated: TSNET_CONV_2CTA=1)
+  // ---- BLOCK_N = 256 launches use the 2-CTA kernel (cta_group::2: half the weight-tile traffic per SM) whenever the
+  // pixel tiles pair up; TSNET_CONV_ONE_CTA forces the 1-CTA kernel (the two are bit-identical; tests compare them)
   auto launch_256 = [&](ConvGemmArgs& x) -> int {
-    const char* e2 = getenv("TSNET_CONV_2CTA");
-    if (e2 != nullptr && atoi(e2) != 0 && x.num_m_tiles >= 2 && x.num_m_tiles % 2 == 0 && d->Cout_pad % kG2N == 0) {
+    if ((d->flags & TSNET_CONV_ONE_CTA) == 0 && x.num_m_tiles >= 2 && x.num_m_tiles % 2 == 0 &&
+        d->Cout_pad % kG2N == 0) {
       ConvGemmArgs y = x;
       const uint64_t K = (uint64_t)d->num_taps * d->Cp;
       const uint64_t dims[2] = {K, (uint64_t)d->Cout_pad};
@@ -1146,7 +1153,7 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
   // computed by a second launch with BLOCK_N / 2 (twice as many half-cost tiles): 10.5 waves instead of 11.
   const int sms = num_sms();
   const int tiles = a.num_m_tiles * a.num_n_tiles;
-  const bool tail_split = getenv("TSNET_NO_TAIL_SPLIT") == nullptr;  // (tests compare the two launch plans)
+  const bool tail_split = (d->flags & TSNET_CONV_NO_TAIL_SPLIT) == 0;  // (tests compare the two launch plans)
   if (tail_split && d->block_n >= 128 && tiles > sms && tiles % sms != 0 && d->Cout_pad % (d->block_n / 2) == 0) {
     const int full_waves = tiles / sms;
     const int main_m = full_waves * sms / a.num_n_tiles;
@@ -1180,4 +1187,64 @@ extern "C" int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* tap
     case 128: return launch_conv_gemm<128>(a, s);
     default: return launch_256(a);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Winograd F(2x2, 3x3): the 16 plane contractions  M[p] = V[p] (tiles x C) . U[p]^T (C x Cout)  as ONE batched launch
+// of the BLOCK_N = 256 kernel (2-CTA pairs whenever the tile count is even).  V comes from tsnet_build_taps(mode
+// TSNET_TAPS_WINO), U from tsnet_wino_weight_transform + tsnet_pack_conv_weight, M goes to tsnet_wino_output.
+// ------------------------------------------------------------------------------------------------
+extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t* v_hi, const uint16_t* v_lo,
+                                   const uint16_t* u_hi, const uint16_t* u_lo, float* m_out, void* stream) {
+  TSNET_ARG_CHECK(d && v_hi && u_hi && m_out, "wino_gemm: null argument");
+  TSNET_ARG_CHECK(!d->split || (v_lo && u_lo), "wino_gemm: split mode needs the lo operands");
+  TSNET_ARG_CHECK(d->B >= 1 && d->TH >= 1 && d->TW >= 1, "wino_gemm: geometry");
+  TSNET_ARG_CHECK(d->C > 0 && d->C % 64 == 0, "wino_gemm: C %d must be a multiple of 64", d->C);
+  TSNET_ARG_CHECK(d->Cout > 0 && d->Cout % kG2N == 0, "wino_gemm: Cout %d must be a multiple of %d", d->Cout, kG2N);
+  const int tiles = d->TH * d->TW;
+  TSNET_ARG_CHECK(tiles % kBlockM == 0, "wino_gemm: TH*TW = %d must be a multiple of 128", tiles);
+  const int Wt = d->TW < kBlockM ? d->TW : kBlockM;
+  TSNET_ARG_CHECK(kBlockM % Wt == 0 && d->TW % Wt == 0, "wino_gemm: unsupported tile-row width %d", d->TW);
+  const int rows = kBlockM / Wt;
+  TSNET_ARG_CHECK(d->TH % rows == 0, "wino_gemm: TH %d not a multiple of %d", d->TH, rows);
+
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tiles_per_img = tiles / kBlockM;
+  a.num_m_tiles = d->B * a.tiles_per_img;
+  const bool two_cta = (d->flags & TSNET_CONV_ONE_CTA) == 0 && a.num_m_tiles % 2 == 0;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->TW, (uint64_t)d->TH, (uint64_t)d->B * 16};
+    const uint64_t str[3] = {(uint64_t)d->C * 2, (uint64_t)d->TW * d->C * 2, (uint64_t)tiles * d->C * 2};
+    const uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)rows, 1};
+    int r = encode_tmap_u16_sw128(&a.a_hi, v_hi, 4, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, v_lo, 4, dims, str, box))) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)16 * d->Cout};
+    const uint64_t str[1] = {(uint64_t)d->C * 2};
+    const uint32_t box[2] = {64, two_cta ? (uint32_t)(kG2N / 2) : (uint32_t)kG2N};
+    int r = encode_tmap_u16_sw128(&a.b_hi, u_hi, 2, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.b_lo, u_lo, 2, dims, str, box))) return r;
+  }
+  a.y = m_out;
+  a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  a.num_n_tiles = d->Cout / kG2N;
+  a.Wt = Wt;
+  a.rows_per_tile = rows;
+  a.wtiles_per_row = d->TW / Wt;
+  a.Cout = d->Cout;
+  a.num_taps = 1;
+  a.kc_per_tap = d->C / 64;
+  a.planes = 16;
+  a.split = d->split;
+  a.fmt = d->fmt;
+  a.chunk_kb = d->chunk_kb > 0 ? d->chunk_kb : (d->split ? 2 : 6);
+  a.batch_planes = 16;
+  a.b_plane_rows = d->Cout;
+  a.y_plane_stride = static_cast<long long>(d->B) * tiles * d->Cout;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return two_cta ? launch_conv_gemm2(a, s) : launch_conv_gemm<256>(a, s);
 }

@@ -883,12 +883,10 @@ __global__ void __launch_bounds__(256) warp_mean_taps_kernel(const WarpTapsArgs 
   }
 }
 
-// 2-CTA tile kernel (cta_group::2) is the default; TSNET_K1_2CTA=0 selects the 1-CTA kernel (tests compare the two).
-// tsnet_corr_prepare and tsnet_corr_tiles of one forward must see the same setting (the work list granularity differs).
-static bool corr_use_2cta() {
-  const char* e = getenv("TSNET_K1_2CTA");
-  return e == nullptr || atoi(e) != 0;
-}
+// 2-CTA tile kernel (cta_group::2) is the default; tsnet_corr_desc.one_cta selects the 1-CTA kernel (tests compare the
+// two).  tsnet_corr_prepare and tsnet_corr_tiles read the same descriptor field, so the work-list granularity always
+// matches the kernel that consumes the list.
+static bool corr_use_2cta(const tsnet_corr_desc* d) { return d->one_cta == 0; }
 
 static int corr_desc_check(const tsnet_corr_desc* d) {
   TSNET_ARG_CHECK(d, "corr: null descriptor");
@@ -947,8 +945,7 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
   a.B = d->B; a.n_src = d->n_src; a.h = d->h; a.w = d->w; a.hw = hw;
   a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
   a.sort = d->sort;
-  if (const char* e = getenv("TSNET_K1_SORT")) a.sort = atoi(e);  // experiments only
-  a.pair = corr_use_2cta() ? 1 : 0;
+  a.pair = corr_use_2cta(d) ? 1 : 0;
   corr_sort_kernel<<<dim3(d->B, d->n_src + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
   corr_plan_kernel<<<d->B, 384, 0, static_cast<cudaStream_t>(stream)>>>(a);
@@ -977,7 +974,7 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
     if (r) return r;
     if (d->split && (r = encode_tmap_u16_sw128(&a.t_lo, tar_lo, 2, dims, str, box))) return r;
   }
-  const bool two_cta = corr_use_2cta();
+  const bool two_cta = corr_use_2cta(d);
   {
     const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)d->n_src * d->B * hw};
     const uint64_t str[1] = {(uint64_t)d->C * 2};
@@ -996,19 +993,14 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
   a.ncand = d->n_src * (hw / kCorrM) * (hw / kCorrN) / (two_cta ? 2 : 1);
   a.NS = 2 * (hw / kCorrN);
   a.split = d->split; a.fmt = d->fmt;
-  a.chunk_kb = d->C / kCorrK;  // whole K accumulated in TMEM (see the header comment)
-  if (const char* e = getenv("TSNET_K1_CHUNK_KB")) a.chunk_kb = atoi(e) > 0 ? atoi(e) : a.chunk_kb;  // experiments only
+  a.chunk_kb = d->chunk_kb > 0 ? d->chunk_kb : d->C / kCorrK;  // default: whole K accumulated in TMEM (header comment)
   // operand_scale is a power of two, so folding it into the temperature is exact up to one rounding of the product
   a.k2 = d->temperature / (d->operand_scale == 0.f ? 1.f : d->operand_scale) * kLog2e;
 
   const int max_items = d->B * a.ncand;
   if (two_cta) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      TSNET_CUDA_CHECK(cudaFuncSetAttribute(corr_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            kCorr2SmemBytes));
-      attr2_set = true;
-    }
+    static int attr2[kMaxDevices] = {0};
+    TSNET_CUDA_CHECK(ensure_dyn_smem(corr_tile2_kernel, kCorr2SmemBytes, attr2));
     const int pairs = max_items < num_sms() / 2 ? max_items : num_sms() / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1027,12 +1019,8 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
     TSNET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, corr_tile2_kernel, a));
     return 0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSNET_CUDA_CHECK(cudaFuncSetAttribute(corr_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kCorrSmemBytes));
-    attr_set = true;
-  }
+  static int attr1[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(corr_tile_kernel, kCorrSmemBytes, attr1));
   const int grid = max_items < num_sms() ? max_items : num_sms();
   corr_tile_kernel<<<grid, kCorrThreads, kCorrSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();

@@ -4,6 +4,7 @@
 // fp32 direct convolution used for on-device validation.
 #include "sm100_prims.cuh"
 #include "host_util.h"
+#include "wino_passes.cuh"
 #include "../../include/tsnet_b200.h"
 #include <stdlib.h>
 #include <cuda_bf16.h>
@@ -635,6 +636,8 @@ __global__ void direct_conv_kernel(const float* __restrict__ x, int B, int H, in
   }
 }
 
+int launch_wino_input(const WinoInArgs& a, cudaStream_t stream);  // winograd.cu
+
 static inline int grid_for(size_t total, int block, int max_blocks = 148 * 16) {
   size_t g = (total + block - 1) / block;
   return static_cast<int>(g < static_cast<size_t>(max_blocks) ? (g ? g : 1) : max_blocks);
@@ -645,14 +648,14 @@ static inline int grid_for(size_t total, int block, int max_blocks = 148 * 16) {
 using namespace tsnet;
 
 namespace tsnet {
-long long& launch_counter() {
-  static long long n = 0;  // host-side bookkeeping of one process; launches are enqueued from one thread at a time
+std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> n{0};
   return n;
 }
 }  // namespace tsnet
 
 extern "C" int tsnet_abi_version(void) { return TSNET_ABI_VERSION; }
-extern "C" long long tsnet_launch_count(void) { return tsnet::launch_counter(); }
+extern "C" long long tsnet_launch_count(void) { return tsnet::launch_counter().load(); }
 extern "C" const char* tsnet_last_error(void) { return last_error_buf(); }
 extern "C" int tsnet_device_ok(void) {
   int dev = 0, major = 0;
@@ -706,6 +709,14 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   TSNET_ARG_CHECK(a.avg_n == 1 || d->mode == TSNET_TAPS_SAME, "build_taps: avg_n needs mode SAME");
   TSNET_ARG_CHECK(a.act_c_off % 4 == 0 && a.act_C_total % 4 == 0 && a.act_c_off + d->C <= a.act_C_total,
                   "build_taps: act_out channel window does not fit");
+  if (d->mode == TSNET_TAPS_WINO) {  // Winograd input transform (wino_passes.cuh / winograd.cu)
+    TSNET_ARG_CHECK(a.avg_n == 1, "build_taps: avg_n needs mode SAME");
+    WinoInArgs w;
+    w.raw = raw; w.mean_rstd = mean_rstd; w.residual = residual; w.act_out = act_out; w.hi = taps_hi; w.lo = taps_lo;
+    w.B = d->B; w.H = d->H; w.W = d->W; w.C = d->C; w.relu = d->relu; w.Cp_total = d->Cp_total; w.c_off = d->c_off;
+    w.fmt = d->fmt; w.act_C_total = a.act_C_total; w.act_c_off = a.act_c_off; w.scale = a.scale;
+    return launch_wino_input(w, static_cast<cudaStream_t>(stream));
+  }
   a.planes = 1;
   switch (d->mode) {
     case TSNET_TAPS_SAME: a.Hd = d->H; a.Wd = d->W; break;
@@ -724,7 +735,8 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
     case TSNET_TAPS_S2ZERO: build_taps_kernel<TSNET_TAPS_S2ZERO><<<rows, 256, 0, st>>>(a); break;
     default:
       // quad kernel (9 instead of 16 normalised fetches per 2 x 2 block); the generic one stays for odd shapes / tests
-      if (a.hi && !act_out && a.avg_n == 1 && d->C % 4 == 0 && d->H >= 2 && d->W >= 2 && getenv("TSNET_UP2_GENERIC") == nullptr)
+      if (a.hi && !act_out && a.avg_n == 1 && d->C % 4 == 0 && d->H >= 2 && d->W >= 2 &&
+          (d->flags & TSNET_TAPS_GENERIC_UP2) == 0)
         build_taps_up2_kernel<<<static_cast<unsigned>(a.B) * a.H, 256, 0, st>>>(a);
       else
         build_taps_kernel<TSNET_TAPS_UP2REFLECT1><<<rows, 256, 0, st>>>(a);

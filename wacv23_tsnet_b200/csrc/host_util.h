@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 
 namespace tsnet {
 
@@ -34,12 +35,30 @@ inline int set_error(int code, const char* fmt, ...) {
 
 // every kernel launch of the library goes through this check: it also counts the launch (tsnet_launch_count(),
 // reported by bench.py as gpu_launches)
-long long& launch_counter();
+std::atomic<long long>& launch_counter();
 #define TSNET_LAUNCH_CHECK()            \
   do {                                  \
     ++::tsnet::launch_counter();        \
     TSNET_CUDA_CHECK(cudaGetLastError()); \
   } while (0)
+
+// Per-device state: function attributes (cudaFuncSetAttribute) and the SM count belong to a device / context, not to
+// the process, so the "done once" flags are kept per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+// opt a kernel in to `bytes` of dynamic shared memory on the current device (once per device and size)
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, int (&cache)[kMaxDevices]) {
+  const int dev = current_device();
+  if (cache[dev] >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) cache[dev] = bytes;
+  return e;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -79,14 +98,14 @@ inline int encode_tmap_u16_sw128(CUtensorMap* out, const void* base, int rank, c
 }
 
 inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace tsnet

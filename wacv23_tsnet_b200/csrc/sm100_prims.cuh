@@ -295,6 +295,8 @@ __device__ __forceinline__ void split16(float x, int fmt, uint16_t& hi, uint16_t
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
   } else {
+    // saturate at the largest finite fp16: an overflowing hi = inf would make lo = x - inf = -inf and the MMA NaN
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
     const __half h = __float2half_rn(x);
     const __half l = __float2half_rn(x - __half2float(h));
     hi = __half_as_ushort(h);

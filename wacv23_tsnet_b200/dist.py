@@ -55,9 +55,13 @@ def broadcast_generator(model, src=0):
     """Make every rank hold rank `src`'s generator parameters (bit-identical replicas)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
-    for name in GENERATOR_NETS:
-        for p in getattr(model, name).parameters():
-            dist.broadcast(p.data, src=src)
+    with torch.no_grad():
+        for name in GENERATOR_NETS:
+            for p in getattr(model, name).parameters():
+                dist.broadcast(p.data, src=src)
+    # the broadcast writes through .data (no version bump): drop packed weights / captured graphs of earlier forwards
+    if hasattr(model, "invalidate_weights"):
+        model.invalidate_weights()
 
 
 def all_gather_frames(x):

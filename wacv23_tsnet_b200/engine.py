@@ -15,7 +15,7 @@ from .ops import MathMode, PackedConv
 
 class ForwardEngine:
     def __init__(self, img_enc, lbl_enc, fuse_net, dec, label_nc, n_blocks_dec, n_downsampling=3, ngf=64,
-                 math_mode="fp16x3"):
+                 math_mode="fp16x3", winograd=True):
         if n_downsampling != 3 or ngf != 64:
             # FuseNet(ngf=1024) is hard-coded in the reference (model/TSNet.py:227): only 64 * 2^3 = 512 fits.
             raise ValueError("TS-Net geometry requires ngf=64, n_downsampling=3 (FuseNet is fixed at 1024 channels)")
@@ -29,8 +29,18 @@ class ForwardEngine:
         # and the longer epilogue serialises with the MMA pipe -- see DESIGN.md section 4.  Default: unfused.
         import os
         self.fused_in = os.environ.get("TSNET_FUSED_IN", "0") == "1"
+        # Winograd F(2x2, 3x3) for every ResnetBlock convolution (img_enc x 18, FuseNet x 2 + its target half, decoder
+        # x 2 n_blocks): 2.25 x fewer tensor-core MACs for the layers that take ~60 % of the step.
+        # winograd=False keeps the direct implicit GEMM for them (A/B comparisons, tests).
+        self.winograd = bool(winograd)
         self._packs = {}
         self._coord = {}
+
+    def invalidate(self):
+        """Drop every packed weight.  Needed after parameter writes that do not bump the tensor version
+        (`p.data.copy_()`, `init.normal_(p.data)`, `dist.broadcast(p.data)`): the pack cache is keyed on
+        (data_ptr, _version) and would otherwise keep serving the old operands."""
+        self._packs.clear()
 
     # ------------------------------------------------------------------ weights
     def _pack(self, net, wkey, fold_kw=False, block_n=None, cin_range=None, with_bias=True):
@@ -47,6 +57,22 @@ class ForwardEngine:
             self._packs[key] = hit
         return hit[1]
 
+    def _pack_wino(self, net, wkey, cin_range=None, with_bias=True):
+        """Winograd-domain packed weight (U = G g G^T, 16 K-major hi/lo matrices); same cache policy as _pack."""
+        sd = self.nets[net].state_dict(keep_vars=True)
+        w, b = sd[wkey + ".weight"], sd[wkey + ".bias"]
+        sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, self.mode.name)
+        key = (net, wkey, cin_range, with_bias, "wino")
+        hit = self._packs.get(key)
+        if hit is None or hit[0] != sig:
+            hit = (sig, ops.PackedWino(w, b if with_bias else None, self.mode, cin_range=cin_range))
+            self._packs[key] = hit
+        return hit[1]
+
+    def _tmode3(self, H, W, Cin, Cout):
+        """Operand format a 3x3 reflect-pad convolution consumes: Winograd planes where the path applies."""
+        return L.TAPS_WINO if (self.winograd and ops.wino_ok(H, W, Cin, Cout)) else L.TAPS_REFLECT1
+
     def _coord_table(self, h, w, device):
         key = (h, w, str(device))
         if key not in self._coord:
@@ -61,15 +87,31 @@ class ForwardEngine:
         mr = ops.instnorm_reduce(stats, B, H * W, pc.Cout) if norm else None
         return y, mr
 
+    def _conv3(self, taps, net, wkey, B, H, W, norm=True, addend=None, cin_range=None, with_bias=True):
+        """3x3 stride-1 reflect-pad convolution (ResnetBlock, model/TSNet.py:27,42) on a REFLECT1 tap source (direct
+        implicit GEMM) or on Winograd planes (taps geometry (16, H/2, W/2)).  Returns (y_raw, mean_rstd or None)."""
+        if taps[2][0] == 16:
+            pw = self._pack_wino(net, wkey, cin_range=cin_range, with_bias=with_bias)
+            y, stats = ops.wino_conv(taps, pw, B, H, W, self.mode, self.mode.act_scale, want_stats=norm, addend=addend)
+            mr = ops.instnorm_reduce(stats, B, H * W, pw.Cout) if norm else None
+            return y, mr
+        pc = self._pack(net, wkey, cin_range=cin_range, with_bias=with_bias)
+        return self._conv(taps, pc, "3x3", B, H, W, norm=norm, addend=addend)
+
     def _conv_in(self, taps, pc, kind, B, H, W, tmode, relu=False, residual=None, need_act=False, dest=None, c_off=0,
                  want_taps=True, addend=None, act_out=None, act_c_off=0):
         """conv -> InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> tap source of the next layer (tmode).
-        One fused kernel when the output is 32x32 (8 tiles per image), else conv + instnorm_reduce + build_taps.
+        `pc` is a PackedConv, or (net, wkey[, cin_range]) for a ResnetBlock 3x3 convolution (direct or Winograd,
+        decided by the operand format of `taps`).
         Returns ((hi, lo, geom) or None, act_out or None)."""
         m = self.mode
+        is3 = isinstance(pc, tuple)
+        Cout = (self.nets[pc[0]].state_dict(keep_vars=True)[pc[1] + ".weight"].shape[0]) if is3 else pc.Cout
         if act_out is None and need_act:
-            act_out = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=taps[0].device)
-        if self.fused_in and H * W == 1024 and tmode in (L.TAPS_SAME, L.TAPS_REFLECT1):
+            act_out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=taps[0].device)
+        if (self.fused_in and H * W == 1024 and tmode in (L.TAPS_SAME, L.TAPS_REFLECT1) and taps[2][0] != 16):
+            if is3:
+                pc = self._pack(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
             planes, Hd, Wd = ops.taps_geometry(tmode, H, W)
             if want_taps and dest is None:
                 hi = torch.empty((B, Hd, Wd, pc.Cout), dtype=torch.int16, device=taps[0].device)
@@ -78,24 +120,27 @@ class ForwardEngine:
                           fuse=dict(relu=relu, tmode=tmode, residual=residual, act_out=act_out, act_c_off=act_c_off,
                                     taps=dest if want_taps else None, c_off=c_off))
             return ((dest[0], dest[1], (planes, Hd, Wd)) if want_taps else None), act_out
-        y, mr = self._conv(taps, pc, kind, B, H, W, addend=addend)
+        if is3:
+            y, mr = self._conv3(taps, pc[0], pc[1], B, H, W, addend=addend, cin_range=pc[2] if len(pc) > 2 else None)
+        else:
+            y, mr = self._conv(taps, pc, kind, B, H, W, addend=addend)
         t = ops.build_taps(y, m, tmode, mean_rstd=mr, relu=relu, residual=residual, act_out=act_out,
                            act_c_off=act_c_off, taps=dest, c_off=c_off, want_taps=want_taps)
         return (t if want_taps else None), act_out
 
-    def _resblock(self, net, prefix, taps, x_res, B, H, W, last_taps=None, last_c_off=0, need_act=True,
-                  want_taps=True, tmode_out=L.TAPS_REFLECT1):
-        """ResnetBlock (model/TSNet.py:10-49). taps = reflect-padded split input, x_res = fp32 input (residual).
-        Returns (taps of the output, fp32 output or None)."""
-        pc1 = self._pack(net, prefix + "conv_block.1")
-        pc5 = self._pack(net, prefix + "conv_block.5")
-        t1, _ = self._conv_in(taps, pc1, "3x3", B, H, W, L.TAPS_REFLECT1, relu=True)
-        return self._conv_in(t1, pc5, "3x3", B, H, W, tmode_out, residual=x_res, need_act=need_act, dest=last_taps,
-                             c_off=last_c_off, want_taps=want_taps)
+    def _resblock(self, net, prefix, taps, x_res, B, H, W, dim, need_act=True, want_taps=True,
+                  tmode_out=L.TAPS_REFLECT1):
+        """ResnetBlock (model/TSNet.py:10-49). taps = operand of conv_block.1 built from x (REFLECT1 or Winograd
+        planes), x_res = fp32 x (residual).  Returns (taps of the output in tmode_out, fp32 output or None)."""
+        t1, _ = self._conv_in(taps, (net, prefix + "conv_block.1"), "3x3", B, H, W, self._tmode3(H, W, dim, dim),
+                              relu=True)
+        return self._conv_in(t1, (net, prefix + "conv_block.5"), "3x3", B, H, W, tmode_out, residual=x_res,
+                             need_act=need_act, want_taps=want_taps)
 
-    def _encoder(self, net, img, img_div, lbl, n_blocks, final_taps=None):
-        """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it or None).
-        For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the residual stream."""
+    def _encoder(self, net, img, img_div, lbl, n_blocks, final_tmode=None):
+        """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it in
+        final_tmode or None).  For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the
+        residual stream."""
         m = self.mode
         X, H, W = lbl.shape[0], lbl.shape[-2], lbl.shape[-1]
         pc = self._pack(net, "model.1", fold_kw=True)
@@ -112,11 +157,12 @@ class ForwardEngine:
         if n_blocks == 0:   # lbl_enc: the feature is relu(IN(conv))
             _, fea = self._conv_in(t, pc, "3x3s2", X, H, W, L.TAPS_SAME, relu=True, need_act=True, want_taps=False)
             return fea, None
-        t, x = self._conv_in(t, pc, "3x3s2", X, H, W, L.TAPS_REFLECT1, relu=True, need_act=True)
+        dim = pc.Cout
+        t, x = self._conv_in(t, pc, "3x3s2", X, H, W, self._tmode3(H, W, dim, dim), relu=True, need_act=True)
         for blk in range(n_blocks):
             last = blk == n_blocks - 1
-            t, x = self._resblock(net, f"model.{13 + blk}.", t, x, X, H, W,
-                                  last_taps=final_taps if last else None)
+            t, x = self._resblock(net, f"model.{13 + blk}.", t, x, X, H, W, dim,
+                                  tmode_out=final_tmode if last else self._tmode3(H, W, dim, dim))
         return x, t
 
     # ------------------------------------------------------------------ whole forward
@@ -139,18 +185,15 @@ class ForwardEngine:
         h, w, Cf = H0 // 8, W0 // 8, 512
         hw = h * w
 
-        # ---- encoders.  The last img_enc block writes its reflect-padded split output straight into the tap source
-        # of FuseNet's first conv.
-        fuse_hi = torch.empty((n * B, h + 2, w + 2, Cf), dtype=torch.int16, device=dev)
-        fuse_lo = torch.empty_like(fuse_hi)
+        # ---- encoders.  The last img_enc block writes the operand of FuseNet's first conv (source half) directly.
         if n > 1 and len(set(img_divs)) > 1:
             # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
             src_imgs = [im if dv == 1.0 else im / dv for im, dv in zip(src_imgs, img_divs)]
             img_divs = [1.0] * n
         img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
         lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
-        src_fea, _ = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]), lbl_cat.contiguous(), 9,
-                                   final_taps=(fuse_hi, fuse_lo))                       # [n*B, h, w, 512]
+        src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]), lbl_cat.contiguous(),
+                                           9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf))  # [n*B, h, w, 512]
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
         # ---- transformation branch (model/TSNet.py:319-366, 392)
@@ -176,14 +219,13 @@ class ForwardEngine:
         ops.build_taps(src_fea, m, L.TAPS_SAME, act_out=cat_act, act_c_off=0, want_taps=False)
         for i in range(n):
             ops.build_taps(tar_fea, m, L.TAPS_SAME, act_out=cat_act[i * B:(i + 1) * B], act_c_off=Cf, want_taps=False)
-        t_taps = ops.build_taps(tar_fea, m, L.TAPS_REFLECT1)
-        pc_t = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(Cf, 2 * Cf), with_bias=False)
-        y_t, _ = self._conv(t_taps, pc_t, "3x3", B, h, w, norm=False)                     # [B, h, w, 1024]
-        pc_s = self._pack("fuse_net", "model.0.conv_block.1", cin_range=(0, Cf))
-        t1, _ = self._conv_in((fuse_hi, fuse_lo, (1, h + 2, w + 2)), pc_s, "3x3", n * B, h, w, L.TAPS_REFLECT1,
-                              relu=True, addend=y_t)
-        pc5 = self._pack("fuse_net", "model.0.conv_block.5")
-        tfo, _ = self._conv_in(t1, pc5, "3x3", n * B, h, w, L.TAPS_SAME, residual=cat_act)
+        t_taps = ops.build_taps(tar_fea, m, self._tmode3(h, w, Cf, 2 * Cf))
+        y_t, _ = self._conv3(t_taps, "fuse_net", "model.0.conv_block.1", B, h, w, norm=False,
+                             cin_range=(Cf, 2 * Cf), with_bias=False)                      # [B, h, w, 1024]
+        t1, _ = self._conv_in(fuse_taps, ("fuse_net", "model.0.conv_block.1", (0, Cf)), "3x3", n * B, h, w,
+                              self._tmode3(h, w, 2 * Cf, 2 * Cf), relu=True, addend=y_t)
+        tfo, _ = self._conv_in(t1, ("fuse_net", "model.0.conv_block.5"), "3x3", n * B, h, w, L.TAPS_SAME,
+                               residual=cat_act)
         pcf = self._pack("fuse_net", "conv")
         sg, _ = self._conv(tfo, pcf, "1x1", n * B, h, w, norm=False)                     # [n*B, h, w, 512]
 
@@ -196,11 +238,11 @@ class ForwardEngine:
         nb = self.n_blocks_dec
         Hc, Wc = h, w
         if nb > 0:
-            t = ops.build_taps(x, m, L.TAPS_REFLECT1)
+            t = ops.build_taps(x, m, self._tmode3(Hc, Wc, Cf, Cf))
             for blk in range(nb):
                 last = blk == nb - 1
-                t, x = self._resblock("dec", f"model{blk}.0.", t, x, B, Hc, Wc,
-                                      tmode_out=L.TAPS_UP2REFLECT1 if last else L.TAPS_REFLECT1,
+                t, x = self._resblock("dec", f"model{blk}.0.", t, x, B, Hc, Wc, Cf,
+                                      tmode_out=L.TAPS_UP2REFLECT1 if last else self._tmode3(Hc, Wc, Cf, Cf),
                                       need_act=not last)
         else:
             t = ops.build_taps(x, m, L.TAPS_UP2REFLECT1)

@@ -10,9 +10,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TSNET_LIB_PATH", os.path.join(_HERE, "libtsnet_sm100.so"))  # override: experiments only
 
 FMT_FP16, FMT_BF16 = 0, 1
-TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1 = 0, 1, 2, 3
+TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1, TAPS_WINO = 0, 1, 2, 3, 4
 MAX_TAPS = 49
-ABI_VERSION = 2
+ABI_VERSION = 3
+CONV_NO_VR, CONV_NO_TAIL_SPLIT, CONV_ONE_CTA = 1, 2, 4   # tsnet_conv_desc.flags (launch-plan switches, tests only)
+TAPS_GENERIC_UP2 = 1                                     # tsnet_taps_desc.flags
 
 vp = C.c_void_p
 
@@ -28,19 +30,27 @@ class ConvDesc(C.Structure):
                 ("fuse_act_C_total", C.c_int), ("fuse_act_c_off", C.c_int),
                 ("fuse_taps_hi", C.c_void_p), ("fuse_taps_lo", C.c_void_p),
                 ("fuse_taps_Cp", C.c_int), ("fuse_taps_c_off", C.c_int),
-                ("fuse_act_scale", C.c_float), ("fuse_eps", C.c_float)]
+                ("fuse_act_scale", C.c_float), ("fuse_eps", C.c_float), ("flags", C.c_int)]
 
 
 class TapsDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("mode", C.c_int),
                 ("relu", C.c_int), ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int),
-                ("scale", C.c_float), ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("avg_n", C.c_int)]
+                ("scale", C.c_float), ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("avg_n", C.c_int),
+                ("flags", C.c_int)]
 
 
 class CorrDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("n_src", C.c_int), ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("bbox_h", C.c_int), ("bbox_w", C.c_int), ("bbox_dtype", C.c_int), ("temperature", C.c_float),
-                ("split", C.c_int), ("fmt", C.c_int), ("operand_scale", C.c_float), ("sort", C.c_int)]
+                ("split", C.c_int), ("fmt", C.c_int), ("operand_scale", C.c_float), ("sort", C.c_int),
+                ("one_cta", C.c_int), ("chunk_kb", C.c_int)]
+
+
+class WinoGemmDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("TH", C.c_int), ("TW", C.c_int), ("C", C.c_int), ("Cout", C.c_int),
+                ("split", C.c_int), ("fmt", C.c_int), ("out_scale", C.c_float), ("chunk_kb", C.c_int),
+                ("flags", C.c_int)]
 
 
 _SIGNATURES = {
@@ -51,6 +61,9 @@ _SIGNATURES = {
     "tsnet_pack_conv_weight": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_int, vp, vp, vp]),
     "tsnet_conv_gemm_fwd": (C.c_int, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "tsnet_wino_weight_transform": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "tsnet_wino_gemm_fwd": (C.c_int, [C.POINTER(WinoGemmDesc), vp, vp, vp, vp, vp, vp]),
+    "tsnet_wino_output": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_longlong, vp, vp, vp]),
     "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

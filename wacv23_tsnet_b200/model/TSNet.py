@@ -91,7 +91,7 @@ class TSNet(nn.Module):
                  is_train=True, getIntermFeat=True, label_nc=5,
                  debug=False, lambda_dec=1.0,
                  addcoords=True,
-                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False):
+                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False, winograd=True):
         super().__init__()
         # is_train=True: forward-only.  The generator is built exactly as for is_train=False (no discriminators, VGG,
         # optimizers -- SURVEY section 8f row 3); forward() then also runs the reference's train-mode branches
@@ -115,7 +115,7 @@ class TSNet(nn.Module):
                                      init_type='normal', init_gain=0.02)
         self.fuse_net = networks.init_net(FuseNet(ngf=1024, n_blocks=1), init_type='normal', init_gain=0.02)
         self._engine = ForwardEngine(self.img_enc, self.lbl_enc, self.fuse_net, self.dec, label_nc, n_blocks,
-                                     n_downsampling=n_downsampling, ngf=ngf, math_mode=math_mode)
+                                     n_downsampling=n_downsampling, ngf=ngf, math_mode=math_mode, winograd=winograd)
         self._pose_fill = None
         self._use_graph = bool(cuda_graph)
         self._graphs = {}
@@ -207,6 +207,13 @@ class TSNet(nn.Module):
         self._use_graph = bool(flag)
         if not flag:
             self._graphs.clear()
+
+    def invalidate_weights(self):
+        """Forget every packed weight and captured CUDA graph.  load_state_dict / optimizer steps bump the parameter
+        version and are picked up automatically; writes through `.data` (`p.data.copy_(...)`, `init.normal_(p.data)`,
+        `dist.broadcast(p.data)`) do NOT bump it and must be followed by this call."""
+        self._engine.invalidate()
+        self._graphs.clear()
 
     def _staged(self):
         n = self.n_source

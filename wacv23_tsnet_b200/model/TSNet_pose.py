@@ -19,12 +19,12 @@ class TSNet(_face.TSNet):
                  ngf=64, n_downsampling=4,
                  use_mask=True,
                  mean=np.array((101.84807705937696, 112.10832843463207, 111.65973036298041), dtype=np.float32),
-                 math_mode="fp16x3", cuda_graph=False):
+                 math_mode="fp16x3", cuda_graph=False, winograd=True):
         super().__init__(lr=lr, beta1=beta1, n_blocks=n_blocks, n_source=n_source, lambda_FML=lambda_FML,
                          lambda_VGG=lambda_VGG, lambda_CON=lambda_CON, lambda_GRAD=lambda_GRAD, is_train=is_train,
                          getIntermFeat=getIntermFeat, label_nc=label_nc, debug=debug, lambda_dec=lambda_dec,
                          addcoords=addcoords, ngf=ngf, n_downsampling=n_downsampling, return_flow=False,
-                         math_mode=math_mode, cuda_graph=cuda_graph)
+                         math_mode=math_mode, cuda_graph=cuda_graph, winograd=winograd)
         self.model_names = ['G', 'D', 'DF']
         self.use_mask = use_mask
         if self.use_mask:

@@ -115,8 +115,73 @@ class PackedConv:
         _count()
 
 
+class PackedWino:
+    """A 3x3 conv weight in the Winograd F(2x2, 3x3) domain, packed for tsnet_wino_gemm_fwd: U = G g G^T
+    (tsnet_wino_weight_transform, fp64 arithmetic) as 16 K-major hi/lo matrices [16 * Cout, Cp]."""
+
+    def __init__(self, weight, bias, mode, cin_range=None):
+        L.require_device()
+        w = weight.detach()
+        if cin_range is not None:
+            w = w[:, cin_range[0]:cin_range[1]]
+        w = _f32(w.contiguous())
+        Cout, Cin, KH, KW = w.shape
+        assert (KH, KW) == (3, 3) and Cout % 256 == 0 and Cin % 64 == 0, (tuple(w.shape),)
+        self.Cout, self.Cin, self.Cp = Cout, Cin, Cin
+        u = torch.empty((16, Cout, Cin), dtype=torch.float32, device=w.device)
+        L.check(L.load().tsnet_wino_weight_transform(_ptr(w), Cout, Cin, _ptr(u), _stream()))
+        _count()
+        self.scale = mode.weight_scale(u)
+        self.u_hi = torch.empty((16 * Cout, Cin), dtype=torch.int16, device=w.device)
+        self.u_lo = torch.empty_like(self.u_hi)
+        self.bias = None if bias is None else _f32(bias.detach())
+        # U viewed as a 1x1 conv weight [16 * Cout, Cin, 1, 1]
+        L.check(L.load().tsnet_pack_conv_weight(_ptr(u), 16 * Cout, Cin, 1, 1, 0, Cin, 16 * Cout,
+                                                C.c_float(self.scale), mode.fmt, _ptr(self.u_hi), _ptr(self.u_lo),
+                                                _stream()))
+        _count()
+
+
+def wino_ok(H, W, Cin, Cout):
+    """Shapes the Winograd path covers: every ResnetBlock convolution of the network (32 x 32, 512 / 1024 channels)."""
+    return (H % 2 == 0 and W % 2 == 0 and ((H // 2) * (W // 2)) % 128 == 0 and (W // 2) % 8 == 0 and
+            (W // 2 <= 128 and 128 % (W // 2) == 0) and Cin % 64 == 0 and Cout % 256 == 0)
+
+
+def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, m_buf=None, flags=0, chunk_kb=0):
+    """3x3 reflect-pad conv via Winograd: taps = (hi, lo, geom) from build_taps(mode TAPS_WINO).
+    Returns (y_raw [B, H, W, Cout], stats_partial or None) -- the outputs of conv_gemm."""
+    hi, lo, geom = taps
+    TH, TW = H // 2, W // 2
+    assert geom == (16, TH, TW) and hi.shape == (B * 16, TH, TW, pw.Cp), (geom, tuple(hi.shape))
+    dev = hi.device
+    n_m = 16 * B * TH * TW * pw.Cout
+    if m_buf is None or m_buf.numel() < n_m:
+        m_buf = torch.empty(n_m, dtype=torch.float32, device=dev)
+    d = L.WinoGemmDesc()
+    d.B, d.TH, d.TW, d.C, d.Cout = B, TH, TW, pw.Cp, pw.Cout
+    d.split, d.fmt, d.out_scale, d.chunk_kb, d.flags = mode.split, mode.fmt, 1.0 / (pw.scale * act_scale), chunk_kb, flags
+    with _Prof(("wino_gemm", "3x3", B, H, W, pw.Cin, pw.Cout, 9)):
+        L.check(L.load().tsnet_wino_gemm_fwd(C.byref(d), _ptr(hi), _ptr(lo), _ptr(pw.u_hi), _ptr(pw.u_lo), _ptr(m_buf),
+                                             _stream()))
+    _count()
+    y = torch.empty((B, H, W, pw.Cout), dtype=torch.float32, device=dev)
+    stats = torch.empty((B * H * W // 32, pw.Cout, 2), dtype=torch.float32, device=dev) if want_stats else None
+    rows = 0
+    if addend is not None:
+        assert addend.shape[-1] == pw.Cout and addend.is_contiguous() and addend.dtype == torch.float32
+        rows = addend.numel() // pw.Cout
+    with _Prof(("wino_output",)):
+        L.check(L.load().tsnet_wino_output(_ptr(m_buf), B, H, W, pw.Cout, _ptr(pw.bias), _ptr(addend), rows, _ptr(y),
+                                           _ptr(stats), _stream()))
+    _count()
+    return y, stats
+
+
 def taps_geometry(mode, H, W):
     """(planes, Hd, Wd) of the tap source built from an H x W activation."""
+    if mode == L.TAPS_WINO:
+        return 16, H // 2, W // 2
     if mode == L.TAPS_SAME:
         return 1, H, W
     if mode == L.TAPS_REFLECT1:
@@ -160,7 +225,7 @@ def _pick_block_n(pc, m_tiles):
 
 
 def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_stats=True, y=None, stats=None,
-              addend=None, fuse=None):
+              addend=None, fuse=None, flags=0):
     """taps_* : int16 [B*planes, Hp, Wp, Cp]; geom = (planes, Hp, Wp). Returns (y_raw [B,H,W,Cout], stats)."""
     planes, Hp, Wp = geom
     d = L.ConvDesc()
@@ -173,6 +238,7 @@ def conv_gemm(taps_hi, taps_lo, geom, pc, kind, B, H, W, mode, act_scale, want_s
         d.tap_dy[t], d.tap_dx[t], d.tap_plane[t] = dy, dx, pl
     d.block_n, d.split, d.fmt = _pick_block_n(pc, B * H * W // 128), mode.split, mode.fmt
     d.out_scale = 1.0 / (pc.scale * act_scale)
+    d.flags = flags
     if addend is not None:  # fp32 [rows, Cout], broadcast over the leading batch dimension by row index modulo
         assert addend.shape[-1] == pc.Cout and addend.is_contiguous() and addend.dtype == torch.float32
         d.addend, d.addend_rows = addend.data_ptr(), addend.numel() // pc.Cout
@@ -223,7 +289,7 @@ def instnorm_reduce(stats, B, HW, Cch, eps=1e-5, out=None):
 
 
 def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_out=None, act_c_off=0,
-               taps=None, c_off=0, want_taps=True, avg_n=1, act_scale=None):
+               taps=None, c_off=0, want_taps=True, avg_n=1, act_scale=None, flags=0):
     """raw: fp32 [avg_n*B, H, W, C].  Returns (taps_hi, taps_lo, geom) (None, None, geom when want_taps=False).
     `taps` = (hi, lo) preallocated destination (for channel-concatenation), else allocated here."""
     Bt, H, W, Cch = raw.shape
@@ -234,6 +300,7 @@ def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_
     d.fmt = mode.fmt
     d.scale = mode.act_scale if act_scale is None else act_scale
     d.avg_n = avg_n
+    d.flags = flags
     hi = lo = None
     if want_taps:
         if taps is None:
@@ -249,7 +316,7 @@ def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_
         d.Cp_total, d.c_off = hi.shape[3], c_off
     if act_out is not None:
         d.act_C_total, d.act_c_off = act_out.shape[-1], act_c_off
-    with _Prof(("build_taps",)):
+    with _Prof(("build_taps", tmode)):
         L.check(L.load().tsnet_build_taps(C.byref(d), _ptr(_f32(raw)), _ptr(mean_rstd), _ptr(residual), _ptr(act_out),
                                           _ptr(hi), _ptr(lo), _stream()))
     _count()
@@ -284,7 +351,8 @@ class CorrPlan:
         self.B, self.n, self.C, self.h, self.w = B, n, Cch, h, w
 
 
-def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=100.0, sort=True):
+def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=100.0, sort=True,
+                 one_cta=False, chunk_kb=0):
     """model/TSNet.py:322-323, :347-348 (nearest down-sampling of the bbox masks) + the class-sorted work plan of the
     correlation kernel.  bboxes [B, Hb, Wb] uint8 or fp32 (full resolution)."""
     n = len(src_bbox_list)
@@ -297,6 +365,7 @@ def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, tempe
     d.temperature, d.split, d.fmt = temperature, mode.split, mode.fmt
     d.operand_scale = mode.corr_scale * mode.corr_scale
     d.sort = 1 if sort else 0
+    d.one_cta, d.chunk_kb = int(one_cta), chunk_kb
     lib = L.load()
     nbytes = lib.tsnet_corr_workspace_bytes(C.byref(d))
     if nbytes == 0:
@@ -357,12 +426,13 @@ def corr_warp(plan, tar_ops, src_ops, src_fea_list, mode, want_grids=False, want
 
 
 def corr_chain(tar_fea, src_fea, tar_bbox, src_bbox_list, coord_table, mode, temperature=100.0, want_grids=True,
-               want_mean=False, taps=None, c_off=0, sort=True):
+               want_mean=False, taps=None, c_off=0, sort=True, one_cta=False):
     """The whole transformation branch on raw features (model/TSNet.py:319-366, :392): tar_fea fp32 [B, hw, C],
     src_fea fp32 [n, B, hw, C] -> (mean of the warped sources [B, hw, C] or None, warp grids [n, B, h, w, 2] or None)."""
     n, B, hw, Cch = src_fea.shape
     h = w = int(round(hw ** 0.5))
-    plan = corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=temperature, sort=sort)
+    plan = corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=temperature, sort=sort,
+                        one_cta=one_cta)
     tar_ops = l2norm_split(tar_fea, mode, rank=plan.rank_t)
     src_ops = l2norm_split(src_fea.view(n * B, hw, Cch), mode, rank=plan.rank_s)
     return corr_warp(plan, tar_ops, src_ops, [src_fea[i] for i in range(n)], mode, want_grids=want_grids,
