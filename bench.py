@@ -33,10 +33,31 @@ def log(msg):
     print(f"[bench +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+def csrc_sha1():
+    """Hash of the kernel sources: ties a committed ncu capture to the code it was taken from."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "wacv23_tsnet_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) +
+                    glob.glob(os.path.join(d, "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def load_traffic():
-    """DRAM bytes per launch from the committed ncu captures (profiles/traffic.json); None when not captured."""
+    """DRAM bytes per launch from the committed ncu captures (profiles/traffic.json).  The file records the hash of
+    the kernel sources the captures were taken from; when csrc/ has changed since, the numbers are stale and `traffic`
+    is reported as null instead (with the reason)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    return json.load(open(p)) if os.path.isfile(p) else {}
+    if not os.path.isfile(p):
+        return {}
+    d = json.load(open(p))
+    if d.get("csrc_sha1") != csrc_sha1():
+        return {"_stale": f"profiles/traffic.json was captured from csrc sha1 {str(d.get('csrc_sha1'))[:12]}, "
+                          f"current sources are {csrc_sha1()[:12]}: traffic not reported"}
+    return d
 
 
 def load_peaks():
@@ -327,6 +348,30 @@ def run_b200(args):
         log(f"e2e region done: {ms_e2e / args.steps:.2f} ms/step")
     gc.enable()
 
+    # ---- N > 1: the batch split must be EXACT, not only fast.  Rank 0 regenerates rank 1's inputs, recomputes its
+    # first two rows on its own GPU and demands bit-identical frames (outside the timed region).
+    shard_check = None
+    if world > 1:
+        with torch.no_grad():
+            step_resident()
+            mine = net.rec_tar_img[:2].contiguous()
+            if rank == 1:
+                tdist.send(mine, dst=0)
+            if rank == 0:
+                theirs = torch.empty_like(mine)
+                tdist.recv(theirs, src=1)
+                inp1 = make_inputs(bs, L, n, seed=1234 + 1, pose=args.pose)
+                t = lambda a: torch.from_numpy(a[:2]).to(dev)
+                net.set_test_input([t(a) for a in inp1["src_img"]], [t(a) for a in inp1["src_lbl"]],
+                                   [t(a) for a in inp1["src_bbox"]], t(inp1["tar_lbl"]), t(inp1["tar_bbox"]))
+                net.forward()
+                same = bool(torch.equal(net.rec_tar_img, theirs))
+                shard_check = {"what": "rows 0-1 of rank 1's shard recomputed on rank 0 (bs=2 instead of inside bs="
+                                       f"{bs}) vs the frames rank 1 produced", "bit_identical": same}
+                log(f"shard check: bit_identical={same}")
+                assert same, "sharded forward differs from the single-GPU forward of the same rows"
+        barrier()
+
     frames = bs * world * args.steps
     value = frames / (ms * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
@@ -357,6 +402,7 @@ def run_b200(args):
         conv_traffic = traffic.get(tkey) if (kind, X, Hh, Cin_eff, Cout) == ("3x3", 96, 32, 512, 512) else None
         roof = {"kernel": f"{kname} {kind} {Cin_eff}->{Cout} @{Hh}x{Ww} x{X} samples", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": conv_traffic,
+                "traffic_source": traffic.get("_stale") or traffic.get("source"),
                 "algorithmic_flops_per_launch": flops,
                 "peak_source": peaks["source"] + ", bf16 sustained",
                 "note": "fp32-faithful mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi): "
@@ -407,6 +453,30 @@ def run_b200(args):
                    "sample": "5 forwards of bs=1 of the same config (oracle/tsnet_oracle.py = bit-exact CPU "
                              "restatement of the reference forward), 1 warm-up"}
         eager = None
+        fast = None
+        if world == 1 and args.fast_point:
+            # clearly labelled NON-PARITY speed point: single-pass fp16 operands (fails the parity tolerance; never the
+            # headline -- tests/test_parity_gpu.py::test_fast_modes_run_and_are_flagged_non_parity)
+            try:
+                torch.manual_seed(1234)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    fnet = TSNet(is_train=False, label_nc=L, n_blocks=nb, n_downsampling=3, n_source=n,
+                                 math_mode="fp16", winograd=args.winograd)
+                fnet.eval()
+                with torch.no_grad():
+                    def fstep():
+                        fnet.set_test_input(devin["src_img"], devin["src_lbl"], devin["src_bbox"], devin["tar_lbl"],
+                                            devin["tar_bbox"])
+                        fnet.forward()
+                    for _ in range(3):
+                        fstep()
+                    fms, _, _ = timed(fstep, 5)
+                fast = {"math_mode": "fp16 (single pass, NOT parity grade)", "frames_per_s": bs * 5 / (fms * 1e-3),
+                        "ms_per_step": fms / 5}
+                del fnet
+                torch.cuda.empty_cache()
+            except Exception as e:
+                fast = {"error": repr(e)[:200]}
         if world == 1 and args.torch_cuda_baseline:
             sds_np = {k: {kk: vv.detach().cpu().numpy() for kk, vv in getattr(net, k).state_dict().items()}
                       for k in D.GENERATOR_NETS}
@@ -433,7 +503,8 @@ def run_b200(args):
                         "api": "FramePipeline.run (H2D / forward / D2H of consecutive batches overlapped)"
                         if args.e2e_mode == "pipelined" else "set_test_input + forward + rec_tar_img.cpu()"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_corr_warp": roof_corr,
-                "kernel_shares": shares, "cpu_baseline": cpu, "torch_cuda_eager_port": eager}
+                "kernel_shares": shares, "cpu_baseline": cpu, "torch_cuda_eager_port": eager,
+                "non_parity_speed_point": fast, "shard_check": shard_check}
         emit(line)
     if world > 1:
         tdist.barrier()
@@ -473,8 +544,11 @@ def main():
     ap.add_argument("--no-winograd", dest="winograd", action="store_false",
                     help="direct implicit GEMM for the ResnetBlock convolutions (A/B against the Winograd default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-cuda-baseline", dest="torch_cuda_baseline", action="store_true",
-                    help="also time the reference's torch op sequence eagerly on the GPU (cuDNN), bs = --batch")
+    ap.add_argument("--no-torch-cuda-baseline", dest="torch_cuda_baseline", action="store_false",
+                    help="skip timing the reference's torch op sequence eagerly on the GPU (cuDNN / cuBLAS, bs = --batch;"
+                         " on by default at N=1: BASELINE.md section 3 step 4)")
+    ap.add_argument("--no-fast-point", dest="fast_point", action="store_false",
+                    help="skip the labelled non-parity single-pass fp16 speed point")
     ap.add_argument("--e2e-mode", dest="e2e_mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined: wacv23_tsnet_b200.pipeline.FramePipeline; sync: set_test_input + forward + .cpu()")
     args = ap.parse_args()

@@ -30,6 +30,9 @@ CONFIGS = {
     "pose_bs1_nb4": dict(kind="ds", bs=1, label_nc=25, n_blocks=4, n_source=3, pose=True, bias_std=0.05),
     "face_bs2_n1": dict(kind="ds", bs=2, label_nc=2, n_blocks=0, n_source=1, pose=False, bias_std=0.0),
     "face_bs1_n5": dict(kind="qs", bs=1, label_nc=2, n_blocks=0, n_source=5, pose=False, bias_std=0.0),
+    # round 2: the top point of the n_source sweep (BASELINE.json config 5) and a batched FaceForensics forward
+    "face_bs1_n8": dict(kind="ds", bs=1, label_nc=2, n_blocks=0, n_source=8, pose=False, bias_std=0.05),
+    "face_bs2_nb4_n3": dict(kind="ds", bs=2, label_nc=2, n_blocks=4, n_source=3, pose=False, bias_std=0.05),
 }
 
 
@@ -98,7 +101,10 @@ def main():
         sys.exit("reference not found: goldens can only be (re)generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])   # optional: names of the configs to (re)generate
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         t0 = time.time()
         sds, inputs = build_case(cfg)
         mean = synth.IMG_MEAN if cfg["pose"] else None

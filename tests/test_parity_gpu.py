@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 # 1.5e-5 (grids) away from an fp64 evaluation of the same network -- random-init weights + softmax(100 x) amplify
 # rounding noise by ~1e3.  We require agreement with the reference within IMG_TOL / GRID_TOL below.
 # Measured on B200 (fp16x3): image 3.7e-4 .. 5.8e-4, grids 1.8e-5, features 2.9e-6 rel, pg_mean 2.4e-4 rel.
-IMG_TOL = 2e-3      # max-abs on rec_tar_img, tanh range (-1, 1): 4x the reference's fp32-vs-fp64 noise
-GRID_TOL = 1e-4     # max-abs on warp grids, [-1, 1] units (= 1.6e-3 feature pixels)
+IMG_TOL = 1e-3      # max-abs on rec_tar_img, tanh range (-1, 1): 2x the reference's own fp32-vs-fp64 noise (5e-4)
+GRID_TOL = 5e-5     # max-abs on warp grids, [-1, 1] units (= 8e-4 feature pixels); reference fp32-vs-fp64: 1.4e-5
 FEA_TOL = 2e-5      # encoder features, relative to max|ref|
 MIX_TOL = 1e-3      # pg_mean / sg_mean, relative to max|ref|
 
@@ -44,7 +44,8 @@ def _feed(net, inputs, sl=slice(None)):
                        torch.from_numpy(inputs["tar_lbl"][sl]), torch.from_numpy(inputs["tar_bbox"][sl]))
 
 
-@pytest.mark.parametrize("name", ["quickstart_bs1", "face_bs1_nb4", "pose_bs1_nb4", "face_bs2_n1", "face_bs1_n5"])
+@pytest.mark.parametrize("name", ["quickstart_bs1", "face_bs1_nb4", "pose_bs1_nb4", "face_bs2_n1", "face_bs1_n5",
+                                  "face_bs1_n8", "face_bs2_nb4_n3"])
 def test_forward_matches_reference_golden(name):
     cfg, gold, inputs, net = _build(name)
     _feed(net, inputs)
@@ -178,6 +179,68 @@ def test_full_batch_properties():
         net.forward()
         assert torch.equal(torch.stack(net.warp_grid2d_list), grids[:, 0:4].flip(0))
         assert float((net.rec_tar_img - full[0:4]).abs().max()) < 2e-3
+
+
+def test_bs32_rows_match_the_oracle():
+    """The benchmark's batch size checked directly: bs=32, n_blocks=4, n_source=3 (BASELINE.json config 2) on the GPU,
+    rows 0, 17 and 31 against the oracle (bit-exact restatement of the reference forward) run on the host for just
+    those samples."""
+    from oracle import synth, tsnet_oracle as O
+    from wacv23_tsnet_b200.model.TSNet import TSNet
+    sds = synth.make_state_dicts(2, 4, seed=1234, bias_std=0.05)
+    inputs = synth.dataset_like_inputs(32, 2, 3, seed=7)
+    net = TSNet(is_train=False, label_nc=2, n_blocks=4, n_downsampling=3, n_source=3, return_flow=True)
+    for k in ("img_enc", "lbl_enc", "fuse_net", "dec"):
+        getattr(net, k).load_state_dict({kk: torch.from_numpy(v) for kk, v in sds[k].items()})
+    net.eval()
+    with torch.no_grad():
+        _feed(net, inputs)
+        net.forward()
+    out = net.rec_tar_img.cpu()
+    grids = torch.stack(net.warp_grid2d_list).cpu()
+    tsd = O.to_torch_sd(sds)
+    for r in (0, 17, 31):
+        one = {k: ([a[r:r + 1] for a in v] if isinstance(v, list) else v[r:r + 1]) for k, v in inputs.items()}
+        ref = O.tsnet_forward(tsd, one, 4)
+        assert float((out[r:r + 1] - ref["rec_tar_img"]).abs().max()) < IMG_TOL, r
+        assert float((grids[:, r:r + 1] - torch.stack(ref["grids"])).abs().max()) < GRID_TOL, r
+
+
+def test_direct_and_winograd_paths_agree():
+    """winograd=False keeps the direct implicit GEMM for the ResnetBlock convolutions: both paths compute the same
+    function (each within the parity tolerance of the reference; against each other within the same noise floor)."""
+    cfg, gold, inputs, net = _build("face_bs1_nb4")
+    from wacv23_tsnet_b200.model.TSNet import TSNet
+    ref_net = TSNet(is_train=False, label_nc=cfg["label_nc"], n_blocks=cfg["n_blocks"], n_downsampling=3,
+                    n_source=cfg["n_source"], return_flow=True, winograd=False)
+    for k in ("img_enc", "lbl_enc", "fuse_net", "dec"):
+        getattr(ref_net, k).load_state_dict(getattr(net, k).state_dict())
+    ref_net.eval()
+    with torch.no_grad():
+        _feed(net, inputs)
+        net.forward()
+        _feed(ref_net, inputs)
+        ref_net.forward()
+    g = torch.from_numpy(gold["rec_tar_img"])
+    assert float((ref_net.rec_tar_img.cpu() - g).abs().max()) < IMG_TOL
+    assert float((net.rec_tar_img.cpu() - g).abs().max()) < IMG_TOL
+    assert float((net.rec_tar_img - ref_net.rec_tar_img).abs().max()) < IMG_TOL
+    assert not torch.equal(net.rec_tar_img, ref_net.rec_tar_img)   # the two paths really are different kernels
+
+
+def test_data_writes_need_invalidate_weights():
+    """Writes through `.data` do not bump the tensor version that keys the packed-weight cache: after
+    invalidate_weights() the forward must see the new values."""
+    cfg, gold, inputs, net = _build("quickstart_bs1")
+    _feed(net, inputs)
+    with torch.no_grad():
+        net.forward()
+        a = net.rec_tar_img.clone()
+        p = net.dec.state_dict(keep_vars=True)["map_conv.weight"]
+        p.data.copy_(p.data * 1.5)
+        net.invalidate_weights()
+        net.forward()
+        assert not torch.equal(net.rec_tar_img, a)
 
 
 def test_fast_modes_run_and_are_flagged_non_parity():

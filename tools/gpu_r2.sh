@@ -1,0 +1,41 @@
+#!/bin/bash
+# Round-2 GPU session script (run under gpurun, 1 GPU):  bash tools/gpu_r2.sh <tag> [stages...]
+# stages: tests bench ab launches ncu_wino   (default: all).  Numbers printed under ncu are never bench values.
+TAG=${1:-r2}; shift
+STAGES=${@:-tests bench ab launches ncu_wino}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $OUT/smi_$TAG.txt 2>&1
+FWD="python tools/one_forward.py --forwards 3"
+for st in $STAGES; do
+  case $st in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -x --durations=8 > $OUT/pytest_$TAG.log 2>&1
+      echo "pytest exit $?" >> $OUT/pytest_$TAG.log; tail -15 $OUT/pytest_$TAG.log ;;
+    tests_all)
+      timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $OUT/pytest_$TAG.log 2>&1
+      echo "pytest exit $?" >> $OUT/pytest_$TAG.log; tail -25 $OUT/pytest_$TAG.log ;;
+    bench)
+      timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+      tail -3 $OUT/bench_$TAG.err; cut -c1-600 $OUT/bench_$TAG.json ;;
+    ab)
+      timeout 400 python bench.py --steps 10 --warmup 3 --no-winograd --no-cpu-baseline > $OUT/bench_nowino_$TAG.json 2> $OUT/bench_nowino_$TAG.err
+      cut -c1-300 $OUT/bench_nowino_$TAG.json ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+          --log-file $OUT/launches_$TAG.csv $FWD > /dev/null 2>&1 ;;
+    ncu_wino)
+      # Winograd GEMM (2-CTA kernel; the first conv_gemm2 launches of a forward are the 64->128/128->256 stride-2 convs:
+      # skip into the ResnetBlock region), input and output transform passes
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm2_kernel -s 60 -c 1 \
+          -f -o $OUT/prof_winogemm_$TAG $FWD > /dev/null 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_input_kernel -s 30 -c 1 \
+          -f -o $OUT/prof_winoin_$TAG $FWD > /dev/null 2>&1
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_output_kernel -s 30 -c 1 \
+          -f -o $OUT/prof_winoout_$TAG $FWD > /dev/null 2>&1 ;;
+    ncu_corr)
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:corr_ -s 6 -c 4 \
+          -f -o $OUT/prof_corr_$TAG $FWD > /dev/null 2>&1 ;;
+  esac
+done
+ls -la $OUT | tail -20
