@@ -265,13 +265,36 @@ def run_b200(args):
     net.eval()
     log("model built")
 
-    inp = make_inputs(bs, L, n, seed=1234 + rank, pose=args.pose)
+    from oracle.synth import IMG_MEAN as _MEAN
+    mean4 = np.asarray(_MEAN, dtype=np.float32).reshape(1, 3, 1, 1)
+
+    def rank_inputs(r):
+        """Synthetic batch of rank r.  Frames are 8-bit pixels (what a video decoder delivers); the fp32 tensors the
+        reference's datasets would emit are exactly `u8 - mean`, so the resident run and the end-to-end run process
+        the SAME frames."""
+        d = make_inputs(bs, L, n, seed=1234 + r, pose=args.pose)
+        u8 = [np.clip(np.rint(a + mean4), 0, 255).astype(np.uint8) for a in d["src_img"]]
+        d["src_img"] = [a.astype(np.float32) - mean4 for a in u8]
+        return d, u8
+    inp, src_u8 = rank_inputs(rank)
     host = {k: ([torch.from_numpy(a).pin_memory() for a in v] if isinstance(v, list) else torch.from_numpy(v).pin_memory())
             for k, v in inp.items() if k != "tar_img"}
     devin = {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in host.items()}
-    h2d = sum(t.numel() * t.element_size() for v in host.values() for t in (v if isinstance(v, list) else [v]))
+    # compact host formats for the end-to-end path (SURVEY section 8f row 2): uint8 BGR frames (+ the dataset mean applied
+    # in the stem loader) and uint8 class-index label maps (vl2ch evaluated in the loader); bit-identical forward
+    # (tests/test_parity_gpu.py::test_uint8_images_give_identical_forward..., ::test_classmap_labels_give_identical_forward)
+    host_c = dict(src_img=[torch.from_numpy(a).pin_memory() for a in src_u8],
+                  src_lbl=[torch.from_numpy(a.argmax(1).astype(np.uint8)).pin_memory() for a in inp["src_lbl"]],
+                  src_bbox=host["src_bbox"], tar_lbl=torch.from_numpy(inp["tar_lbl"].argmax(1).astype(np.uint8)).pin_memory(),
+                  tar_bbox=host["tar_bbox"])
+    net.set_image_mean(_MEAN)
+    nbytes = lambda d: sum(t.numel() * t.element_size() for v in d.values() for t in (v if isinstance(v, list) else [v]))
+    h2d_fp32 = nbytes(host)
+    if args.e2e_inputs == "compact":
+        host = host_c
+    h2d = nbytes(host)
     d2h = bs * 3 * 256 * 256 * 4
-    log("inputs staged")
+    log(f"inputs staged (e2e host bytes per step: {h2d}; reference fp32 formats would be {h2d_fp32})")
 
     def step_resident():
         net.set_test_input(devin["src_img"], devin["src_lbl"], devin["src_bbox"], devin["tar_lbl"], devin["tar_bbox"])
@@ -360,7 +383,7 @@ def run_b200(args):
             if rank == 0:
                 theirs = torch.empty_like(mine)
                 tdist.recv(theirs, src=1)
-                inp1 = make_inputs(bs, L, n, seed=1234 + 1, pose=args.pose)
+                inp1, _ = rank_inputs(1)
                 t = lambda a: torch.from_numpy(a[:2]).to(dev)
                 net.set_test_input([t(a) for a in inp1["src_img"]], [t(a) for a in inp1["src_lbl"]],
                                    [t(a) for a in inp1["src_bbox"]], t(inp1["tar_lbl"]), t(inp1["tar_bbox"]))
@@ -501,7 +524,11 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
                         "api": "FramePipeline.run (H2D / forward / D2H of consecutive batches overlapped)"
-                        if args.e2e_mode == "pipelined" else "set_test_input + forward + rec_tar_img.cpu()"},
+                        if args.e2e_mode == "pipelined" else "set_test_input + forward + rec_tar_img.cpu()",
+                        "host_formats": ("uint8 BGR frames + dataset mean, uint8 class-index labels, uint8 bboxes "
+                                         "(bit-identical forward; the reference's fp32 formats would be "
+                                         f"{h2d_fp32 * world} B per step)") if args.e2e_inputs == "compact"
+                        else "fp32 mean-subtracted frames, fp32 one-hot labels, uint8 bboxes (the reference's formats)"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_corr_warp": roof_corr,
                 "kernel_shares": shares, "cpu_baseline": cpu, "torch_cuda_eager_port": eager,
                 "non_parity_speed_point": fast, "shard_check": shard_check}
@@ -549,6 +576,9 @@ def main():
                          " on by default at N=1: BASELINE.md section 3 step 4)")
     ap.add_argument("--no-fast-point", dest="fast_point", action="store_false",
                     help="skip the labelled non-parity single-pass fp16 speed point")
+    ap.add_argument("--e2e-inputs", dest="e2e_inputs", default="compact", choices=["compact", "fp32"],
+                    help="host formats of the end-to-end path: compact = uint8 frames + uint8 class maps (default), "
+                         "fp32 = the reference callers' formats")
     ap.add_argument("--e2e-mode", dest="e2e_mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined: wacv23_tsnet_b200.pipeline.FramePipeline; sync: set_test_input + forward + .cpu()")
     args = ap.parse_args()

@@ -186,11 +186,16 @@ int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* me
  * s = 0..6, the Cin = Cimg + Clbl + 3 channels of source pixel (reflect(yp-3), reflect(x+s-3)).
  * img may be NULL (label encoder).  The image is DIVIDED by img_div (the /255.0 of set_*_input, :268-286;
  * a true division so the rounding matches the reference).
+ * img_kind 0: img = fp32 planes [B, Cimg, H, W] (mean-subtracted BGR in 0..255 units, what the reference's datasets
+ *             emit); img_kind 1: img = uint8 BGR planes [B, 3, H, W] and img_mean3_host = the dataset mean (3 host
+ *             floats): the dataset's `image -= mean` (dataset/dataset_video_face.py:329, :401) moves into the loader,
+ *             (float(u8) - mean_c) / img_div -- 4 x fewer image bytes over PCIe and HBM, bit-identical values.
  * lbl_kind 0: lbl = fp32 one-hot planes [B, Clbl, H, W] (what the reference's callers pass);
  * lbl_kind 1: lbl = uint8 class-index map [B, H, W]; channel c is (lbl == c), i.e. utils/misc.py:50-67 `vl2ch`
  *             evaluated inside the loader -- 4 x Clbl fewer bytes over PCIe and HBM. */
-int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const void* lbl, int Clbl, int lbl_kind, int B,
-                    int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
+int tsnet_stem_taps(const void* img_nchw, int Cimg, int img_kind, const float* img_mean3_host, float img_div,
+                    const void* lbl, int Clbl, int lbl_kind, int B, int H, int W, int Cp, int fmt, float scale,
+                    uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
 
 /* ---- correlation: masks -> class-sorted order, operands, tensor-core tiles, warp + mean -----------------------
  * model/TSNet.py:319-323 (normalise, target mask), :339-366 (per source: normalise, mask, two masked bmm,
@@ -283,11 +288,13 @@ int tsnet_head_conv_tanh(const float* act_nhwc, const float* mean_rstd, int relu
  * demo/demo_face.py:194-199 + sample_img :96-105 (demo_pose.py analogous): per image and channel
  *   y = (x - mean) / std * ref_std + ref_mean      (mean / unbiased std of the generated frame, per channel)
  *   y = clamp(y + img_mean, 0, 1) * 255 ; BGR -> RGB ; uint8 (truncation)
- * rec_nchw [B,3,H,W] fp32 (device); ref_mean3 / ref_std3 device pointers to 3 floats (statistics of the source
- * frames, computed by the caller as in demo_face.py:180-182); img_mean3_host = IMG_MEAN/255 (host pointer);
- * out [B,H,W,3] uint8 RGB (device).  Removes the fp32 D2H + numpy passes per frame. */
-int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* ref_mean3, const float* ref_std3,
-                         const float* img_mean3_host, uint8_t* out_hwc_rgb, void* stream);
+ * rec_nchw [B,3,H,W] fp32 (device); gen_mean_std [B*3, 2] = (mean, unbiased std) of every generated plane from
+ * tsnet_plane_stats(rec_nchw, B*3, H*W, 1, ...) (device); ref_mean3 / ref_std3 device pointers to 3 floats (statistics
+ * of the source frames, computed by the caller as in demo_face.py:180-182); img_mean3_host = IMG_MEAN/255 (host
+ * pointer); out [B,H,W,3] uint8 RGB (device).  Given the same statistics the bytes equal the reference's fp32
+ * arithmetic exactly (tests compare with torch.equal).  Removes the fp32 D2H + numpy passes per frame. */
+int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* gen_mean_std, const float* ref_mean3,
+                         const float* ref_std3, const float* img_mean3_host, uint8_t* out_hwc_rgb, void* stream);
 
 /* ---- train-mode branches inside forward() (forward only) ---------------------------------
  * model/TSNet.py:327-331 (target image statistics), :372-390 (image-space warp: F.unfold(src_img, 8, 8) ->

@@ -369,6 +369,42 @@ def test_classmap_labels_give_identical_forward():
         assert torch.equal(net.rec_tar_img, a)
 
 
+def test_uint8_images_give_identical_forward_and_bad_shapes_raise():
+    """SURVEY section 8f row 2 (remainder): uint8 BGR source images + the dataset mean staged on the device; the
+    loader evaluates (u8 - mean) / 255 (dataset/dataset_video_face.py:329 + model/TSNet.py:286) -> same bits as feeding
+    the mean-subtracted fp32 images.  Mismatched source tensors raise instead of being read out of bounds."""
+    from oracle import synth
+    from wacv23_tsnet_b200.model.TSNet import TSNet
+    torch.manual_seed(4)
+    net = TSNet(is_train=False, label_nc=2, n_blocks=0, n_downsampling=3, n_source=2, img_mean=synth.IMG_MEAN)
+    net.eval()
+    inp = synth.dataset_like_inputs(2, 2, 2, seed=13)
+    t = torch.from_numpy
+    g = torch.Generator().manual_seed(0)
+    u8 = [torch.randint(0, 256, (2, 3, 256, 256), generator=g).to(torch.uint8) for _ in range(2)]
+    mean = torch.tensor(np.asarray(synth.IMG_MEAN, dtype=np.float32)).view(1, 3, 1, 1)
+    f32 = [x.float() - mean for x in u8]                                # what the dataset would have produced
+    with torch.no_grad():
+        net.set_test_input(f32, [t(a) for a in inp["src_lbl"]], [t(a) for a in inp["src_bbox"]], t(inp["tar_lbl"]),
+                           t(inp["tar_bbox"]))
+        net.forward()
+        a = net.rec_tar_img.clone()
+        net.set_test_input(u8, [t(a_) for a_ in inp["src_lbl"]], [t(a_) for a_ in inp["src_bbox"]], t(inp["tar_lbl"]),
+                           t(inp["tar_bbox"]))
+        assert net._src_img_raw[0].dtype == torch.uint8
+        net.forward()
+        assert torch.equal(net.rec_tar_img, a)
+        assert torch.equal(net.src_img_list[1], f32[1].cuda() / 255.0)
+        with pytest.raises(ValueError):
+            net.set_test_input(u8, [t(a_) for a_ in inp["src_lbl"]], [t(a_)[:1] for a_ in inp["src_bbox"]],
+                               t(inp["tar_lbl"]), t(inp["tar_bbox"]))
+            net.forward()
+        with pytest.raises(ValueError):
+            net.set_test_input([x[:, :, :128] for x in u8], [t(a_) for a_ in inp["src_lbl"]],
+                               [t(a_) for a_ in inp["src_bbox"]], t(inp["tar_lbl"]), t(inp["tar_bbox"]))
+            net.forward()
+
+
 def test_use_prev_sources_skip_the_255_division():
     """set_train_input(use_prev=...) (model/TSNet.py:266-276): flagged sources are used as they are, the others /255."""
     from oracle import synth

@@ -33,6 +33,8 @@ for st in $STAGES; do
           -f -o $OUT/prof_winoin_$TAG $FWD > /dev/null 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_output_kernel -s 30 -c 1 \
           -f -o $OUT/prof_winoout_$TAG $FWD > /dev/null 2>&1 ;;
+    winobench)
+      timeout 300 python tools/wino_bench.py > $OUT/winobench_$TAG.log 2>&1; cat $OUT/winobench_$TAG.log ;;
     ncu_corr)
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:corr_ -s 6 -c 4 \
           -f -o $OUT/prof_corr_$TAG $FWD > /dev/null 2>&1 ;;

@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(256, 4) build_taps_up2_kernel(const TapsArgs a
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemTW = 64;
 
-__global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict__ img, int Cimg, float img_div,
+// img_kind: 0 = fp32 planes (mean-subtracted BGR, what the reference's datasets emit); 1 = uint8 BGR planes, the
+// dataset's `image -= mean` (dataset/dataset_video_face.py:329, :401) is then applied here: (float(u8) - mean_c) / 255.
+__global__ void __launch_bounds__(256) stem_taps_kernel(const void* __restrict__ img, int Cimg, int img_kind,
+                                                        float mean0, float mean1, float mean2, float img_div,
                                                         const void* __restrict__ lbl, int Clbl, int lbl_kind, int B,
                                                         int H, int W, int Cp, int fmt, float scale,
                                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
@@ -379,7 +382,13 @@ __global__ void __launch_bounds__(256) stem_taps_kernel(const float* __restrict_
     const int xs = reflect_idx(xt + k - 3, W);
     float v;
     if (c < Cimg) {
-      v = __fdiv_rn(img[(static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs], img_div);
+      const size_t off = (static_cast<size_t>(b) * Cimg + c) * plane + static_cast<size_t>(ys) * W + xs;
+      if (img_kind == 0) {
+        v = __fdiv_rn(static_cast<const float*>(img)[off], img_div);
+      } else {
+        const float mc = c == 0 ? mean0 : (c == 1 ? mean1 : mean2);
+        v = __fdiv_rn(__fadd_rn(static_cast<float>(static_cast<const uint8_t*>(img)[off]), -mc), img_div);
+      }
     } else if (c < Cimg + Clbl) {
       if (lbl_kind == 0)
         v = static_cast<const float*>(lbl)[(static_cast<size_t>(b) * Clbl + (c - Cimg)) * plane +
@@ -557,48 +566,25 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
 // demo post-processing (demo/demo_face.py:96-105, 194-199): per image and channel, re-normalise the generated frame
 // to the reference statistics of the source video, add the dataset mean, clamp, x255, BGR -> RGB, uint8.
 //   y = (x - mean_c) / std_c * ref_std_c + ref_mean_c ;  y = clamp(y + img_mean_c, 0, 1) * 255 ;  out[.., 2 - c] = (u8) y
-// std is the unbiased torch.std.  One block per (image, channel); two-pass statistics in fp32 + block reduction.
+// mean / std (unbiased, torch.std) of the generated frame come from tsnet_plane_stats (fp64, fixed order): given the
+// same statistics the byte output equals the reference's fp32 arithmetic bit for bit (every operation individually
+// rounded, truncating uint8 conversion).  grid = (pixel chunks, 3, B).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) postprocess_u8_kernel(const float* __restrict__ x, int HW,
+__global__ void __launch_bounds__(256) postprocess_u8_kernel(const float* __restrict__ x, int HW,
+                                                             const float* __restrict__ gen_mean_std,
                                                              const float* __restrict__ ref_mean,
                                                              const float* __restrict__ ref_std, float m0, float m1,
                                                              float m2, uint8_t* __restrict__ out) {
-  __shared__ float s_red[16];
-  __shared__ float s_bcast;
-  const int c = blockIdx.x, b = blockIdx.y;
+  const int c = blockIdx.y, b = blockIdx.z;
   const float* p = x + (static_cast<size_t>(b) * 3 + c) * HW;
-  auto block_sum = [&](float v) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
-#pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (threadIdx.x == 0) s_bcast = t;
-    }
-    __syncthreads();
-    const float r = s_bcast;
-    __syncthreads();
-    return r;
-  };
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += p[i];
-  const float mean = block_sum(acc) / static_cast<float>(HW);
-  acc = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float d = p[i] - mean;
-    acc = fmaf(d, d, acc);
-  }
-  const float stdv = sqrtf(block_sum(acc) / static_cast<float>(HW - 1));
+  const float mean = gen_mean_std[(b * 3 + c) * 2], stdv = gen_mean_std[(b * 3 + c) * 2 + 1];
   const float rs = ref_std[c], rm = ref_mean[c];
   const float im = c == 0 ? m0 : (c == 1 ? m1 : m2);
   uint8_t* o = out + static_cast<size_t>(b) * HW * 3 + (2 - c);
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     float y = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(p[i], -mean), stdv), rs), rm);
     y = __fadd_rn(y, im);
-    y = fminf(fmaxf(y, 0.f), 1.f) * 255.f;
+    y = __fmul_rn(fminf(fmaxf(y, 0.f), 1.f), 255.f);
     o[static_cast<size_t>(i) * 3] = static_cast<uint8_t>(y);  // astype('uint8'): truncation
   }
 }
@@ -746,19 +732,23 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   return 0;
 }
 
-extern "C" int tsnet_stem_taps(const float* img_nchw, int Cimg, float img_div, const void* lbl, int Clbl,
-                               int lbl_kind, int B, int H, int W, int Cp, int fmt, float scale, uint16_t* taps_hi,
-                               uint16_t* taps_lo, void* stream) {
+extern "C" int tsnet_stem_taps(const void* img_nchw, int Cimg, int img_kind, const float* img_mean3_host,
+                               float img_div, const void* lbl, int Clbl, int lbl_kind, int B, int H, int W, int Cp,
+                               int fmt, float scale, uint16_t* taps_hi, uint16_t* taps_lo, void* stream) {
   TSNET_ARG_CHECK(lbl && taps_hi && taps_lo, "stem_taps: null argument");
   TSNET_ARG_CHECK((img_nchw != nullptr) == (Cimg > 0), "stem_taps: img pointer / Cimg mismatch");
+  TSNET_ARG_CHECK(img_kind == 0 || (img_kind == 1 && Cimg == 3 && img_mean3_host),
+                  "stem_taps: img_kind %d (uint8 images need Cimg == 3 and a host pointer to the 3 channel means)", img_kind);
   TSNET_ARG_CHECK(lbl_kind == 0 || lbl_kind == 1, "stem_taps: lbl_kind %d", lbl_kind);
   TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= 7 * (Cimg + Clbl + 3) && Cp <= 1024, "stem_taps: Cp %d out of range", Cp);
   TSNET_ARG_CHECK(Cimg + Clbl + 3 <= 127, "stem_taps: too many input channels");
   TSNET_ARG_CHECK(W % kStemTW == 0 && W >= 4 && H >= 4, "stem_taps: W %d must be a multiple of %d", W, kStemTW);
   dim3 grid(W / kStemTW, H + 6, B);
   const size_t smem = static_cast<size_t>(Cimg + Clbl + 3) * (kStemTW + 6) * sizeof(float);
+  const float m0 = img_kind == 1 ? img_mean3_host[0] : 0.f, m1 = img_kind == 1 ? img_mean3_host[1] : 0.f,
+              m2 = img_kind == 1 ? img_mean3_host[2] : 0.f;
   stem_taps_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      img_nchw, Cimg, img_div == 0.f ? 1.f : img_div, lbl, Clbl, lbl_kind, B, H, W, Cp, fmt,
+      img_nchw, Cimg, img_kind, m0, m1, m2, img_div == 0.f ? 1.f : img_div, lbl, Clbl, lbl_kind, B, H, W, Cp, fmt,
       scale == 0.f ? 1.f : scale, taps_hi, taps_lo);
   TSNET_LAUNCH_CHECK();
   return 0;
@@ -791,14 +781,17 @@ extern "C" int tsnet_head_conv_tanh(const float* act_nhwc, const float* mean_rst
   return 0;
 }
 
-extern "C" int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* ref_mean3,
-                                    const float* ref_std3, const float* img_mean3_host, uint8_t* out_hwc_rgb,
-                                    void* stream) {
-  TSNET_ARG_CHECK(rec_nchw && ref_mean3 && ref_std3 && img_mean3_host && out_hwc_rgb, "postprocess_u8: null argument");
+extern "C" int tsnet_postprocess_u8(const float* rec_nchw, int B, int H, int W, const float* gen_mean_std,
+                                    const float* ref_mean3, const float* ref_std3, const float* img_mean3_host,
+                                    uint8_t* out_hwc_rgb, void* stream) {
+  TSNET_ARG_CHECK(rec_nchw && gen_mean_std && ref_mean3 && ref_std3 && img_mean3_host && out_hwc_rgb,
+                  "postprocess_u8: null argument");
   TSNET_ARG_CHECK(H * W >= 2, "postprocess_u8: image too small");
-  dim3 grid(3, B);
-  postprocess_u8_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-      rec_nchw, H * W, ref_mean3, ref_std3, img_mean3_host[0], img_mean3_host[1], img_mean3_host[2], out_hwc_rgb);
+  const int chunks = (H * W + 256 * 8 - 1) / (256 * 8);
+  dim3 grid(chunks, 3, B);
+  postprocess_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rec_nchw, H * W, gen_mean_std, ref_mean3, ref_std3, img_mean3_host[0], img_mean3_host[1], img_mean3_host[2],
+      out_hwc_rgb);
   TSNET_LAUNCH_CHECK();
   return 0;
 }

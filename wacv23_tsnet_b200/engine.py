@@ -137,14 +137,14 @@ class ForwardEngine:
         return self._conv_in(t1, (net, prefix + "conv_block.5"), "3x3", B, H, W, tmode_out, residual=x_res,
                              need_act=need_act, want_taps=want_taps)
 
-    def _encoder(self, net, img, img_div, lbl, n_blocks, final_tmode=None):
+    def _encoder(self, net, img, img_div, lbl, n_blocks, final_tmode=None, img_mean=None):
         """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it in
         final_tmode or None).  For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the
         residual stream."""
         m = self.mode
         X, H, W = lbl.shape[0], lbl.shape[-2], lbl.shape[-1]
         pc = self._pack(net, "model.1", fold_kw=True)
-        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc)
+        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc, img_mean=img_mean)
         y, mr = self._conv(t, pc, "7x1", X, H, W)
         for k, idx in enumerate((4, 7)):
             t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
@@ -168,7 +168,7 @@ class ForwardEngine:
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
     def forward(self, src_imgs, img_divs, src_lbls, src_bboxes, tar_lbl, tar_bbox, return_flow=False,
-                pose_fill=None, collect=None, train=None):
+                pose_fill=None, collect=None, train=None, img_mean=None):
         """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (labels may instead be
         uint8 class-index maps [B,256,256]: vl2ch is then evaluated inside the stem loader; images NOT yet /255:
         img_divs[i] is the divisor set_*_input would have applied: 255, or 1 for use_prev sources); src_bboxes / tar_bbox: [B,256,256] uint8|fp32.
@@ -186,6 +186,28 @@ class ForwardEngine:
         hw = h * w
 
         # ---- encoders.  The last img_enc block writes the operand of FuseNet's first conv (source half) directly.
+        # ---- argument validation (a mismatched source would otherwise be read out of bounds on the device)
+        if not (len(img_divs) == len(src_lbls) == len(src_bboxes) == n and n >= 1):
+            raise ValueError(f"forward: {n} source images but {len(src_lbls)} labels / {len(src_bboxes)} bboxes")
+        for i in range(n):
+            if src_imgs[i].shape != (B, 3, H0, W0):
+                raise ValueError(f"forward: source image {i} has shape {tuple(src_imgs[i].shape)}, expected {(B, 3, H0, W0)}")
+            if (src_lbls[i].shape[0] != B or src_lbls[i].shape[-2:] != (H0, W0) or
+                    src_lbls[i].dtype != src_lbls[0].dtype or src_lbls[i].shape != src_lbls[0].shape):
+                raise ValueError(f"forward: source label {i} {tuple(src_lbls[i].shape)} / {src_lbls[i].dtype} does not "
+                                 f"match batch {B}, size {(H0, W0)} or the format of source label 0")
+            if src_bboxes[i].shape != tar_bbox.shape or src_bboxes[i].dtype != tar_bbox.dtype:
+                raise ValueError(f"forward: source bbox {i} {tuple(src_bboxes[i].shape)} / {src_bboxes[i].dtype} does not "
+                                 f"match the target bbox {tuple(tar_bbox.shape)} / {tar_bbox.dtype}")
+        if tar_bbox.shape[0] != B:
+            raise ValueError("forward: target bbox batch size differs from the target label's")
+        if src_imgs[0].dtype == torch.uint8 and (img_mean is None or len(set(img_divs)) > 1):
+            if img_mean is None:
+                raise ValueError("forward: uint8 source images need img_mean")
+            mean_t = torch.tensor(img_mean, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+            src_imgs, img_mean = [im.float() - mean_t for im in src_imgs], None
+        if src_imgs[0].dtype != torch.uint8:
+            img_mean = None
         if n > 1 and len(set(img_divs)) > 1:
             # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
             src_imgs = [im if dv == 1.0 else im / dv for im, dv in zip(src_imgs, img_divs)]
@@ -193,7 +215,8 @@ class ForwardEngine:
         img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
         lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
         src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]), lbl_cat.contiguous(),
-                                           9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf))  # [n*B, h, w, 512]
+                                           9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf),
+                                           img_mean=img_mean)                              # [n*B, h, w, 512]
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
         # ---- transformation branch (model/TSNet.py:319-366, 392)

@@ -66,8 +66,8 @@ _SIGNATURES = {
     "tsnet_wino_output": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_longlong, vp, vp, vp]),
     "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
-    "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_float, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                  C.c_int, C.c_float, vp, vp, vp]),
+    "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, vp, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
     "tsnet_l2norm_split": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp]),
     "tsnet_corr_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
     "tsnet_corr_prepare": (C.c_int, [C.POINTER(CorrDesc), vp, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
@@ -86,7 +86,7 @@ _SIGNATURES = {
     "tsnet_plane_stats": (C.c_int, [vp, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_head_conv_tanh": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                        C.POINTER(C.c_float), vp, vp]),
-    "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_float), vp, vp]),
+    "tsnet_postprocess_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_float), vp, vp]),
     "tsnet_direct_conv_fp32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, vp, vp]),
 }

@@ -91,7 +91,8 @@ class TSNet(nn.Module):
                  is_train=True, getIntermFeat=True, label_nc=5,
                  debug=False, lambda_dec=1.0,
                  addcoords=True,
-                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False, winograd=True):
+                 ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False, winograd=True,
+                 img_mean=None):
         super().__init__()
         # is_train=True: forward-only.  The generator is built exactly as for is_train=False (no discriminators, VGG,
         # optimizers -- SURVEY section 8f row 3); forward() then also runs the reference's train-mode branches
@@ -117,6 +118,10 @@ class TSNet(nn.Module):
         self._engine = ForwardEngine(self.img_enc, self.lbl_enc, self.fuse_net, self.dec, label_nc, n_blocks,
                                      n_downsampling=n_downsampling, ngf=ngf, math_mode=math_mode, winograd=winograd)
         self._pose_fill = None
+        # extension: uint8 BGR source images may be staged as they come out of the decoder /
+        # image file; the dataset's `image -= mean` (dataset/dataset_video_face.py:329, :401) is then evaluated inside
+        # the stem loader kernel with this mean (3 floats, BGR order)
+        self.img_mean = None if img_mean is None else tuple(float(v) for v in img_mean)
         self._use_graph = bool(cuda_graph)
         self._graphs = {}
         self._src_img_raw, self._src_img_div = None, None
@@ -140,6 +145,22 @@ class TSNet(nn.Module):
         t = t.cuda()
         return t if t.dtype == torch.float32 else t.float()
 
+    def set_image_mean(self, mean):
+        """Dataset mean (3 floats, BGR) used when source images are passed as uint8 tensors."""
+        self.img_mean = None if mean is None else tuple(float(v) for v in mean)
+
+    def _img(self, t, keep_u8=True):
+        """Source image: fp32 mean-subtracted BGR (what the reference's datasets emit), or uint8 BGR [B,3,H,W] when an
+        image mean is known -- kept as uint8 on the device (4 x fewer bytes), `(u8 - mean) / 255` happens in the loader."""
+        t = t.cuda()
+        if t.dtype == torch.uint8:
+            if self.img_mean is None:
+                raise ValueError("uint8 source images need the dataset mean: TSNet(..., img_mean=...) or set_image_mean()")
+            if keep_u8:
+                return t.contiguous()
+            return t.float() - torch.tensor(self.img_mean, dtype=torch.float32, device=t.device).view(1, 3, 1, 1)
+        return t if t.dtype == torch.float32 else t.float()
+
     @staticmethod
     def _lbl(t):
         """Labels: fp32 one-hot planes [B, L, H, W] as the reference's callers pass them, or (extension, SURVEY
@@ -161,10 +182,11 @@ class TSNet(nn.Module):
         the kernels read the raw images and divide on the fly."""
         if self._src_img_raw is None:
             return None
-        return [x if d == 1.0 else x / d for x, d in zip(self._src_img_raw, self._src_img_div)]
+        return [x if d == 1.0 else x / d
+                for x, d in zip([self._img(x, keep_u8=False) for x in self._src_img_raw], self._src_img_div)]
 
     def set_train_input(self, src_img_list, src_lbl_list, src_bbox_list, tar_img, tar_lbl, tar_bbox, use_prev=None):
-        self._src_img_raw = [self._f32(x) for x in src_img_list]
+        self._src_img_raw = [self._img(x, keep_u8=False) for x in src_img_list]
         self._src_img_div = [1.0 if (use_prev is not None and use_prev[i]) else 255.0
                              for i in range(len(self._src_img_raw))]
         self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
@@ -177,7 +199,7 @@ class TSNet(nn.Module):
     def set_test_input(self, src_img_list, src_lbl_list, src_bbox_list,
                        tar_lbl, tar_bbox,
                        prev_tar_img=None, prev_tar_lbl=None, prev_tar_bbox=None):
-        self._src_img_raw = [self._f32(x) for x in src_img_list]
+        self._src_img_raw = [self._img(x) for x in src_img_list]
         self._src_img_div = [255.0] * len(self._src_img_raw)
         self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
         self.src_bbox_list = [self._mask(x).unsqueeze(dim=1) for x in src_bbox_list]
@@ -227,7 +249,8 @@ class TSNet(nn.Module):
                      for p in net.parameters())
 
     def _forward_graph(self, imgs, divs, lbls, bbs, tar_lbl, tar_bbox):
-        key = (tuple(tar_lbl.shape), len(imgs), tuple(divs), tar_bbox.dtype, self.return_flow, self._param_signature())
+        key = (tuple(tar_lbl.shape), len(imgs), tuple(divs), tar_bbox.dtype, imgs[0].dtype, lbls[0].dtype,
+               self.return_flow, self._param_signature())
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs.clear()  # one live graph: its private pool holds every workspace of the forward
@@ -237,7 +260,7 @@ class TSNet(nn.Module):
             def run():
                 return self._engine.forward(static["imgs"], divs, static["lbls"], static["bbs"], static["tar_lbl"],
                                             static["tar_bbox"], return_flow=self.return_flow,
-                                            pose_fill=self._pose_fill)
+                                            pose_fill=self._pose_fill, img_mean=self.img_mean)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -263,7 +286,8 @@ class TSNet(nn.Module):
                 raise RuntimeError("is_train=True forward needs set_train_input (the target image)")
             train = {"tar_img": self._tar_img_raw, "align": self._pose_fill is None}
             rec, grids = self._engine.forward(imgs, divs, lbls, bbs, tar_lbl, tar_bbox, return_flow=True,
-                                              pose_fill=self._pose_fill, collect=_collect, train=train)
+                                              pose_fill=self._pose_fill, collect=_collect, train=train,
+                                              img_mean=self.img_mean)
             self.warp_src_img_list = [train["warp"][i] for i in range(len(imgs))]
             self.loss_warp = train["losses"][0]
             if self._pose_fill is None:
@@ -273,7 +297,7 @@ class TSNet(nn.Module):
                 rec, grids = self._forward_graph(imgs, divs, lbls, bbs, tar_lbl, tar_bbox)
         else:
             rec, grids = self._engine.forward(imgs, divs, lbls, bbs, tar_lbl, tar_bbox, return_flow=self.return_flow,
-                                              pose_fill=self._pose_fill, collect=_collect)
+                                              pose_fill=self._pose_fill, collect=_collect, img_mean=self.img_mean)
         self.rec_tar_img = rec
         if self.return_flow:
             self.warp_grid2d_list = grids

@@ -24,7 +24,8 @@ class TSNet(_face.TSNet):
                          lambda_VGG=lambda_VGG, lambda_CON=lambda_CON, lambda_GRAD=lambda_GRAD, is_train=is_train,
                          getIntermFeat=getIntermFeat, label_nc=label_nc, debug=debug, lambda_dec=lambda_dec,
                          addcoords=addcoords, ngf=ngf, n_downsampling=n_downsampling, return_flow=False,
-                         math_mode=math_mode, cuda_graph=cuda_graph, winograd=winograd)
+                         math_mode=math_mode, cuda_graph=cuda_graph, winograd=winograd,
+                         img_mean=np.asarray(mean, dtype=np.float32))
         self.model_names = ['G', 'D', 'DF']
         self.use_mask = use_mask
         if self.use_mask:

@@ -323,21 +323,30 @@ def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_
     return hi, lo, (planes, Hd, Wd)
 
 
-def stem_taps(img, img_div, lbl, Cp, mode, label_nc=None):
-    """img [B,3,H,W] fp32 NCHW or None (divided by img_div in the kernel); lbl [B,L,H,W] fp32 one-hot planes, or a
-    uint8 class-index map [B,H,W] together with label_nc.  Returns (hi, lo, geom) of the kw-folded tap source."""
+def stem_taps(img, img_div, lbl, Cp, mode, label_nc=None, img_mean=None):
+    """img [B,3,H,W] NCHW or None: fp32 (divided by img_div in the kernel) or uint8 BGR together with img_mean (3 floats:
+    (u8 - mean) / img_div is evaluated in the loader); lbl [B,L,H,W] fp32 one-hot planes, or a uint8 class-index map
+    [B,H,W] together with label_nc.  Returns (hi, lo, geom) of the kw-folded tap source."""
     if lbl.dtype == torch.uint8:
         assert lbl.dim() == 3 and label_nc is not None and lbl.is_contiguous()
         (B, H, W), Clbl, kind = lbl.shape, label_nc, 1
     else:
         (B, Clbl, H, W), kind = _f32(lbl).shape, 0
-    Cimg = 0 if img is None else img.shape[1]
+    Cimg, img_kind, mean3 = 0, 0, None
+    if img is not None:
+        Cimg = img.shape[1]
+        assert img.is_cuda and img.is_contiguous()
+        if img.dtype == torch.uint8:
+            assert img_mean is not None and Cimg == 3, "uint8 images need the 3 channel means"
+            img_kind, mean3 = 1, (C.c_float * 3)(*[float(v) for v in img_mean])
+        else:
+            _f32(img)
     hi = torch.empty((B, H + 6, W, Cp), dtype=torch.int16, device=lbl.device)
     lo = torch.empty_like(hi)
     with _Prof(("stem_taps",)):
-        L.check(L.load().tsnet_stem_taps(_ptr(None if img is None else _f32(img)), Cimg, C.c_float(img_div),
-                                         _ptr(lbl), Clbl, kind, B, H, W, Cp, mode.fmt, C.c_float(mode.act_scale),
-                                         _ptr(hi), _ptr(lo), _stream()))
+        L.check(L.load().tsnet_stem_taps(_ptr(img), Cimg, img_kind, mean3, C.c_float(img_div), _ptr(lbl), Clbl, kind,
+                                         B, H, W, Cp, mode.fmt, C.c_float(mode.act_scale), _ptr(hi), _ptr(lo),
+                                         _stream()))
     _count()
     return hi, lo, (1, H + 6, W)
 
@@ -503,16 +512,29 @@ def head_conv_tanh(act, weight, bias, fore=None, fill=None, mean_rstd=None, relu
     return out
 
 
-def postprocess_u8(rec, ref_mean, ref_std, img_mean):
+def plane_stats(x, planes, n, div=1.0):
+    """(mean, unbiased std) of x / div over each of `planes` contiguous runs of n floats -> fp32 [planes, 2]
+    (tensor.mean / tensor.std of the reference, fp64 accumulation in a fixed order)."""
+    out = torch.empty((planes, 2), dtype=torch.float32, device=x.device)
+    with _Prof(("plane_stats",)):
+        L.check(L.load().tsnet_plane_stats(_ptr(_f32(x)), planes, n, C.c_float(div), _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def postprocess_u8(rec, ref_mean, ref_std, img_mean, gen_stats=None):
     """rec fp32 NCHW [B,3,H,W] -> uint8 RGB [B,H,W,3]: the demos' colour re-normalisation + sample_img
-    (demo/demo_face.py:96-105, 194-199) in one kernel.  ref_mean / ref_std: CUDA tensors with 3 floats;
-    img_mean: 3 python floats (IMG_MEAN / 255)."""
+    (demo/demo_face.py:96-105, 194-199).  ref_mean / ref_std: CUDA tensors with 3 floats; img_mean: 3 python floats
+    (IMG_MEAN / 255); gen_stats: [B*3, 2] statistics of the generated planes (default: tsnet_plane_stats of rec)."""
     B, _, H, W = rec.shape
+    if gen_stats is None:
+        gen_stats = plane_stats(rec, B * 3, H * W)
     out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=rec.device)
     im = (C.c_float * 3)(*[float(v) for v in img_mean])
     with _Prof(("postprocess_u8",)):
-        L.check(L.load().tsnet_postprocess_u8(_ptr(_f32(rec)), B, H, W, _ptr(_f32(ref_mean.reshape(3))),
-                                              _ptr(_f32(ref_std.reshape(3))), im, _ptr(out), _stream()))
+        L.check(L.load().tsnet_postprocess_u8(_ptr(_f32(rec)), B, H, W, _ptr(_f32(gen_stats)),
+                                              _ptr(_f32(ref_mean.reshape(3))), _ptr(_f32(ref_std.reshape(3))), im,
+                                              _ptr(out), _stream()))
     _count()
     return out
 
