@@ -434,15 +434,17 @@ def run_b200(args):
         if kname == "wino_gemm":
             # the whole Winograd convolution layer = input transform pass + batched GEMM + output transform pass
             n_l = c / args.steps
-            t_in = sum(v[0] for k, v in kern.items() if k[0] == "build_taps" and k[1] == 4) / args.steps
-            n_in = sum(v[1] for k, v in kern.items() if k[0] == "build_taps" and k[1] == 4) / args.steps
-            t_out = kern.get(("wino_output",), (0.0, 1))[0] / args.steps
-            n_out = kern.get(("wino_output",), (0.0, 1))[1] / args.steps
-            layer_ms = t / c + (t_in / n_in if n_in else 0.0) + (t_out / n_out if n_out else 0.0)
+            # transform passes of ALL Winograd layers of the step (fused bridge passes, or separate input / output
+            # passes at the edges of a Winograd chain), spread over the Winograd GEMM launches of the step
+            t_pass = sum(v[0] for k, v in kern.items()
+                         if (k[0] == "build_taps" and k[1] == 4) or k[0] in ("wino_output", "wino_bridge")) / args.steps
+            n_gemm = sum(v[1] for k, v in kern.items() if k[0] == "wino_gemm") / args.steps
+            layer_ms = t / c + t_pass / n_gemm
             roof["winograd_layer"] = {
-                "what": "per 3x3 conv layer of this shape: GEMM launch + mean input-transform pass + mean output-"
-                        "transform pass (the passes are averaged over all Winograd layers of the step)",
-                "ms": layer_ms, "gemm_ms": t / c, "launches_per_step": n_l,
+                "what": "per 3x3 conv layer of this shape: GEMM launch + the transform passes of the step (bridge = output"
+                        " transform + InstanceNorm + input transform in one pass; separate passes at the chain edges) "
+                        "averaged over all Winograd GEMM launches of the step",
+                "ms": layer_ms, "gemm_ms": t / c, "passes_ms_per_layer": t_pass / n_gemm, "launches_per_step": n_l,
                 "conv_equivalent_tflops": conv_flops / (layer_ms * 1e-3) / 1e12,
                 "conv_equivalent_frac_of_peak": conv_flops / (layer_ms * 1e-3) / 1e12 / peak}
         chain = ("corr_prepare", "l2norm_split", "corr_tiles", "corr_finish")
@@ -519,7 +521,7 @@ def run_b200(args):
                 "config": {"workload": f"{'Youtube-dance (pose)' if args.pose else 'FaceForensics'} config: bs={bs}/GPU, 256x256, label_nc={L}, n_source={n}, "
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
-                           "math_mode": args.math, "winograd_f2x2_3x3": bool(args.winograd),
+                           "math_mode": args.math, "winograd_f2x2_3x3": (args.winograd if isinstance(args.winograd, str) else bool(args.winograd)),
                            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
@@ -568,8 +570,10 @@ def main():
     ap.add_argument("--math", default="fp16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"],
                     help="fp16x3 is the parity-grade default; single-pass modes are non-parity speed points")
     ap.add_argument("--pose", action="store_true", help="TSNet_pose, label_nc=25 (BASELINE.json config 3)")
-    ap.add_argument("--no-winograd", dest="winograd", action="store_false",
+    ap.add_argument("--no-winograd", dest="winograd", action="store_const", const=False, default=True,
                     help="direct implicit GEMM for the ResnetBlock convolutions (A/B against the Winograd default)")
+    ap.add_argument("--winograd-unfused", dest="winograd", action="store_const", const="unfused",
+                    help="Winograd with separate transform passes instead of the fused bridge pass (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-cuda-baseline", dest="torch_cuda_baseline", action="store_false",
                     help="skip timing the reference's torch op sequence eagerly on the GPU (cuDNN / cuBLAS, bs = --batch;"

@@ -147,6 +147,25 @@ int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t* v_hi, con
 int tsnet_wino_output(const float* m, int B, int H, int W, int C, const float* bias, const float* addend,
                       long long addend_rows, float* y_raw, float* stats_partial, void* stream);
 
+/* Bridge between two consecutive Winograd layers (conv -> InstanceNorm -> [ReLU | + x] -> ReflectionPad2d -> conv,
+ * model/TSNet.py:25-48): output transform of layer k (+ bias, + addend), InstanceNorm statistics (fp64, fixed order,
+ * CTA-local: one CTA = one image x 32 channels held in shared memory), normalisation, ReLU / residual, optional fp32
+ * act_out, and the input transform of layer k+1 in ONE pass: M is read once, the next V is written once; y_raw,
+ * stats_partial, tsnet_instnorm_reduce and the separate tsnet_build_taps pass of that layer boundary disappear.
+ * mean_rstd_out (optional, [B, C, 2]) receives the statistics. */
+typedef struct {
+  int B, H, W, C;
+  int relu;
+  int Cp_total, c_off;          /* destination operand planes [B, 16, H/2, W/2, Cp_total], channel window [c_off, +C) */
+  int fmt;
+  float scale, eps;             /* operand pre-scale (power of two); InstanceNorm eps (0 = 1e-5) */
+  int act_C_total, act_c_off;   /* act_out channel window (0 = C) */
+  long long addend_rows;
+} tsnet_wino_bridge_desc;
+int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m, const float* bias, const float* addend,
+                      const float* residual, float* act_out, float* mean_rstd_out, uint16_t* v_hi, uint16_t* v_lo,
+                      void* stream);
+
 /* ---- InstanceNorm statistics -----------------------------------------------------------------
  * nn.InstanceNorm2d(affine=False, eps=1e-5, biased variance): model/TSNet.py:28,43,66,71,149.
  * partial [B*HW/32, C, 2] -> mean_rstd [B, C, 2]; fixed-order (deterministic) Chan merge in fp64. */

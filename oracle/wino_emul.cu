@@ -32,3 +32,28 @@ extern "C" void wino_emul_output(const float* m, const float* bias, const float*
   for (int blk = 0; blk < blocks; ++blk)
     for (int t = 0; t < nthreads; ++t) wino_output_body(a, blk, t, nthreads);
 }
+
+extern "C" void wino_emul_bridge(const float* m, const float* bias, const float* addend, long long addend_rows,
+                                 const float* residual, float* act_out, float* mean_rstd_out, uint16_t* hi, uint16_t* lo,
+                                 int B, int H, int W, int C, int relu, int Cp_total, int c_off, int fmt, int act_C_total,
+                                 int act_c_off, float scale, float eps, int nthreads) {
+  WinoBridgeArgs a;
+  a.m = m; a.bias = bias; a.addend = addend; a.residual = residual; a.act_out = act_out; a.mean_rstd_out = mean_rstd_out;
+  a.hi = hi; a.lo = lo; a.B = B; a.H = H; a.W = W; a.C = C; a.relu = relu; a.Cp_total = Cp_total; a.c_off = c_off;
+  a.fmt = fmt; a.act_C_total = act_C_total; a.act_c_off = act_c_off; a.addend_rows = addend_rows; a.scale = scale;
+  a.eps = eps;
+  const size_t bytes = wino_bridge_smem_bytes(H, W, nthreads);
+  uint8_t* smem = new uint8_t[bytes + 16];
+  float* s_y = reinterpret_cast<float*>(smem);
+  double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(H) * W * kBridgeCS * 4);
+  float* s_mr = reinterpret_cast<float*>(s_part + (nthreads / kBridgeCS) * kBridgeCS * 2);
+  const int blocks = B * (C / kBridgeCS);
+  for (int blk = 0; blk < blocks; ++blk) {   // phases separated by block-wide barriers in the kernel
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_a(a, blk, t, nthreads, s_y);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s1(a, t, nthreads, s_y, s_part);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s2(a, blk, t, nthreads, s_part, s_mr);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_b(a, blk, t, nthreads, s_y, s_mr);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_c(a, blk, t, nthreads, s_y);
+  }
+  delete[] smem;
+}

@@ -686,3 +686,47 @@ def test_wino_passes_equal_host_emulation():
     torch.cuda.synchronize()
     assert torch.equal(y_g.cpu(), y_c)
     assert _relerr(st_g.cpu(), st_c) < 1e-6
+
+
+@pytest.mark.parametrize("relu,with_res,with_addend", [(True, False, False), (False, True, False), (True, False, True)])
+def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
+    """tsnet_wino_bridge (output transform + InstanceNorm + ReLU / residual + input transform in one pass, statistics
+    CTA-local in fp64) against the separate passes tsnet_wino_output -> tsnet_instnorm_reduce -> tsnet_build_taps(WINO)."""
+    from wacv23_tsnet_b200 import lib as L, ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(15)
+    B, Cin, Cout = 3, 128, 256
+    x = torch.randn(B, 32, 32, Cin, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.05
+    b = torch.randn(Cout, device="cuda")
+    res = torch.randn(B, 32, 32, Cout, device="cuda") if with_res else None
+    addend = torch.randn(1, 32, 32, Cout, device="cuda") if with_addend else None
+    pw = ops.PackedWino(w, b, m)
+    taps = ops.build_taps(x, m, L.TAPS_WINO)
+    mbuf = ops.wino_gemm(taps, pw, B, 32, 32, m, m.act_scale)
+    # separate passes
+    y, stats = ops.wino_output(mbuf, pw, B, 32, 32, addend=addend)
+    mr = ops.instnorm_reduce(stats, B, 1024, Cout)
+    act_s = torch.zeros(B, 32, 32, Cout, device="cuda")
+    hs, ls, _ = ops.build_taps(y, m, L.TAPS_WINO, mean_rstd=mr, relu=relu, residual=res, act_out=act_s)
+    # fused bridge
+    act_f = torch.zeros(B, 32, 32, Cout + 64, device="cuda")
+    mr_f = torch.zeros(B, Cout, 2, device="cuda")
+    hf = torch.zeros(B * 16, 16, 16, Cout + 64, dtype=torch.int16, device="cuda")
+    lf = torch.zeros_like(hf)
+    ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, act_out=act_f, act_c_off=64,
+                    taps=(hf, lf), c_off=64, mean_rstd_out=mr_f)
+    torch.cuda.synchronize()
+    assert _relerr(mr_f[..., 0], mr[..., 0]) < 1e-5 and _relerr(mr_f[..., 1], mr[..., 1]) < 1e-5
+    assert _relerr(act_f[..., 64:], act_s) < 2e-6 and float(act_f[..., :64].abs().max()) == 0.0
+    assert _relerr(_recon(hf, lf, m.fmt)[..., 64:], _recon(hs, ls, m.fmt)) < 4e-6
+    assert int(hf[..., :64].abs().max()) == 0
+    # deterministic, and a sample does not depend on the batch it rides in
+    h2, l2, _ = ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res)
+    t1 = ops.build_taps(x[1:2].contiguous(), m, L.TAPS_WINO)
+    m1 = ops.wino_gemm(t1, pw, 1, 32, 32, m, m.act_scale)
+    h1, l1, _ = ops.wino_bridge(m1, pw, 1, 32, 32, m, relu=relu, addend=addend,
+                                residual=None if res is None else res[1:2].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(h2[16:32], h1) and torch.equal(l2[16:32], l1)
+    assert torch.equal(h2, hf[..., 64:]) and torch.equal(l2, lf[..., 64:])

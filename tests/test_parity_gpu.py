@@ -206,13 +206,15 @@ def test_bs32_rows_match_the_oracle():
         assert float((grids[:, r:r + 1] - torch.stack(ref["grids"])).abs().max()) < GRID_TOL, r
 
 
-def test_direct_and_winograd_paths_agree():
-    """winograd=False keeps the direct implicit GEMM for the ResnetBlock convolutions: both paths compute the same
-    function (each within the parity tolerance of the reference; against each other within the same noise floor)."""
+@pytest.mark.parametrize("variant", [False, "unfused"])
+def test_direct_and_winograd_paths_agree(variant):
+    """winograd=False keeps the direct implicit GEMM for the ResnetBlock convolutions, winograd="unfused" the separate
+    transform passes instead of the fused bridge: all paths compute the same function (each within the parity tolerance
+    of the reference; against each other within the same noise floor)."""
     cfg, gold, inputs, net = _build("face_bs1_nb4")
     from wacv23_tsnet_b200.model.TSNet import TSNet
     ref_net = TSNet(is_train=False, label_nc=cfg["label_nc"], n_blocks=cfg["n_blocks"], n_downsampling=3,
-                    n_source=cfg["n_source"], return_flow=True, winograd=False)
+                    n_source=cfg["n_source"], return_flow=True, winograd=variant)
     for k in ("img_enc", "lbl_enc", "fuse_net", "dec"):
         getattr(ref_net, k).load_state_dict(getattr(net, k).state_dict())
     ref_net.eval()
@@ -225,7 +227,7 @@ def test_direct_and_winograd_paths_agree():
     assert float((ref_net.rec_tar_img.cpu() - g).abs().max()) < IMG_TOL
     assert float((net.rec_tar_img.cpu() - g).abs().max()) < IMG_TOL
     assert float((net.rec_tar_img - ref_net.rec_tar_img).abs().max()) < IMG_TOL
-    assert not torch.equal(net.rec_tar_img, ref_net.rec_tar_img)   # the two paths really are different kernels
+    assert not torch.equal(net.rec_tar_img, ref_net.rec_tar_img)   # the paths really are different kernels
 
 
 def test_data_writes_need_invalidate_weights():

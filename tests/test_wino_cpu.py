@@ -161,3 +161,44 @@ def test_whole_chain_equals_reflect_pad_conv(emul):
     ref = F.conv2d(F.pad(x.permute(0, 3, 1, 2).double(), (1, 1, 1, 1), mode="reflect"), w.double(), bias.double())
     ref = ref.permute(0, 2, 3, 1)
     assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("H,W,Cc,relu,with_res,nthreads", [(32, 32, 64, True, False, 512), (32, 32, 32, False, True, 512),
+                                                           (8, 16, 32, True, True, 64), (4, 4, 64, False, False, 32)])
+def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_res, nthreads):
+    """The fused bridge (csrc/wino_passes.cuh: phases A, S, B, C) == output transform + bias + addend -> InstanceNorm ->
+    [ReLU | + residual] -> reflect pad + input transform, evaluated in torch fp64."""
+    vp = C.c_void_p
+    emul.wino_emul_bridge.argtypes = [vp, vp, vp, C.c_longlong, vp, vp, vp, vp, vp] + [C.c_int] * 10 + \
+                                     [C.c_float, C.c_float, C.c_int]
+    torch.manual_seed(8)
+    B = 2
+    T = (H // 2) * (W // 2)
+    m = torch.randn(16, B * T, Cc)
+    bias = torch.randn(Cc)
+    addend = torch.randn(H * W, Cc)
+    res = torch.randn(B, H, W, Cc) if with_res else None
+    hi = torch.zeros((B, 16, H // 2, W // 2, Cc + 32), dtype=torch.int16)
+    lo = torch.zeros_like(hi)
+    act = torch.zeros(B, H, W, Cc + 8)
+    mr = torch.zeros(B, Cc, 2)
+    emul.wino_emul_bridge(_p(m), _p(bias), _p(addend), H * W, _p(res), _p(act), _p(mr), _p(hi), _p(lo), B, H, W, Cc,
+                          int(relu), Cc + 32, 32, 0, Cc + 8, 8, 16.0, 1e-5, nthreads)
+    M = m.double().view(4, 4, B, H // 2, W // 2, Cc)
+    y = torch.einsum("ai,ijbxyc,ej->bxayec", AT, M, AT).reshape(B, H, W, Cc) + bias.double() + \
+        addend.double().view(1, H, W, Cc)
+    mean = y.mean((1, 2), keepdim=True)
+    var = y.var((1, 2), unbiased=False, keepdim=True)
+    v = (y - mean) / torch.sqrt(var + 1e-5)
+    if relu:
+        v = torch.relu(v)
+    if with_res:
+        v = v + res.double()
+    assert float((mr[..., 0].double() - mean.view(B, Cc)).abs().max()) < 1e-6
+    assert float((mr[..., 1].double() * torch.sqrt(var + 1e-5).view(B, Cc) - 1).abs().max()) < 1e-6
+    assert float((act[..., 8:].double() - v).abs().max()) < 1e-5 and float(act[..., :8].abs().max()) == 0.0
+    # the operands are the transform of the fp32 activations the pass itself produced (act_out)
+    ref = ref_input_transform(act[..., 8:]) * 16.0
+    got = _recon(hi, lo)
+    assert float((got[..., 32:] - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert int(hi[..., :32].abs().max()) == 0

@@ -33,6 +33,22 @@ for st in $STAGES; do
           -f -o $OUT/prof_winoin_$TAG $FWD > /dev/null 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_output_kernel -s 30 -c 1 \
           -f -o $OUT/prof_winoout_$TAG $FWD > /dev/null 2>&1 ;;
+    tests_new)
+      timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "postprocess or uint8 or wino or invalidate or bs32 or direct_and or golden or two_cta or stem or classmap" > $OUT/pytest_new_$TAG.log 2>&1
+      echo "pytest exit $?" >> $OUT/pytest_new_$TAG.log; tail -25 $OUT/pytest_new_$TAG.log ;;
+    parity)
+      timeout 600 python tools/parity_report.py --winograd bridge --chunk-kb 2 4 8 > $OUT/parity_$TAG.log 2>&1
+      timeout 300 python tools/parity_report.py --winograd off >> $OUT/parity_$TAG.log 2>&1
+      grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
+    tests_wino)
+      timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "wino or direct_and or golden or cuda_graph or train_mode or full_batch" > $OUT/pytest_wino_$TAG.log 2>&1
+      echo "pytest exit $?" >> $OUT/pytest_wino_$TAG.log; tail -25 $OUT/pytest_wino_$TAG.log ;;
+    bench_unfused)
+      timeout 400 python bench.py --steps 10 --warmup 3 --winograd-unfused --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_unfused_$TAG.json 2> $OUT/bench_unfused_$TAG.err
+      cut -c1-300 $OUT/bench_unfused_$TAG.json ;;
+    ncu_bridge)
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_bridge_kernel -s 20 -c 1 \
+          -f -o $OUT/prof_bridge_$TAG $FWD > /dev/null 2>&1 ;;
     winobench)
       timeout 300 python tools/wino_bench.py > $OUT/winobench_$TAG.log 2>&1; cat $OUT/winobench_$TAG.log ;;
     ncu_corr)

@@ -309,4 +309,192 @@ TSNET_HD void wino_output_body(const WinoOutArgs& a, int block, int thread, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bridge pass "I+T": output transform of layer k, InstanceNorm, [ReLU | + residual], input transform of layer k+1 in ONE
+// pass over HBM -- M[k] is read once, V[k+1] is written once; the fp32 conv output, its statistics partials and the
+// separate instnorm_reduce launch disappear.  One CTA = one image x a slab of kBridgeCS channels: the whole H x W x CS
+// conv output lives in shared memory (128 KB at 32 x 32 x 32), so the per-(image, channel) statistics are CTA-local.
+// Phases (block-wide barriers between them; the host emulation runs each phase for every thread in turn):
+//   A  y = A^T M A + bias (+ addend)                      -> shared memory
+//   S  per-channel sum / sum of squares in fp64, fixed order -> mean, 1/sqrt(var + eps)   (S1 partials, S2 merge)
+//   B  v = (y - mean) * rstd ; ReLU ; + residual ; act_out  -> shared memory (in place) and optional fp32 output
+//   C  reflect pad + B^T d B + hi/lo split                  -> the 16 operand planes of the next plane GEMMs
+// ------------------------------------------------------------------------------------------------
+constexpr int kBridgeCS = 32;
+
+struct WinoBridgeArgs {
+  const float* m;         // fp32 [16][B * TH * TW][C]
+  const float* bias;      // [C] or null
+  const float* addend;    // fp32 [addend_rows, C] or null
+  const float* residual;  // fp32 [B, H, W, C] or null
+  float* act_out;         // fp32 [B, H, W, act_C_total] window [act_c_off, +C) or null
+  float* mean_rstd_out;   // [B, C, 2] or null (tests / diagnostics)
+  uint16_t* hi;           // [B, 16, H/2, W/2, Cp_total] window [c_off, +C)
+  uint16_t* lo;
+  int B, H, W, C, relu, Cp_total, c_off, fmt, act_C_total, act_c_off;
+  long long addend_rows;
+  float scale, eps;
+};
+
+// shared-memory layout: float y[H * W * CS]; double part[nseg * CS * 2]; float mr[CS * 2]
+TSNET_HD size_t wino_bridge_smem_bytes(int H, int W, int nthreads) {
+  return static_cast<size_t>(H) * W * kBridgeCS * 4 + static_cast<size_t>(nthreads / kBridgeCS) * kBridgeCS * 2 * 8 +
+         kBridgeCS * 2 * 4;
+}
+
+TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y) {
+  const int slabs = a.C / kBridgeCS;
+  const int b = block / slabs, slab = block - b * slabs;
+  const int TH = a.H / 2, TW = a.W / 2, T = TH * TW;
+  const size_t ptile = static_cast<size_t>(a.B) * T;
+  constexpr int CQ = kBridgeCS / 4;
+  for (int u = thread; u < T * CQ; u += nthreads) {
+    const int tile = u / CQ, cq = u - tile * CQ;
+    const int ty = tile / TW, tx = tile - ty * TW;
+    const int c = slab * kBridgeCS + cq * 4;
+    const float* mp = a.m + (static_cast<size_t>(b) * T + tile) * a.C + c;
+    f4 bias = f4{0.f, 0.f, 0.f, 0.f};
+    if (a.bias) bias = ld_f4(a.bias + c);
+    f4 z[2][4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) {
+      const f4 m0 = ld_f4(mp + (0 * 4 + j) * ptile * a.C);
+      const f4 m1 = ld_f4(mp + (1 * 4 + j) * ptile * a.C);
+      const f4 m2 = ld_f4(mp + (2 * 4 + j) * ptile * a.C);
+      const f4 m3 = ld_f4(mp + (3 * 4 + j) * ptile * a.C);
+      z[0][j] = f4_add(f4_add(m0, m1), m2);
+      z[1][j] = f4_sub(f4_sub(m1, m2), m3);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int re = 0; re < 4; ++re) {
+      const int r = re >> 1, e = re & 1;
+      f4 o = e == 0 ? f4_add(f4_add(f4_add(z[r][0], z[r][1]), z[r][2]), bias)
+                    : f4_add(f4_sub(f4_sub(z[r][1], z[r][2]), z[r][3]), bias);
+      const int pix = (2 * ty + r) * a.W + 2 * tx + e;
+      if (a.addend) {
+        const size_t gp = static_cast<size_t>(b) * a.H * a.W + pix;
+        o = f4_add(o, ld_f4(a.addend + (gp % static_cast<size_t>(a.addend_rows)) * a.C + c));
+      }
+      st_f4(s_y + static_cast<size_t>(pix) * kBridgeCS + cq * 4, o);
+    }
+  }
+}
+
+TSNET_HD void wino_bridge_phase_s1(const WinoBridgeArgs& a, int thread, int nthreads, const float* s_y, double* s_part) {
+  const int HW = a.H * a.W;
+  const int nseg = nthreads / kBridgeCS;
+  const int c = thread % kBridgeCS, seg = thread / kBridgeCS;
+  if (seg >= nseg) return;
+  const int per = (HW + nseg - 1) / nseg;
+  const int p0 = seg * per, p1 = p0 + per < HW ? p0 + per : HW;
+  double s = 0.0, q = 0.0;
+  for (int p = p0; p < p1; ++p) {
+    const double v = static_cast<double>(s_y[static_cast<size_t>(p) * kBridgeCS + c]);
+    s += v;
+    q += v * v;
+  }
+  s_part[(seg * kBridgeCS + c) * 2 + 0] = s;
+  s_part[(seg * kBridgeCS + c) * 2 + 1] = q;
+}
+
+TSNET_HD void wino_bridge_phase_s2(const WinoBridgeArgs& a, int block, int thread, int nthreads, const double* s_part,
+                                   float* s_mr) {
+  if (thread >= kBridgeCS) return;
+  const int nseg = nthreads / kBridgeCS;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < nseg; ++k) {
+    s += s_part[(k * kBridgeCS + thread) * 2 + 0];
+    q += s_part[(k * kBridgeCS + thread) * 2 + 1];
+  }
+  const double n = static_cast<double>(a.H) * a.W;
+  const double mean = s / n;
+  double var = q / n - mean * mean;  // biased, as nn.InstanceNorm2d
+  var = var > 0.0 ? var : 0.0;
+  const float mf = static_cast<float>(mean);
+#if defined(__CUDA_ARCH__)
+  const float rf = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+#else
+  const float rf = static_cast<float>(1.0 / __builtin_sqrt(var + static_cast<double>(a.eps)));
+#endif
+  s_mr[thread * 2 + 0] = mf;
+  s_mr[thread * 2 + 1] = rf;
+  if (a.mean_rstd_out) {
+    const int slabs = a.C / kBridgeCS;
+    const int b = block / slabs, slab = block - b * slabs;
+    float* o = a.mean_rstd_out + (static_cast<size_t>(b) * a.C + slab * kBridgeCS + thread) * 2;
+    o[0] = mf;
+    o[1] = rf;
+  }
+}
+
+TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y,
+                                  const float* s_mr) {
+  const int slabs = a.C / kBridgeCS;
+  const int b = block / slabs, slab = block - b * slabs;
+  const int HW = a.H * a.W;
+  constexpr int CQ = kBridgeCS / 4;
+  for (int u = thread; u < HW * CQ; u += nthreads) {
+    const int pix = u / CQ, cq = u - pix * CQ;
+    float* sp = s_y + static_cast<size_t>(pix) * kBridgeCS + cq * 4;
+    f4 v = ld_f4(sp);
+    const f4 m01 = ld_f4(s_mr + cq * 8), m23 = ld_f4(s_mr + cq * 8 + 4);  // (mean, rstd) x 4 channels
+    v.x = (v.x - m01.x) * m01.y; v.y = (v.y - m01.z) * m01.w;
+    v.z = (v.z - m23.x) * m23.y; v.w = (v.w - m23.z) * m23.w;
+    if (a.relu) {
+      v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+      v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+    }
+    const size_t gp = static_cast<size_t>(b) * HW + pix;
+    const int c = slab * kBridgeCS + cq * 4;
+    if (a.residual) v = f4_add(v, ld_f4(a.residual + gp * a.C + c));
+    st_f4(sp, v);
+    if (a.act_out) st_f4(a.act_out + gp * a.act_C_total + a.act_c_off + c, v);
+  }
+}
+
+TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y) {
+  const int slabs = a.C / kBridgeCS;
+  const int b = block / slabs, slab = block - b * slabs;
+  const int TH = a.H / 2, TW = a.W / 2, T = TH * TW;
+  constexpr int CQ = kBridgeCS / 4;
+  const size_t pstride = static_cast<size_t>(T) * a.Cp_total;
+  for (int u = thread; u < T * CQ; u += nthreads) {
+    const int tile = u / CQ, cq = u - tile * CQ;
+    const int ty = tile / TW, tx = tile - ty * TW;
+    const int ys[4] = {wino_reflect(2 * ty - 1, a.H), 2 * ty, 2 * ty + 1, wino_reflect(2 * ty + 2, a.H)};
+    const int xs[4] = {wino_reflect(2 * tx - 1, a.W), 2 * tx, 2 * tx + 1, wino_reflect(2 * tx + 2, a.W)};
+    f4 t[4][4];  // t[s][i] = (B^T d)[i][s]
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int sx = 0; sx < 4; ++sx) {
+      const float* col = s_y + static_cast<size_t>(xs[sx]) * kBridgeCS + cq * 4;
+      const f4 d0 = ld_f4(col + static_cast<size_t>(ys[0]) * a.W * kBridgeCS);
+      const f4 d1 = ld_f4(col + static_cast<size_t>(ys[1]) * a.W * kBridgeCS);
+      const f4 d2 = ld_f4(col + static_cast<size_t>(ys[2]) * a.W * kBridgeCS);
+      const f4 d3 = ld_f4(col + static_cast<size_t>(ys[3]) * a.W * kBridgeCS);
+      t[sx][0] = f4_sub(d0, d2);
+      t[sx][1] = f4_add(d1, d2);
+      t[sx][2] = f4_sub(d2, d1);
+      t[sx][3] = f4_sub(d1, d3);
+    }
+    WinoInArgs w;  // only the fields wino_store_plane reads
+    w.hi = a.hi; w.lo = a.lo; w.scale = a.scale; w.fmt = a.fmt;
+    const size_t d0 = ((static_cast<size_t>(b) * 16 * TH + ty) * TW + tx) * a.Cp_total + a.c_off + slab * kBridgeCS + cq * 4;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+      wino_store_plane(w, d0 + (i * 4 + 0) * pstride, f4_sub(t[0][i], t[2][i]));
+      wino_store_plane(w, d0 + (i * 4 + 1) * pstride, f4_add(t[1][i], t[2][i]));
+      wino_store_plane(w, d0 + (i * 4 + 2) * pstride, f4_sub(t[2][i], t[1][i]));
+      wino_store_plane(w, d0 + (i * 4 + 3) * pstride, f4_sub(t[1][i], t[3][i]));
+    }
+  }
+}
+
 }  // namespace tsnet

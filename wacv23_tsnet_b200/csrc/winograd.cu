@@ -19,6 +19,23 @@ __global__ void __launch_bounds__(256, 3) wino_output_kernel(const WinoOutArgs a
   wino_output_body(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
+constexpr int kBridgeThreads = 512;
+__global__ void __launch_bounds__(kBridgeThreads, 1) wino_bridge_kernel(const WinoBridgeArgs a) {
+  extern __shared__ __align__(16) uint8_t bridge_smem[];
+  float* s_y = reinterpret_cast<float*>(bridge_smem);
+  double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * kBridgeCS * 4);
+  float* s_mr = reinterpret_cast<float*>(s_part + (kBridgeThreads / kBridgeCS) * kBridgeCS * 2);
+  wino_bridge_phase_a(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
+  __syncthreads();
+  wino_bridge_phase_s1(a, threadIdx.x, kBridgeThreads, s_y, s_part);
+  __syncthreads();
+  wino_bridge_phase_s2(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_part, s_mr);
+  __syncthreads();
+  wino_bridge_phase_b(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y, s_mr);
+  __syncthreads();
+  wino_bridge_phase_c(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
+}
+
 // called by tsnet_build_taps (elementwise.cu) for mode TSNET_TAPS_WINO
 int launch_wino_input(const WinoInArgs& a, cudaStream_t stream) {
   TSNET_ARG_CHECK(a.H % 2 == 0 && a.W % 2 == 0 && a.H >= 4 && a.W >= 4, "build_taps(WINO): H, W must be even, >= 4");
@@ -55,6 +72,35 @@ extern "C" int tsnet_wino_output(const float* m, int B, int H, int W, int C, con
   a.B = B; a.H = H; a.W = W; a.C = C; a.addend_rows = addend_rows;
   const unsigned rows = static_cast<unsigned>(B) * (H / 2);
   wino_output_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TSNET_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m, const float* bias, const float* addend,
+                                 const float* residual, float* act_out, float* mean_rstd_out, uint16_t* v_hi,
+                                 uint16_t* v_lo, void* stream) {
+  TSNET_ARG_CHECK(d && m && v_hi && v_lo, "wino_bridge: null argument");
+  TSNET_ARG_CHECK(d->H % 2 == 0 && d->W % 2 == 0 && d->H >= 4 && d->W >= 4, "wino_bridge: H, W must be even, >= 4");
+  TSNET_ARG_CHECK(d->C > 0 && d->C % kBridgeCS == 0, "wino_bridge: C %d must be a multiple of %d", d->C, kBridgeCS);
+  TSNET_ARG_CHECK(d->Cp_total % 4 == 0 && d->c_off % 4 == 0 && d->c_off + d->C <= d->Cp_total,
+                  "wino_bridge: operand channel window does not fit");
+  TSNET_ARG_CHECK(!addend || d->addend_rows > 0, "wino_bridge: addend needs addend_rows > 0");
+  const int actC = d->act_C_total > 0 ? d->act_C_total : d->C;
+  TSNET_ARG_CHECK(!act_out || (actC % 4 == 0 && d->act_c_off % 4 == 0 && d->act_c_off + d->C <= actC),
+                  "wino_bridge: act_out channel window does not fit");
+  const size_t smem = wino_bridge_smem_bytes(d->H, d->W, kBridgeThreads);
+  TSNET_ARG_CHECK(smem <= 227 * 1024, "wino_bridge: %d x %d image needs %zu B of shared memory", d->H, d->W, smem);
+  WinoBridgeArgs a;
+  a.m = m; a.bias = bias; a.addend = addend; a.residual = residual; a.act_out = act_out;
+  a.mean_rstd_out = mean_rstd_out; a.hi = v_hi; a.lo = v_lo;
+  a.B = d->B; a.H = d->H; a.W = d->W; a.C = d->C; a.relu = d->relu; a.Cp_total = d->Cp_total; a.c_off = d->c_off;
+  a.fmt = d->fmt; a.act_C_total = actC; a.act_c_off = d->act_c_off; a.addend_rows = d->addend_rows;
+  a.scale = d->scale == 0.f ? 1.f : d->scale;
+  a.eps = d->eps == 0.f ? 1e-5f : d->eps;
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(wino_bridge_kernel, static_cast<int>(smem), smem_attr));
+  const unsigned blocks = static_cast<unsigned>(d->B) * (d->C / kBridgeCS);
+  wino_bridge_kernel<<<blocks, kBridgeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
   return 0;
 }

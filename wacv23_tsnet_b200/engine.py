@@ -32,7 +32,14 @@ class ForwardEngine:
         # Winograd F(2x2, 3x3) for every ResnetBlock convolution (img_enc x 18, FuseNet x 2 + its target half, decoder
         # x 2 n_blocks): 2.25 x fewer tensor-core MACs for the layers that take ~60 % of the step.
         # winograd=False keeps the direct implicit GEMM for them (A/B comparisons, tests).
+        # winograd="unfused" keeps the separate output-transform / instnorm_reduce / input-transform passes between two
+        # Winograd layers instead of the fused bridge pass (tsnet_wino_bridge).
         self.winograd = bool(winograd)
+        self.bridge = self.winograd and winograd != "unfused"
+        # K blocks (of 64 channels) accumulated in TMEM before the partial sum is promoted to fp32 registers in the
+        # Winograd plane GEMMs (K = Cin per plane).  Measured on the B200 (tools/wino_bench.py, 512 -> 512 x 96 samples):
+        # 2 -> 0.572 ms / 6.4e-7 of max|ref| vs an fp64 conv; 4 -> 0.503 ms / 1.1e-6; 8 (no promotion) -> 0.474 ms / 2.1e-6
+        self.wino_chunk_kb = 4
         self._packs = {}
         self._coord = {}
 
@@ -92,7 +99,8 @@ class ForwardEngine:
         implicit GEMM) or on Winograd planes (taps geometry (16, H/2, W/2)).  Returns (y_raw, mean_rstd or None)."""
         if taps[2][0] == 16:
             pw = self._pack_wino(net, wkey, cin_range=cin_range, with_bias=with_bias)
-            y, stats = ops.wino_conv(taps, pw, B, H, W, self.mode, self.mode.act_scale, want_stats=norm, addend=addend)
+            y, stats = ops.wino_conv(taps, pw, B, H, W, self.mode, self.mode.act_scale, want_stats=norm, addend=addend,
+                                     chunk_kb=self.wino_chunk_kb)
             mr = ops.instnorm_reduce(stats, B, H * W, pw.Cout) if norm else None
             return y, mr
         pc = self._pack(net, wkey, cin_range=cin_range, with_bias=with_bias)
@@ -120,6 +128,13 @@ class ForwardEngine:
                           fuse=dict(relu=relu, tmode=tmode, residual=residual, act_out=act_out, act_c_off=act_c_off,
                                     taps=dest if want_taps else None, c_off=c_off))
             return ((dest[0], dest[1], (planes, Hd, Wd)) if want_taps else None), act_out
+        if is3 and self.bridge and taps[2][0] == 16 and tmode == L.TAPS_WINO and want_taps:
+            # Winograd layer feeding a Winograd layer: GEMM + ONE bridge pass (no y_raw / statistics round trip)
+            pw = self._pack_wino(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
+            mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self.wino_chunk_kb)
+            t = ops.wino_bridge(mbuf, pw, B, H, W, m, relu=relu, addend=addend, residual=residual, act_out=act_out,
+                                act_c_off=act_c_off, taps=dest, c_off=c_off)
+            return t, act_out
         if is3:
             y, mr = self._conv3(taps, pc[0], pc[1], B, H, W, addend=addend, cin_range=pc[2] if len(pc) > 2 else None)
         else:

@@ -53,6 +53,12 @@ class WinoGemmDesc(C.Structure):
                 ("flags", C.c_int)]
 
 
+class WinoBridgeDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("relu", C.c_int),
+                ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int), ("scale", C.c_float), ("eps", C.c_float),
+                ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("addend_rows", C.c_longlong)]
+
+
 _SIGNATURES = {
     "tsnet_abi_version": (C.c_int, []),
     "tsnet_last_error": (C.c_char_p, []),
@@ -64,6 +70,7 @@ _SIGNATURES = {
     "tsnet_wino_weight_transform": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "tsnet_wino_gemm_fwd": (C.c_int, [C.POINTER(WinoGemmDesc), vp, vp, vp, vp, vp, vp]),
     "tsnet_wino_output": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_longlong, vp, vp, vp]),
+    "tsnet_wino_bridge": (C.c_int, [C.POINTER(WinoBridgeDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, vp, C.c_int, C.c_int, C.c_int,

@@ -148,16 +148,15 @@ def wino_ok(H, W, Cin, Cout):
             (W // 2 <= 128 and 128 % (W // 2) == 0) and Cin % 64 == 0 and Cout % 256 == 0)
 
 
-def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, m_buf=None, flags=0, chunk_kb=0):
-    """3x3 reflect-pad conv via Winograd: taps = (hi, lo, geom) from build_taps(mode TAPS_WINO).
-    Returns (y_raw [B, H, W, Cout], stats_partial or None) -- the outputs of conv_gemm."""
+def wino_gemm(taps, pw, B, H, W, mode, act_scale, m_buf=None, flags=0, chunk_kb=0):
+    """The 16 plane GEMMs of a Winograd 3x3 conv as one batched launch: taps = (hi, lo, geom) from
+    build_taps(mode TAPS_WINO) or wino_bridge.  Returns M, fp32 [16, B * H/2 * W/2, Cout] (flat buffer)."""
     hi, lo, geom = taps
     TH, TW = H // 2, W // 2
     assert geom == (16, TH, TW) and hi.shape == (B * 16, TH, TW, pw.Cp), (geom, tuple(hi.shape))
-    dev = hi.device
     n_m = 16 * B * TH * TW * pw.Cout
     if m_buf is None or m_buf.numel() < n_m:
-        m_buf = torch.empty(n_m, dtype=torch.float32, device=dev)
+        m_buf = torch.empty(n_m, dtype=torch.float32, device=hi.device)
     d = L.WinoGemmDesc()
     d.B, d.TH, d.TW, d.C, d.Cout = B, TH, TW, pw.Cp, pw.Cout
     d.split, d.fmt, d.out_scale, d.chunk_kb, d.flags = mode.split, mode.fmt, 1.0 / (pw.scale * act_scale), chunk_kb, flags
@@ -165,6 +164,12 @@ def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, 
         L.check(L.load().tsnet_wino_gemm_fwd(C.byref(d), _ptr(hi), _ptr(lo), _ptr(pw.u_hi), _ptr(pw.u_lo), _ptr(m_buf),
                                              _stream()))
     _count()
+    return m_buf
+
+
+def wino_output(m_buf, pw, B, H, W, want_stats=True, addend=None):
+    """Output transform + bias (+ addend) + InstanceNorm partial statistics: (y_raw [B, H, W, Cout], stats or None)."""
+    dev = m_buf.device
     y = torch.empty((B, H, W, pw.Cout), dtype=torch.float32, device=dev)
     stats = torch.empty((B * H * W // 32, pw.Cout, 2), dtype=torch.float32, device=dev) if want_stats else None
     rows = 0
@@ -176,6 +181,46 @@ def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, 
                                            _ptr(stats), _stream()))
     _count()
     return y, stats
+
+
+def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, m_buf=None, flags=0, chunk_kb=0):
+    """3x3 reflect-pad conv via Winograd (GEMM + output pass).  Returns (y_raw [B, H, W, Cout], stats_partial or None)
+    -- the outputs of conv_gemm."""
+    m_buf = wino_gemm(taps, pw, B, H, W, mode, act_scale, m_buf=m_buf, flags=flags, chunk_kb=chunk_kb)
+    return wino_output(m_buf, pw, B, H, W, want_stats=want_stats, addend=addend)
+
+
+def wino_bridge(m_buf, pw, B, H, W, mode, relu=False, addend=None, residual=None, act_out=None, act_c_off=0, taps=None,
+                c_off=0, mean_rstd_out=None, act_scale=None):
+    """Fused layer boundary between two Winograd convolutions (tsnet_wino_bridge): output transform + bias (+ addend) ->
+    InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> input transform.  Returns (hi, lo, (16, H/2, W/2))."""
+    Cc = pw.Cout
+    dev = m_buf.device
+    if taps is None:
+        hi = torch.empty((B * 16, H // 2, W // 2, Cc), dtype=torch.int16, device=dev)
+        lo = torch.empty_like(hi)
+    else:
+        hi, lo = taps
+    assert hi.shape[:3] == (B * 16, H // 2, W // 2)
+    d = L.WinoBridgeDesc()
+    d.B, d.H, d.W, d.C, d.relu = B, H, W, Cc, int(relu)
+    d.Cp_total, d.c_off, d.fmt = hi.shape[3], c_off, mode.fmt
+    d.scale, d.eps = (mode.act_scale if act_scale is None else act_scale), 1e-5
+    rows = 0
+    if addend is not None:
+        assert addend.shape[-1] == Cc and addend.is_contiguous() and addend.dtype == torch.float32
+        rows = addend.numel() // Cc
+    d.addend_rows = rows
+    if act_out is not None:
+        assert act_out.dtype == torch.float32 and act_out.is_contiguous() and act_out.shape[:3] == (B, H, W)
+        d.act_C_total, d.act_c_off = act_out.shape[-1], act_c_off
+    if residual is not None:
+        assert _f32(residual).shape == (B, H, W, Cc)
+    with _Prof(("wino_bridge",)):
+        L.check(L.load().tsnet_wino_bridge(C.byref(d), _ptr(m_buf), _ptr(pw.bias), _ptr(addend), _ptr(residual),
+                                           _ptr(act_out), _ptr(mean_rstd_out), _ptr(hi), _ptr(lo), _stream()))
+    _count()
+    return hi, lo, (16, H // 2, W // 2)
 
 
 def taps_geometry(mode, H, W):
