@@ -263,6 +263,8 @@ def run_b200(args):
                         winograd=args.winograd)
     D.broadcast_generator(net, src=0)
     net.eval()
+    if args.wino_chunk_kb > 0:
+        net._engine.wino_chunk_kb = args.wino_chunk_kb
     log("model built")
 
     from oracle.synth import IMG_MEAN as _MEAN
@@ -522,6 +524,7 @@ def run_b200(args):
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
                            "math_mode": args.math, "winograd_f2x2_3x3": (args.winograd if isinstance(args.winograd, str) else bool(args.winograd)),
+                           "wino_chunk_kb": net._engine.wino_chunk_kb,
                            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
@@ -572,6 +575,9 @@ def main():
     ap.add_argument("--pose", action="store_true", help="TSNet_pose, label_nc=25 (BASELINE.json config 3)")
     ap.add_argument("--no-winograd", dest="winograd", action="store_const", const=False, default=True,
                     help="direct implicit GEMM for the ResnetBlock convolutions (A/B against the Winograd default)")
+    ap.add_argument("--wino-chunk-kb", dest="wino_chunk_kb", type=int, default=0,
+                    help="experiment: K blocks accumulated in TMEM per promotion in the Winograd GEMMs (default: the "
+                         "engine's parity-validated 2; 4 is faster but misses the image tolerance on one golden)")
     ap.add_argument("--winograd-unfused", dest="winograd", action="store_const", const="unfused",
                     help="Winograd with separate transform passes instead of the fused bridge pass (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -192,6 +192,12 @@ typedef struct {
   int avg_n;        /* > 1 (mode SAME only): v = mean over i < avg_n of f(raw[i*B + b]) -- torch.stack().mean(1)
                        of model/TSNet.py:400; raw / mean_rstd / residual then hold avg_n*B samples */
   int flags;        /* TSNET_TAPS_GENERIC_UP2: one-destination-pixel-per-thread kernel for mode UP2REFLECT1 (tests) */
+  /* two-part residual (modes SAME / REFLECT1 / S2ZERO): the residual is torch.cat([residual, residual2], 1) without the
+   * concatenation ever being written -- channels [0, res_split) from `residual` [B, H, W, res_split], the others from
+   * residual2 [res2_batch, H, W, C - res_split], sample index modulo res2_batch (FuseNet: x = cat[src_fea_i, tar_fea],
+   * model/TSNet.py:196, with ONE tar_fea shared by the n sources) */
+  const float* residual2;
+  int res_split, res2_batch;
 } tsnet_taps_desc;
 #define TSNET_TAPS_GENERIC_UP2 1
 

@@ -45,7 +45,7 @@ extern "C" void wino_emul_bridge(const float* m, const float* bias, const float*
   const size_t bytes = wino_bridge_smem_bytes(H, W, nthreads);
   uint8_t* smem = new uint8_t[bytes + 16];
   float* s_y = reinterpret_cast<float*>(smem);
-  double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(H) * W * kBridgeCS * 4);
+  double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(H) * W * kBridgePS * 4);
   float* s_mr = reinterpret_cast<float*>(s_part + (nthreads / kBridgeCS) * kBridgeCS * 2);
   const int blocks = B * (C / kBridgeCS);
   for (int blk = 0; blk < blocks; ++blk) {   // phases separated by block-wide barriers in the kernel

@@ -187,6 +187,13 @@ def test_build_taps_modes(mode):
     refp = F.pad(ref.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1) * m.act_scale
     assert _relerr(_recon(cat_hi, cat_lo, m.fmt)[..., 64:], refp) < tol
     assert int(cat_hi[..., :64].abs().max()) == 0
+    # two-part residual: x + torch.cat([r0, r1 broadcast over the batch], C) without materialising the concatenation
+    r0 = torch.randn(2, 16, 16, 40, device="cuda")
+    r1 = torch.randn(1, 16, 16, 24, device="cuda")
+    a2 = torch.empty(2, 16, 16, 64, device="cuda")
+    ops.build_taps(x, m, L.TAPS_SAME, mean_rstd=mr, residual=(r0, r1), act_out=a2, want_taps=False)
+    ref2 = F.instance_norm(xn, eps=1e-5).permute(0, 2, 3, 1) + torch.cat([r0, r1.expand(2, -1, -1, -1)], -1)
+    assert _relerr(a2, ref2) < 1e-6
     # mean over sources (torch.stack(...).mean(1), model/TSNet.py:400)
     x3 = torch.randn(6, 8, 8, 64, device="cuda")
     a3 = torch.empty(2, 8, 8, 64, device="cuda")

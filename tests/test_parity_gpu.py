@@ -134,6 +134,44 @@ def test_demo_call_sequence_5d_lists_uint8_bbox_and_source_count():
         assert not torch.equal(net.rec_tar_img.data.cpu(), a)
 
 
+def test_source_feature_cache_is_exact_and_detects_changes():
+    """Opt-in cache for the demo loop (demo/demo_face.py:170-192 re-feeds the same source frames for every driving
+    frame): a hit skips img_enc and gives the same bits; an in-place edit of the sources (version bump) or new weights
+    are detected."""
+    from wacv23_tsnet_b200 import ops
+    cfg, gold, inputs, net = _build("face_bs1_nb4")
+    imgs = torch.from_numpy(np.stack(inputs["src_img"]))
+    lbls = torch.from_numpy(np.stack(inputs["src_lbl"]))
+    bbs = torch.from_numpy(np.stack(inputs["src_bbox"]))
+    tl, tb = torch.from_numpy(inputs["tar_lbl"]), torch.from_numpy(inputs["tar_bbox"])
+    with torch.no_grad():
+        net.set_test_input(imgs, lbls, bbs, tl, tb)
+        l0 = ops.kernel_launches()
+        net.forward()
+        miss = ops.kernel_launches() - l0
+        a = net.rec_tar_img.clone()
+        net.enable_source_cache(True)
+        for k in range(3):
+            net.set_test_input(imgs, lbls, bbs, tl, tb)
+            l0 = ops.kernel_launches()
+            net.forward()
+            hit = ops.kernel_launches() - l0
+            assert torch.equal(net.rec_tar_img, a)
+        assert hit < miss - 40, (hit, miss)          # the 9 ResnetBlocks + stem of img_enc were skipped
+        net.set_test_input(imgs, lbls, bbs, tl, tb.flip(-1).contiguous())    # a new driving frame, same sources
+        net.forward()
+        assert not torch.equal(net.rec_tar_img, a)
+        imgs.mul_(0.5)                                # in-place edit: the version counter changes
+        net.set_test_input(imgs, lbls, bbs, tl, tb)
+        net.forward()
+        b = net.rec_tar_img.clone()
+        assert not torch.equal(b, a)
+        net.enable_source_cache(False)
+        net.set_test_input(imgs, lbls, bbs, tl, tb)
+        net.forward()
+        assert torch.equal(net.rec_tar_img, b)
+
+
 def test_load_state_dict_repacks_weights():
     from oracle import make_golden as MG
     cfg, gold, inputs, net = _build("quickstart_bs1")

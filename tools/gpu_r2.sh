@@ -40,6 +40,12 @@ for st in $STAGES; do
       timeout 600 python tools/parity_report.py --winograd bridge --chunk-kb 2 4 8 > $OUT/parity_$TAG.log 2>&1
       timeout 300 python tools/parity_report.py --winograd off >> $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
+    parity_mix)
+      timeout 700 python tools/parity_report.py --winograd bridge --chunk-kb 2 img_enc=2,default=4 img_enc=4,default=2 3 > $OUT/parity_$TAG.log 2>&1
+      grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
+    bench_c4)
+      timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
+      cut -c1-300 $OUT/bench_c4_$TAG.json ;;
     tests_wino)
       timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "wino or direct_and or golden or cuda_graph or train_mode or full_batch" > $OUT/pytest_wino_$TAG.log 2>&1
       echo "pytest exit $?" >> $OUT/pytest_wino_$TAG.log; tail -25 $OUT/pytest_wino_$TAG.log ;;
@@ -52,7 +58,7 @@ for st in $STAGES; do
     winobench)
       timeout 300 python tools/wino_bench.py > $OUT/winobench_$TAG.log 2>&1; cat $OUT/winobench_$TAG.log ;;
     ncu_corr)
-      timeout 300 ncu --set full --clock-control none --import-source on -k regex:corr_ -s 6 -c 4 \
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:"corr_|l2norm|warp_mean" -s 6 -c 6 \
           -f -o $OUT/prof_corr_$TAG $FWD > /dev/null 2>&1 ;;
   esac
 done

@@ -11,7 +11,8 @@ from wacv23_tsnet_b200.model.TSNet_pose import TSNet as TSNetPose
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--winograd", default="bridge")
-ap.add_argument("--chunk-kb", dest="chunk_kb", type=int, nargs="*", default=[4])
+ap.add_argument("--chunk-kb", dest="chunk_kb", nargs="*", default=["2"],
+                help="ints, or per-net specs like img_enc=2,default=4")
 args = ap.parse_args()
 wino = {"bridge": True, "unfused": "unfused", "off": False}[args.winograd]
 for ck in args.chunk_kb:
@@ -24,7 +25,8 @@ for ck in args.chunk_kb:
         with contextlib.redirect_stdout(io.StringIO()):
             net = cls(is_train=False, label_nc=cfg["label_nc"], n_blocks=cfg["n_blocks"], n_downsampling=3,
                       n_source=cfg["n_source"], winograd=wino, **kw)
-        net._engine.wino_chunk_kb = ck
+        net._engine.wino_chunk_kb = (int(ck) if ck.isdigit() else
+                                     {kv.split("=")[0]: int(kv.split("=")[1]) for kv in ck.split(",")})
         for k in ("img_enc", "lbl_enc", "fuse_net", "dec"):
             getattr(net, k).load_state_dict({kk: torch.from_numpy(v) for kk, v in sds[k].items()})
         t = torch.from_numpy

@@ -109,6 +109,11 @@ struct TapsArgs {
   float scale;
   int Hd, Wd, planes;  // destination geometry
   int act_C_total, act_c_off, avg_n;
+  // residual given as a channel concatenation of two tensors (torch.cat([a, t], 1) never materialised): channels
+  // [0, res_split) from `residual` [B, H, W, res_split], the rest from residual2 [res2_batch, H, W, C - res_split] with
+  // the sample index taken modulo res2_batch (one target feature map shared by all sources)
+  const float* residual2;
+  int res_split, res2_batch;
 };
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -131,7 +136,17 @@ __device__ __forceinline__ void fetch_act8(const TapsArgs& a, int b, int y, int 
   }
   if (a.residual) {
     float r[8];
-    load8(a.residual + off, r);
+    if (a.residual2 == nullptr) {
+      load8(a.residual + off, r);
+    } else {
+      const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+      if (c < a.res_split) {
+        load8(a.residual + pix * a.res_split + c, r);
+      } else {
+        const size_t pix2 = (static_cast<size_t>(b % a.res2_batch) * a.H + y) * a.W + x;
+        load8(a.residual2 + pix2 * (a.C - a.res_split) + (c - a.res_split), r);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += r[j];
   }
@@ -692,6 +707,12 @@ extern "C" int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, cons
   a.act_C_total = d->act_C_total > 0 ? d->act_C_total : d->C;
   a.act_c_off = d->act_c_off;
   a.avg_n = d->avg_n > 1 ? d->avg_n : 1;
+  a.residual2 = d->residual2; a.res_split = d->res_split; a.res2_batch = d->res2_batch;
+  TSNET_ARG_CHECK(!d->residual2 || (residual && d->res_split > 0 && d->res_split < d->C && d->res_split % 8 == 0 &&
+                                    (d->C - d->res_split) % 8 == 0 && d->res2_batch > 0 && d->avg_n <= 1 &&
+                                    (d->mode == TSNET_TAPS_SAME || d->mode == TSNET_TAPS_REFLECT1 ||
+                                     d->mode == TSNET_TAPS_S2ZERO)),
+                  "build_taps: two-part residual needs mode SAME / REFLECT1 / S2ZERO, res_split %% 8 == 0, res2_batch > 0");
   TSNET_ARG_CHECK(a.avg_n == 1 || d->mode == TSNET_TAPS_SAME, "build_taps: avg_n needs mode SAME");
   TSNET_ARG_CHECK(a.act_c_off % 4 == 0 && a.act_C_total % 4 == 0 && a.act_c_off + d->C <= a.act_C_total,
                   "build_taps: act_out channel window does not fit");

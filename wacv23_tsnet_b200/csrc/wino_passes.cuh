@@ -313,14 +313,18 @@ TSNET_HD void wino_output_body(const WinoOutArgs& a, int block, int thread, int 
 // bridge pass "I+T": output transform of layer k, InstanceNorm, [ReLU | + residual], input transform of layer k+1 in ONE
 // pass over HBM -- M[k] is read once, V[k+1] is written once; the fp32 conv output, its statistics partials and the
 // separate instnorm_reduce launch disappear.  One CTA = one image x a slab of kBridgeCS channels: the whole H x W x CS
-// conv output lives in shared memory (128 KB at 32 x 32 x 32), so the per-(image, channel) statistics are CTA-local.
+// conv output lives in shared memory (96 KB at 32 x 32 x 16 with padding), so the per-(image, channel) statistics are
+// CTA-local.
 // Phases (block-wide barriers between them; the host emulation runs each phase for every thread in turn):
 //   A  y = A^T M A + bias (+ addend)                      -> shared memory
 //   S  per-channel sum / sum of squares in fp64, fixed order -> mean, 1/sqrt(var + eps)   (S1 partials, S2 merge)
 //   B  v = (y - mean) * rstd ; ReLU ; + residual ; act_out  -> shared memory (in place) and optional fp32 output
 //   C  reflect pad + B^T d B + hi/lo split                  -> the 16 operand planes of the next plane GEMMs
 // ------------------------------------------------------------------------------------------------
-constexpr int kBridgeCS = 32;
+constexpr int kBridgeCS = 16;  // channels per CTA: 64 KB image buffer -> two CTAs per SM, whose read-heavy (A) and
+                               // write-heavy (C) phases overlap (one CTA per SM with 32 channels ran at 3.8 TB/s)
+constexpr int kBridgePS = 24;  // shared-memory pixel stride in floats (16 channels + 8 pad): the 64-byte groups that the
+                               // lanes of a warp touch (pixels 2 apart in A / C, adjacent in B) alternate bank halves
 
 struct WinoBridgeArgs {
   const float* m;         // fp32 [16][B * TH * TW][C]
@@ -336,9 +340,9 @@ struct WinoBridgeArgs {
   float scale, eps;
 };
 
-// shared-memory layout: float y[H * W * CS]; double part[nseg * CS * 2]; float mr[CS * 2]
+// shared-memory layout: float y[H * W * PS]; double part[nseg * CS * 2]; float mr[CS * 2]
 TSNET_HD size_t wino_bridge_smem_bytes(int H, int W, int nthreads) {
-  return static_cast<size_t>(H) * W * kBridgeCS * 4 + static_cast<size_t>(nthreads / kBridgeCS) * kBridgeCS * 2 * 8 +
+  return static_cast<size_t>(H) * W * kBridgePS * 4 + static_cast<size_t>(nthreads / kBridgeCS) * kBridgeCS * 2 * 8 +
          kBridgeCS * 2 * 4;
 }
 
@@ -379,7 +383,7 @@ TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread
         const size_t gp = static_cast<size_t>(b) * a.H * a.W + pix;
         o = f4_add(o, ld_f4(a.addend + (gp % static_cast<size_t>(a.addend_rows)) * a.C + c));
       }
-      st_f4(s_y + static_cast<size_t>(pix) * kBridgeCS + cq * 4, o);
+      st_f4(s_y + static_cast<size_t>(pix) * kBridgePS + cq * 4, o);
     }
   }
 }
@@ -393,7 +397,7 @@ TSNET_HD void wino_bridge_phase_s1(const WinoBridgeArgs& a, int thread, int nthr
   const int p0 = seg * per, p1 = p0 + per < HW ? p0 + per : HW;
   double s = 0.0, q = 0.0;
   for (int p = p0; p < p1; ++p) {
-    const double v = static_cast<double>(s_y[static_cast<size_t>(p) * kBridgeCS + c]);
+    const double v = static_cast<double>(s_y[static_cast<size_t>(p) * kBridgePS + c]);
     s += v;
     q += v * v;
   }
@@ -439,7 +443,7 @@ TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread
   constexpr int CQ = kBridgeCS / 4;
   for (int u = thread; u < HW * CQ; u += nthreads) {
     const int pix = u / CQ, cq = u - pix * CQ;
-    float* sp = s_y + static_cast<size_t>(pix) * kBridgeCS + cq * 4;
+    float* sp = s_y + static_cast<size_t>(pix) * kBridgePS + cq * 4;
     f4 v = ld_f4(sp);
     const f4 m01 = ld_f4(s_mr + cq * 8), m23 = ld_f4(s_mr + cq * 8 + 4);  // (mean, rstd) x 4 channels
     v.x = (v.x - m01.x) * m01.y; v.y = (v.y - m01.z) * m01.w;
@@ -472,11 +476,11 @@ TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread
 #pragma unroll
 #endif
     for (int sx = 0; sx < 4; ++sx) {
-      const float* col = s_y + static_cast<size_t>(xs[sx]) * kBridgeCS + cq * 4;
-      const f4 d0 = ld_f4(col + static_cast<size_t>(ys[0]) * a.W * kBridgeCS);
-      const f4 d1 = ld_f4(col + static_cast<size_t>(ys[1]) * a.W * kBridgeCS);
-      const f4 d2 = ld_f4(col + static_cast<size_t>(ys[2]) * a.W * kBridgeCS);
-      const f4 d3 = ld_f4(col + static_cast<size_t>(ys[3]) * a.W * kBridgeCS);
+      const float* col = s_y + static_cast<size_t>(xs[sx]) * kBridgePS + cq * 4;
+      const f4 d0 = ld_f4(col + static_cast<size_t>(ys[0]) * a.W * kBridgePS);
+      const f4 d1 = ld_f4(col + static_cast<size_t>(ys[1]) * a.W * kBridgePS);
+      const f4 d2 = ld_f4(col + static_cast<size_t>(ys[2]) * a.W * kBridgePS);
+      const f4 d3 = ld_f4(col + static_cast<size_t>(ys[3]) * a.W * kBridgePS);
       t[sx][0] = f4_sub(d0, d2);
       t[sx][1] = f4_add(d1, d2);
       t[sx][2] = f4_sub(d2, d1);

@@ -19,11 +19,11 @@ __global__ void __launch_bounds__(256, 3) wino_output_kernel(const WinoOutArgs a
   wino_output_body(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
-constexpr int kBridgeThreads = 512;
-__global__ void __launch_bounds__(kBridgeThreads, 1) wino_bridge_kernel(const WinoBridgeArgs a) {
+constexpr int kBridgeThreads = 256;
+__global__ void __launch_bounds__(kBridgeThreads, 2) wino_bridge_kernel(const WinoBridgeArgs a) {
   extern __shared__ __align__(16) uint8_t bridge_smem[];
   float* s_y = reinterpret_cast<float*>(bridge_smem);
-  double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * kBridgeCS * 4);
+  double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * kBridgePS * 4);
   float* s_mr = reinterpret_cast<float*>(s_part + (kBridgeThreads / kBridgeCS) * kBridgeCS * 2);
   wino_bridge_phase_a(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
   __syncthreads();

@@ -39,15 +39,20 @@ class ForwardEngine:
         # K blocks (of 64 channels) accumulated in TMEM before the partial sum is promoted to fp32 registers in the
         # Winograd plane GEMMs (K = Cin per plane).  Measured on the B200 (tools/wino_bench.py, 512 -> 512 x 96 samples):
         # 2 -> 0.572 ms / 6.4e-7 of max|ref| vs an fp64 conv; 4 -> 0.503 ms / 1.1e-6; 8 (no promotion) -> 0.474 ms / 2.1e-6
-        self.wino_chunk_kb = 4
+        # Whole-forward parity (tools/parity_report.py, worst of the 7 goldens, tolerance 1e-3 / 5e-5): chunk 2 -> image
+        # 8.7e-4, grids 2.4e-5 (the direct path: 9.3e-4 / 2.3e-5); chunk 4 -> 1.07e-3 / 2.6e-5; chunk 8 -> 1.3e-3 / 3.4e-5.
+        # The default is therefore 2, as in tsnet_conv_gemm_fwd; an int, or a dict {net name: chunk} with key "default".
+        self.wino_chunk_kb = 2
         self._packs = {}
         self._coord = {}
+        self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))
 
     def invalidate(self):
         """Drop every packed weight.  Needed after parameter writes that do not bump the tensor version
         (`p.data.copy_()`, `init.normal_(p.data)`, `dist.broadcast(p.data)`): the pack cache is keyed on
         (data_ptr, _version) and would otherwise keep serving the old operands."""
         self._packs.clear()
+        self._src_cache = None
 
     # ------------------------------------------------------------------ weights
     def _pack(self, net, wkey, fold_kw=False, block_n=None, cin_range=None, with_bias=True):
@@ -76,6 +81,10 @@ class ForwardEngine:
             self._packs[key] = hit
         return hit[1]
 
+    def _chunk(self, net):
+        ck = self.wino_chunk_kb
+        return ck.get(net, ck.get("default", 2)) if isinstance(ck, dict) else ck
+
     def _tmode3(self, H, W, Cin, Cout):
         """Operand format a 3x3 reflect-pad convolution consumes: Winograd planes where the path applies."""
         return L.TAPS_WINO if (self.winograd and ops.wino_ok(H, W, Cin, Cout)) else L.TAPS_REFLECT1
@@ -100,7 +109,7 @@ class ForwardEngine:
         if taps[2][0] == 16:
             pw = self._pack_wino(net, wkey, cin_range=cin_range, with_bias=with_bias)
             y, stats = ops.wino_conv(taps, pw, B, H, W, self.mode, self.mode.act_scale, want_stats=norm, addend=addend,
-                                     chunk_kb=self.wino_chunk_kb)
+                                     chunk_kb=self._chunk(net))
             mr = ops.instnorm_reduce(stats, B, H * W, pw.Cout) if norm else None
             return y, mr
         pc = self._pack(net, wkey, cin_range=cin_range, with_bias=with_bias)
@@ -117,7 +126,8 @@ class ForwardEngine:
         Cout = (self.nets[pc[0]].state_dict(keep_vars=True)[pc[1] + ".weight"].shape[0]) if is3 else pc.Cout
         if act_out is None and need_act:
             act_out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=taps[0].device)
-        if (self.fused_in and H * W == 1024 and tmode in (L.TAPS_SAME, L.TAPS_REFLECT1) and taps[2][0] != 16):
+        if (self.fused_in and H * W == 1024 and tmode in (L.TAPS_SAME, L.TAPS_REFLECT1) and taps[2][0] != 16 and
+                not isinstance(residual, tuple)):
             if is3:
                 pc = self._pack(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
             planes, Hd, Wd = ops.taps_geometry(tmode, H, W)
@@ -131,7 +141,7 @@ class ForwardEngine:
         if is3 and self.bridge and taps[2][0] == 16 and tmode == L.TAPS_WINO and want_taps:
             # Winograd layer feeding a Winograd layer: GEMM + ONE bridge pass (no y_raw / statistics round trip)
             pw = self._pack_wino(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
-            mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self.wino_chunk_kb)
+            mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self._chunk(pc[0]))
             t = ops.wino_bridge(mbuf, pw, B, H, W, m, relu=relu, addend=addend, residual=residual, act_out=act_out,
                                 act_c_off=act_c_off, taps=dest, c_off=c_off)
             return t, act_out
@@ -183,12 +193,15 @@ class ForwardEngine:
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
     def forward(self, src_imgs, img_divs, src_lbls, src_bboxes, tar_lbl, tar_bbox, return_flow=False,
-                pose_fill=None, collect=None, train=None, img_mean=None):
+                pose_fill=None, collect=None, train=None, img_mean=None, src_key=None):
         """src_imgs / src_lbls: lists of n fp32 NCHW CUDA tensors [B,3,256,256] / [B,L,256,256] (labels may instead be
         uint8 class-index maps [B,256,256]: vl2ch is then evaluated inside the stem loader; images NOT yet /255:
         img_divs[i] is the divisor set_*_input would have applied: 255, or 1 for use_prev sources); src_bboxes / tar_bbox: [B,256,256] uint8|fp32.
         Returns (rec_tar_img NCHW fp32, list of warp grids [B,h,w,2] or None).
         `collect`: optional dict receiving intermediates (tests).
+        `src_key`: optional hashable identifying the CONTENT of the source images + labels (opt-in source-feature cache
+        for the demo loops, which re-feed the same source frames for every driving frame, demo/demo_face.py:170-192): when
+        it equals the key of the previous forward (and the img_enc weights are unchanged) img_enc is not re-run.
         `train`: optional dict {"tar_img": raw NCHW target image, "align": bool}: the is_train=True branches of the
         reference forward (image-space warp, warp / alignment losses) are evaluated and returned in it as
         "warp" [n,B,3,H,W] and "losses" (device float[2])."""
@@ -227,11 +240,19 @@ class ForwardEngine:
             # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
             src_imgs = [im if dv == 1.0 else im / dv for im, dv in zip(src_imgs, img_divs)]
             img_divs = [1.0] * n
-        img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
-        lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
-        src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]), lbl_cat.contiguous(),
-                                           9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf),
-                                           img_mean=img_mean)                              # [n*B, h, w, 512]
+        cache_sig = None
+        if src_key is not None:
+            cache_sig = (src_key, n, B, tuple(img_divs), m.name, self.winograd, self.bridge, str(self.wino_chunk_kb),
+                         tuple((p.data_ptr(), p._version) for p in self.nets["img_enc"].parameters()))
+        if cache_sig is not None and self._src_cache is not None and self._src_cache[0] == cache_sig:
+            src_fea, fuse_taps = self._src_cache[1]
+        else:
+            img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
+            lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
+            src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]),
+                                               lbl_cat.contiguous(), 9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf),
+                                               img_mean=img_mean)                          # [n*B, h, w, 512]
+            self._src_cache = (cache_sig, (src_fea, fuse_taps)) if cache_sig is not None else None
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
         # ---- transformation branch (model/TSNet.py:319-366, 392)
@@ -253,10 +274,9 @@ class ForwardEngine:
         # ---- synthesis branch: FuseNet on all sources at once (model/TSNet.py:177-200, 396-400).
         # conv1(reflpad(cat[s_i, t])) = W[:, :512] * reflpad(s_i) + W[:, 512:] * reflpad(t): pad and conv are linear, so
         # the target half is evaluated ONCE per frame and added (fp32) in the epilogue of the per-source GEMM.
-        cat_act = torch.empty((n * B, h, w, 2 * Cf), dtype=torch.float32, device=dev)   # x of "x + conv_block(x)"
-        ops.build_taps(src_fea, m, L.TAPS_SAME, act_out=cat_act, act_c_off=0, want_taps=False)
-        for i in range(n):
-            ops.build_taps(tar_fea, m, L.TAPS_SAME, act_out=cat_act[i * B:(i + 1) * B], act_c_off=Cf, want_taps=False)
+        # x of "x + conv_block(x)" is cat[src_fea_i, tar_fea]: read through two pointers by the pass that adds it, the
+        # 1024-channel concatenation is never written
+        cat_act = (src_fea, tar_fea)
         t_taps = ops.build_taps(tar_fea, m, self._tmode3(h, w, Cf, 2 * Cf))
         y_t, _ = self._conv3(t_taps, "fuse_net", "model.0.conv_block.1", B, h, w, norm=False,
                              cin_range=(Cf, 2 * Cf), with_bias=False)                      # [B, h, w, 1024]

@@ -37,7 +37,7 @@ class TapsDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("mode", C.c_int),
                 ("relu", C.c_int), ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int),
                 ("scale", C.c_float), ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("avg_n", C.c_int),
-                ("flags", C.c_int)]
+                ("flags", C.c_int), ("residual2", C.c_void_p), ("res_split", C.c_int), ("res2_batch", C.c_int)]
 
 
 class CorrDesc(C.Structure):

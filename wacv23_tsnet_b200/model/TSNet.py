@@ -92,7 +92,7 @@ class TSNet(nn.Module):
                  debug=False, lambda_dec=1.0,
                  addcoords=True,
                  ngf=64, n_downsampling=4, return_flow=False, math_mode="fp16x3", cuda_graph=False, winograd=True,
-                 img_mean=None):
+                 img_mean=None, cache_sources=False):
         super().__init__()
         # is_train=True: forward-only.  The generator is built exactly as for is_train=False (no discriminators, VGG,
         # optimizers -- SURVEY section 8f row 3); forward() then also runs the reference's train-mode branches
@@ -124,6 +124,10 @@ class TSNet(nn.Module):
         self.img_mean = None if img_mean is None else tuple(float(v) for v in img_mean)
         self._use_graph = bool(cuda_graph)
         self._graphs = {}
+        # opt-in (demo loops): skip re-staging and re-encoding source frames that are the same tensors, at the same
+        # version, as in the previous set_test_input (the demos feed identical sources for every driving frame)
+        self._cache_sources = bool(cache_sources)
+        self._src_sig = None
         self._src_img_raw, self._src_img_div = None, None
         self._tar_img_raw = None
         self.loss_warp = 0.0
@@ -144,6 +148,18 @@ class TSNet(nn.Module):
     def _f32(t):
         t = t.cuda()
         return t if t.dtype == torch.float32 else t.float()
+
+    def enable_source_cache(self, flag=True):
+        """Opt-in: when set_test_input receives the SAME source image / label tensors (same storage, shape and version
+        counter) as the previous call, their device copies and their img_enc features are reused.  In-place edits that
+        do not bump the tensor version (e.g. through a numpy view) are not detected -- leave this off in that case."""
+        self._cache_sources = bool(flag)
+        self._src_sig = None
+        self._engine._src_cache = None
+
+    @staticmethod
+    def _tensor_sig(ts):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.dtype), str(t.device)) for t in ts)
 
     def set_image_mean(self, mean):
         """Dataset mean (3 floats, BGR) used when source images are passed as uint8 tensors."""
@@ -186,6 +202,7 @@ class TSNet(nn.Module):
                 for x, d in zip([self._img(x, keep_u8=False) for x in self._src_img_raw], self._src_img_div)]
 
     def set_train_input(self, src_img_list, src_lbl_list, src_bbox_list, tar_img, tar_lbl, tar_bbox, use_prev=None):
+        self._src_sig = None
         self._src_img_raw = [self._img(x, keep_u8=False) for x in src_img_list]
         self._src_img_div = [1.0 if (use_prev is not None and use_prev[i]) else 255.0
                              for i in range(len(self._src_img_raw))]
@@ -199,9 +216,14 @@ class TSNet(nn.Module):
     def set_test_input(self, src_img_list, src_lbl_list, src_bbox_list,
                        tar_lbl, tar_bbox,
                        prev_tar_img=None, prev_tar_lbl=None, prev_tar_bbox=None):
-        self._src_img_raw = [self._img(x) for x in src_img_list]
-        self._src_img_div = [255.0] * len(self._src_img_raw)
-        self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
+        sig = None
+        if self._cache_sources:
+            sig = (self._tensor_sig(list(src_img_list)), self._tensor_sig(list(src_lbl_list)), self.img_mean)
+        if sig is None or sig != self._src_sig or self._src_img_raw is None:
+            self._src_img_raw = [self._img(x) for x in src_img_list]
+            self._src_img_div = [255.0] * len(self._src_img_raw)
+            self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
+        self._src_sig = sig
         self.src_bbox_list = [self._mask(x).unsqueeze(dim=1) for x in src_bbox_list]
         self.tar_lbl = self._lbl(tar_lbl)
         self.tar_bbox = self._mask(tar_bbox).unsqueeze(dim=1)
@@ -244,13 +266,22 @@ class TSNet(nn.Module):
         return (list(self._src_img_raw[:n]), list(self._src_img_div[:n]), list(self.src_lbl_list[:n]), src_bb,
                 self.tar_lbl, self.tar_bbox.squeeze(1))
 
+    def _src_key(self):
+        """Key of the source-feature cache for this forward: the content signature of the staged sources (None = cache
+        off) restricted to the first n_source entries."""
+        if not self._cache_sources or self._src_sig is None:
+            return None
+        n = self.n_source
+        return (self._src_sig[0][:n], self._src_sig[1][:n], self._src_sig[2])
+
     def _param_signature(self):
         return tuple((p.data_ptr(), p._version) for net in (self.img_enc, self.lbl_enc, self.fuse_net, self.dec)
                      for p in net.parameters())
 
     def _forward_graph(self, imgs, divs, lbls, bbs, tar_lbl, tar_bbox):
+        src_key = self._src_key()
         key = (tuple(tar_lbl.shape), len(imgs), tuple(divs), tar_bbox.dtype, imgs[0].dtype, lbls[0].dtype,
-               self.return_flow, self._param_signature())
+               self.return_flow, self._param_signature(), src_key)
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs.clear()  # one live graph: its private pool holds every workspace of the forward
@@ -260,7 +291,7 @@ class TSNet(nn.Module):
             def run():
                 return self._engine.forward(static["imgs"], divs, static["lbls"], static["bbs"], static["tar_lbl"],
                                             static["tar_bbox"], return_flow=self.return_flow,
-                                            pose_fill=self._pose_fill, img_mean=self.img_mean)
+                                            pose_fill=self._pose_fill, img_mean=self.img_mean, src_key=src_key)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -297,7 +328,8 @@ class TSNet(nn.Module):
                 rec, grids = self._forward_graph(imgs, divs, lbls, bbs, tar_lbl, tar_bbox)
         else:
             rec, grids = self._engine.forward(imgs, divs, lbls, bbs, tar_lbl, tar_bbox, return_flow=self.return_flow,
-                                              pose_fill=self._pose_fill, collect=_collect, img_mean=self.img_mean)
+                                              pose_fill=self._pose_fill, collect=_collect, img_mean=self.img_mean,
+                                              src_key=self._src_key())
         self.rec_tar_img = rec
         if self.return_flow:
             self.warp_grid2d_list = grids

@@ -346,6 +346,12 @@ def build_taps(raw, mode, tmode, mean_rstd=None, relu=False, residual=None, act_
     d.scale = mode.act_scale if act_scale is None else act_scale
     d.avg_n = avg_n
     d.flags = flags
+    keep = None
+    if isinstance(residual, (tuple, list)):  # torch.cat([r0, r1], -1) with r1's batch broadcast, never materialised
+        r0, r1 = _f32(residual[0]), _f32(residual[1])
+        assert r0.shape[:3] == (B, H, W) and r1.shape[1:3] == (H, W) and r0.shape[3] + r1.shape[3] == Cch
+        d.residual2, d.res_split, d.res2_batch = r1.data_ptr(), r0.shape[3], r1.shape[0]
+        keep, residual = (r0, r1), r0
     hi = lo = None
     if want_taps:
         if taps is None:
