@@ -726,8 +726,9 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
     torch.cuda.synchronize()
     assert _relerr(mr_f[..., 0], mr[..., 0]) < 1e-5 and _relerr(mr_f[..., 1], mr[..., 1]) < 1e-5
     assert _relerr(act_f[..., 64:], act_s) < 2e-6 and float(act_f[..., :64].abs().max()) == 0.0
-    assert _relerr(_recon(hf, lf, m.fmt)[..., 64:], _recon(hs, ls, m.fmt)) < 4e-6
-    assert int(hf[..., :64].abs().max()) == 0
+    vl = ops.wino_v_logical   # operand planes are stored K-block-major
+    assert _relerr(_recon(vl(hf), vl(lf), m.fmt)[..., 64:], _recon(vl(hs), vl(ls), m.fmt)) < 4e-6
+    assert int(vl(hf)[..., :64].abs().max()) == 0
     # deterministic, and a sample does not depend on the batch it rides in
     h2, l2, _ = ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res)
     t1 = ops.build_taps(x[1:2].contiguous(), m, L.TAPS_WINO)
@@ -736,4 +737,4 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
                                 residual=None if res is None else res[1:2].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(h2[16:32], h1) and torch.equal(l2[16:32], l1)
-    assert torch.equal(h2, hf[..., 64:]) and torch.equal(l2, lf[..., 64:])
+    assert torch.equal(vl(h2), vl(hf)[..., 64:]) and torch.equal(vl(l2), vl(lf)[..., 64:])

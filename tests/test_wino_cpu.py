@@ -41,23 +41,36 @@ def _recon(hi, lo, fmt=0):
     return hi.view(dt).double() + lo.view(dt).double()
 
 
+def v_logical(t):
+    """V as stored, [B, 16, Cp/64, TH, TW, 64] (K-block-major), -> [B, 16, TH, TW, Cp]"""
+    B, P, KB, TH, TW, _ = t.shape
+    return t.permute(0, 1, 3, 4, 2, 5).reshape(B, P, TH, TW, KB * 64)
+
+
+def m_slab(m_logical, B, Cc):
+    """M logical [16, B * T, C] -> as stored, slab-major [16, B, C/32, T, 32]"""
+    T = m_logical.shape[1] // B
+    return m_logical.view(16, B, T, Cc // 32, 32).permute(0, 1, 3, 2, 4).contiguous()
+
+
 def run_input(emul, x, mean_rstd=None, relu=False, residual=None, want_act=False, scale=16.0, fmt=0, nthreads=64,
               Cp_total=None, c_off=0, act_extra=0):
     B, H, W, Cc = x.shape
-    Cp_total = Cp_total or Cc
-    hi = torch.zeros((B, 16, H // 2, W // 2, Cp_total), dtype=torch.int16)
+    Cp_total = Cp_total or (Cc + 63) // 64 * 64
+    hi = torch.zeros((B, 16, Cp_total // 64, H // 2, W // 2, 64), dtype=torch.int16)
     lo = torch.zeros_like(hi)
     act = torch.zeros((B, H, W, Cc + act_extra), dtype=torch.float32) if want_act else None
     emul.wino_emul_input(_p(x), _p(mean_rstd), _p(residual), _p(act), _p(hi), _p(lo), B, H, W, Cc, int(relu), Cp_total,
                          c_off, fmt, Cc + act_extra, act_extra, scale, nthreads)
-    return hi, lo, act
+    return v_logical(hi), v_logical(lo), act
 
 
 def run_output(emul, m, B, H, W, Cc, bias=None, addend=None, want_stats=True, nthreads=64):
     y = torch.zeros((B, H, W, Cc), dtype=torch.float32)
     stats = torch.zeros((B * H * W // 32, Cc, 2), dtype=torch.float32) if want_stats else None
     rows = 0 if addend is None else addend.numel() // Cc
-    emul.wino_emul_output(_p(m), _p(bias), _p(addend), rows, _p(y), _p(stats), B, H, W, Cc, nthreads)
+    ms = m_slab(m, B, Cc)
+    emul.wino_emul_output(_p(ms), _p(bias), _p(addend), rows, _p(y), _p(stats), B, H, W, Cc, nthreads)
     return y, stats
 
 
@@ -90,16 +103,18 @@ def test_input_pass(emul, H, W, Cc, nthreads):
     hi, lo, _ = run_input(emul, x, nthreads=nthreads)
     ref = ref_input_transform(x) * 16.0
     got = _recon(hi, lo)
-    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-6
-    # InstanceNorm + ReLU + residual + act_out (with a channel offset in a wider act_out and tap source)
+    assert float((got[..., :Cc] - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert int(hi[..., Cc:].abs().max()) == 0                      # channels padded up to the 64-wide K block stay zero
+    # InstanceNorm + ReLU + residual + act_out (with a channel offset in a wider act_out and operand buffer)
     hi, lo, act = run_input(emul, x, mean_rstd=mr, relu=True, residual=res, want_act=True, nthreads=nthreads,
-                            Cp_total=Cc + 8, c_off=8, act_extra=4)
+                            Cp_total=128, c_off=8, act_extra=4)
     v = torch.relu((x - mr[..., 0].view(B, 1, 1, Cc)) * mr[..., 1].view(B, 1, 1, Cc)) + res
     assert torch.equal(act[..., 4:], v) and float(act[..., :4].abs().max()) == 0.0
     ref = ref_input_transform(v) * 16.0
     got = _recon(hi, lo)
-    assert float((got[..., 8:] - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert float((got[..., 8:8 + Cc] - ref).abs().max() / ref.abs().max()) < 2e-6
     assert int(hi[..., :8].abs().max()) == 0 and int(lo[..., :8].abs().max()) == 0
+    assert int(hi[..., 8 + Cc:].abs().max()) == 0
 
 
 def test_input_pass_bf16_and_saturation(emul):
@@ -107,13 +122,13 @@ def test_input_pass_bf16_and_saturation(emul):
     x = torch.randn(1, 8, 8, 4)
     hi, lo, _ = run_input(emul, x, scale=1.0, fmt=1)
     ref = ref_input_transform(x)
-    assert float((_recon(hi, lo, 1) - ref).abs().max() / ref.abs().max()) < 1e-4
+    assert float((_recon(hi, lo, 1)[..., :4] - ref).abs().max() / ref.abs().max()) < 1e-4
     x[0, 3, 3, 0] = 3.0e4                                   # 16 * 3e4 overflows fp16: must saturate, not turn into NaN
     hi, lo, _ = run_input(emul, x)
     assert torch.isfinite(_recon(hi, lo)).all()
 
 
-@pytest.mark.parametrize("H,W,Cc,nthreads", [(32, 32, 16, 64), (4, 16, 4, 1), (8, 32, 8, 5)])
+@pytest.mark.parametrize("H,W,Cc,nthreads", [(32, 32, 32, 64), (4, 16, 64, 1), (8, 32, 32, 5)])
 def test_output_pass(emul, H, W, Cc, nthreads):
     torch.manual_seed(3)
     B = 3
@@ -142,7 +157,7 @@ def test_whole_chain_equals_reflect_pad_conv(emul):
     """T -> 16 plane GEMMs over the hi/lo operands (layouts of tsnet_wino_gemm_fwd: A = V[b, p] rows = tiles, B rows
     p * Cout + o, M = [16, B * tiles, Cout]) -> I  ==  Conv2d(ReflectionPad2d(1)(x)) in fp64."""
     torch.manual_seed(4)
-    B, H, W, Cin, Cout = 2, 32, 32, 16, 8
+    B, H, W, Cin, Cout = 2, 32, 32, 16, 32
     x = torch.randn(B, H, W, Cin) * 2
     w = torch.randn(Cout, Cin, 3, 3) * 0.05
     bias = torch.randn(Cout)
@@ -153,7 +168,7 @@ def test_whole_chain_equals_reflect_pad_conv(emul):
     u_hi = us.half()
     u_lo = (us - u_hi.float()).half()
     hi, lo, _ = run_input(emul, x)
-    V = _recon(hi, lo).view(B, 16, (H // 2) * (W // 2), Cin)              # [B, 16, tiles, C]
+    V = _recon(hi, lo)[..., :Cin].reshape(B, 16, (H // 2) * (W // 2), Cin)  # [B, 16, tiles, C]
     U = (u_hi.double() + u_lo.double()).view(16, Cout, Cin)
     # hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative) ~ full product of the reconstructed operands
     M = torch.einsum("bptc,poc->pbto", V, U).reshape(16, B * (H // 2) * (W // 2), Cout) / (wscale * 16.0)
@@ -178,12 +193,15 @@ def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_r
     bias = torch.randn(Cc)
     addend = torch.randn(H * W, Cc)
     res = torch.randn(B, H, W, Cc) if with_res else None
-    hi = torch.zeros((B, 16, H // 2, W // 2, Cc + 32), dtype=torch.int16)
+    Cp = (Cc + 32 + 63) // 64 * 64
+    hi = torch.zeros((B, 16, Cp // 64, H // 2, W // 2, 64), dtype=torch.int16)
     lo = torch.zeros_like(hi)
     act = torch.zeros(B, H, W, Cc + 8)
     mr = torch.zeros(B, Cc, 2)
-    emul.wino_emul_bridge(_p(m), _p(bias), _p(addend), H * W, _p(res), _p(act), _p(mr), _p(hi), _p(lo), B, H, W, Cc,
-                          int(relu), Cc + 32, 32, 0, Cc + 8, 8, 16.0, 1e-5, nthreads)
+    ms = m_slab(m, B, Cc)
+    emul.wino_emul_bridge(_p(ms), _p(bias), _p(addend), H * W, _p(res), _p(act), _p(mr), _p(hi), _p(lo), B, H, W, Cc,
+                          int(relu), Cp, 32, 0, Cc + 8, 8, 16.0, 1e-5, nthreads)
+    hi, lo = v_logical(hi), v_logical(lo)
     M = m.double().view(4, 4, B, H // 2, W // 2, Cc)
     y = torch.einsum("ai,ijbxyc,ej->bxayec", AT, M, AT).reshape(B, H, W, Cc) + bias.double() + \
         addend.double().view(1, H, W, Cc)
@@ -200,5 +218,5 @@ def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_r
     # the operands are the transform of the fp32 activations the pass itself produced (act_out)
     ref = ref_input_transform(act[..., 8:]) * 16.0
     got = _recon(hi, lo)
-    assert float((got[..., 32:] - ref).abs().max() / ref.abs().max()) < 2e-6
-    assert int(hi[..., :32].abs().max()) == 0
+    assert float((got[..., 32:32 + Cc] - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert int(hi[..., :32].abs().max()) == 0 and (32 + Cc == Cp or int(hi[..., 32 + Cc:].abs().max()) == 0)

@@ -52,6 +52,10 @@ struct alignas(64) ConvGemmArgs {
   // y + p * y_plane_stride.
   int batch_planes, b_plane_rows;
   long long y_plane_stride;
+  // Winograd-domain layouts (tsnet_wino_gemm_fwd): the A operand is K-block-major, [B * 16][Cp / 64][TH][TW][64] (5-D
+  // tensor map), and M is written slab-major, [16][B][Cout / 32][tiles per image][32], so that the transform passes, which
+  // own (image, channel slab) pairs, stream contiguous memory (y_slab_tiles = tiles per image; 0 = plain [M, Cout])
+  int a_kblock_major, y_slab_tiles;
   // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
   const float* f_residual;   // fp32 [B, H, W, Cout] or null
   float* f_act_out;          // fp32, channel window [f_act_c_off, +Cout) of f_act_C_total, or null
@@ -213,10 +217,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
             const int kb = tap * args.kc_per_tap + kc;
-            tma_load_4d(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+            if (args.a_kblock_major) tma_load_5d(st, &args.a_hi, &full_bar[stage], 0, cx, cy, kc, cn);
+            else tma_load_4d(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
             tma_load_2d(st + 2 * Cfg::kABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, brow);
             if (args.split) {
-              tma_load_4d(st + Cfg::kABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+              if (args.a_kblock_major) tma_load_5d(st + Cfg::kABytes, &args.a_lo, &full_bar[stage], 0, cx, cy, kc, cn);
+              else tma_load_4d(st + Cfg::kABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
               tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &args.b_lo, &full_bar[stage], kb * kBlockK, brow);
             }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -438,6 +444,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       }
       // ---- tile epilogue: scale + bias, store, InstanceNorm partial statistics ----
       float* yrow = args.y + static_cast<size_t>(plane) * args.y_plane_stride + gm * args.Cout;
+      // slab-major M (Winograd): [image][Cout / 32][tiles per image][32]
+      const size_t simg = args.y_slab_tiles ? gm / args.y_slab_tiles : 0;
+      const size_t stile = args.y_slab_tiles ? gm - simg * args.y_slab_tiles : 0;
+      float* ybase = args.y + static_cast<size_t>(plane) * args.y_plane_stride +
+                     simg * static_cast<size_t>(args.Cout) * args.y_slab_tiles + stile * 32;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
               v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
             }
           }
-          store_row32(yrow + n0, v);
+          store_row32(args.y_slab_tiles ? ybase + static_cast<size_t>(n0 >> 5) * args.y_slab_tiles * 32 : yrow + n0, v);
           if (srow) {
             // per-column (sum, centred M2) over this warp's 32 pixels
             float t[32];
@@ -570,10 +581,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
               uint8_t* st = smem + stage * kG2StageBytes;
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
               const int kb = tap * args.kc_per_tap + kc;
-              tma_load_4d_2sm(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+              if (args.a_kblock_major) tma_load_5d_2sm(st, &args.a_hi, &full_bar[stage], 0, cx, cy, kc, cn);
+              else tma_load_4d_2sm(st, &args.a_hi, &full_bar[stage], kc * kBlockK, cx, cy, cn);
               tma_load_2d_2sm(st + 2 * kG2ABytes, &args.b_hi, &full_bar[stage], kb * kBlockK, brow);
               if (args.split) {
-                tma_load_4d_2sm(st + kG2ABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
+                if (args.a_kblock_major)
+                  tma_load_5d_2sm(st + kG2ABytes, &args.a_lo, &full_bar[stage], 0, cx, cy, kc, cn);
+                else tma_load_4d_2sm(st + kG2ABytes, &args.a_lo, &full_bar[stage], kc * kBlockK, cx, cy, cn);
                 tma_load_2d_2sm(st + 2 * kG2ABytes + kG2BBytes, &args.b_lo, &full_bar[stage], kb * kBlockK, brow);
               }
               if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
@@ -661,6 +675,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;
       const float* arow = args.addend ? args.addend + (gm % args.addend_rows) * args.Cout : nullptr;
       float* yrow = args.y + static_cast<size_t>(plane) * args.y_plane_stride + gm * args.Cout;
+      // slab-major M (Winograd): [image][Cout / 32][tiles per image][32]
+      const size_t simg = args.y_slab_tiles ? gm / args.y_slab_tiles : 0;
+      const size_t stile = args.y_slab_tiles ? gm - simg * args.y_slab_tiles : 0;
+      float* ybase = args.y + static_cast<size_t>(plane) * args.y_plane_stride +
+                     simg * static_cast<size_t>(args.Cout) * args.y_slab_tiles + stile * 32;
       float* srow = args.stats ? args.stats + (static_cast<size_t>(m_tile) * 4 + q) * args.Cout * 2 : nullptr;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -677,7 +696,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
               v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
             }
           }
-          store_row32(yrow + n0, v);
+          store_row32(args.y_slab_tiles ? ybase + static_cast<size_t>(n0 >> 5) * args.y_slab_tiles * 32 : yrow + n0, v);
           if (srow) {
             float t[32];
 #pragma unroll
@@ -1213,13 +1232,13 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   a.tiles_per_img = tiles / kBlockM;
   a.num_m_tiles = d->B * a.tiles_per_img;
   const bool two_cta = (d->flags & TSNET_CONV_ONE_CTA) == 0 && a.num_m_tiles % 2 == 0;
-  {
-    const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->TW, (uint64_t)d->TH, (uint64_t)d->B * 16};
-    const uint64_t str[3] = {(uint64_t)d->C * 2, (uint64_t)d->TW * d->C * 2, (uint64_t)tiles * d->C * 2};
-    const uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)rows, 1};
-    int r = encode_tmap_u16_sw128(&a.a_hi, v_hi, 4, dims, str, box);
+  {  // V, K-block-major: [B * 16][C / 64][TH][TW][64]
+    const uint64_t dims[5] = {64, (uint64_t)d->TW, (uint64_t)d->TH, (uint64_t)d->C / 64, (uint64_t)d->B * 16};
+    const uint64_t str[4] = {128, (uint64_t)d->TW * 128, (uint64_t)tiles * 128, (uint64_t)(d->C / 64) * tiles * 128};
+    const uint32_t box[5] = {64, (uint32_t)Wt, (uint32_t)rows, 1, 1};
+    int r = encode_tmap_u16_sw128(&a.a_hi, v_hi, 5, dims, str, box);
     if (r) return r;
-    if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, v_lo, 4, dims, str, box))) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.a_lo, v_lo, 5, dims, str, box))) return r;
   }
   {
     const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)16 * d->Cout};
@@ -1245,6 +1264,8 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   a.batch_planes = 16;
   a.b_plane_rows = d->Cout;
   a.y_plane_stride = static_cast<long long>(d->B) * tiles * d->Cout;
+  a.a_kblock_major = 1;
+  a.y_slab_tiles = tiles;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return two_cta ? launch_conv_gemm2(a, s) : launch_conv_gemm<256>(a, s);
 }

@@ -72,6 +72,19 @@ TSNET_HD int wino_reflect(int i, int n) {
 
 constexpr int kWinoRun = 8;  // tiles one thread walks along a tile row (= 32 output pixels = one statistics partial)
 
+// Winograd-domain layouts in HBM (both chosen so that a pass that owns an (image, channel slab) pair streams contiguous
+// memory, and so that the plane GEMMs read / write whole 128-byte lines):
+//   V (16-bit hi and lo operands of the plane GEMMs)  [B][16 planes][Cp / 64 K blocks][T tiles][64]   (K-block-major)
+//   M (fp32 results of the plane GEMMs)               [16 planes][B][C / 32 slabs][T tiles][32]       (slab-major)
+constexpr int kWinoMSlab = 32;
+TSNET_HD size_t wino_v_index(int b, int p, int T, int Cp_total, int tile, int cc) {
+  return (((static_cast<size_t>(b) * 16 + p) * (Cp_total >> 6) + (cc >> 6)) * T + tile) * 64 + (cc & 63);
+}
+TSNET_HD size_t wino_m_index(int B, int C, int T, int p, int b, int tile, int c) {
+  return (((static_cast<size_t>(p) * B + b) * (C / kWinoMSlab) + c / kWinoMSlab) * T + tile) * kWinoMSlab +
+         (c % kWinoMSlab);
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights: one thread per (o, c).  fp64 arithmetic, fp32 result [16][Cout][Cin].
 // ------------------------------------------------------------------------------------------------
@@ -108,7 +121,7 @@ struct WinoInArgs {
   const float* mean_rstd;  // [B, C, 2] or null
   const float* residual;   // fp32 [B, H, W, C] or null
   float* act_out;          // fp32 [B, H, W, act_C_total] window [act_c_off, +C) or null
-  uint16_t* hi;            // [B, 16, H/2, W/2, Cp_total] window [c_off, +C)
+  uint16_t* hi;            // V layout (wino_v_index), channel window [c_off, +C) of Cp_total
   uint16_t* lo;
   int B, H, W, C, relu, Cp_total, c_off, fmt, act_C_total, act_c_off;
   float scale;
@@ -143,6 +156,37 @@ TSNET_HD void wino_store_plane(const WinoInArgs& a, size_t d, const f4& v) {
     a.hi[d + j] = h[j];
     a.lo[d + j] = l[j];
   }
+#endif
+}
+
+// Store the 16 planes of one tile with ONE running (hi, lo) pointer pair that advances by the plane stride: keeps the
+// compiler from materialising 32 destination pointers at once (176 bytes of spills in the bridge kernel otherwise).
+struct WinoPlaneWriter {
+  uint16_t* ph;
+  uint16_t* pl;
+  size_t pstride;
+  float scale;
+  int fmt;
+};
+TSNET_HD void wino_write_next(WinoPlaneWriter& w, const f4& v) {
+  uint16_t h[4], l[4];
+  wino_split16(v.x * w.scale, w.fmt, h[0], l[0]);
+  wino_split16(v.y * w.scale, w.fmt, h[1], l[1]);
+  wino_split16(v.z * w.scale, w.fmt, h[2], l[2]);
+  wino_split16(v.w * w.scale, w.fmt, h[3], l[3]);
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint2*>(w.ph) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+  *reinterpret_cast<uint2*>(w.pl) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+  w.ph += w.pstride;
+  w.pl += w.pstride;
+  asm volatile("" : "+l"(w.ph), "+l"(w.pl));  // sequential dependence: no precomputed pointer table
+#else
+  for (int j = 0; j < 4; ++j) {
+    w.ph[j] = h[j];
+    w.pl[j] = l[j];
+  }
+  w.ph += w.pstride;
+  w.pl += w.pstride;
 #endif
 }
 
@@ -191,17 +235,17 @@ TSNET_HD void wino_input_body(const WinoInArgs& a, int block, int thread, int nt
       wino_in_column(a, b, ys, 2 * tx + 1, true, c, mean, rstd, t[2]);
       const int x3 = 2 * tx + 2;
       wino_in_column(a, b, ys, wino_reflect(x3, a.W), x3 < 2 * tx1 && x3 < a.W, c, mean, rstd, t[3]);
-      const size_t tile = (static_cast<size_t>(b) * 16 * TH + ty) * TW + tx;  // plane 0; plane p adds p * TH * TW
-      const size_t pstride = static_cast<size_t>(TH) * TW * a.Cp_total;
-      const size_t d0 = tile * a.Cp_total + a.c_off + c;
+      const size_t pstride = static_cast<size_t>(TH) * TW * a.Cp_total;  // one plane of one image
+      const size_t d0 = wino_v_index(b, 0, TH * TW, a.Cp_total, ty * TW + tx, a.c_off + c);
+      WinoPlaneWriter w{a.hi + d0, a.lo + d0, pstride, a.scale, a.fmt};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (int i = 0; i < 4; ++i) {
-        wino_store_plane(a, d0 + (i * 4 + 0) * pstride, f4_sub(t[0][i], t[2][i]));
-        wino_store_plane(a, d0 + (i * 4 + 1) * pstride, f4_add(t[1][i], t[2][i]));
-        wino_store_plane(a, d0 + (i * 4 + 2) * pstride, f4_sub(t[2][i], t[1][i]));
-        wino_store_plane(a, d0 + (i * 4 + 3) * pstride, f4_sub(t[1][i], t[3][i]));
+      for (int i = 0; i < 4; ++i) {  // planes p = 4 i + j in order
+        wino_write_next(w, f4_sub(t[0][i], t[2][i]));
+        wino_write_next(w, f4_add(t[1][i], t[2][i]));
+        wino_write_next(w, f4_sub(t[2][i], t[1][i]));
+        wino_write_next(w, f4_sub(t[1][i], t[3][i]));
       }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -216,7 +260,7 @@ TSNET_HD void wino_input_body(const WinoInArgs& a, int block, int thread, int nt
 
 // ------------------------------------------------------------------------------------------------
 // pass I: output transform + bias (+ addend) + InstanceNorm partial statistics.
-// M fp32 [16][B * TH * TW][C]; y fp32 [B, H, W, C]; stats [B * H*W/32, C, 2] = (sum, centred M2) of 32 pixels:
+// M fp32 in the slab-major layout (wino_m_index); y fp32 [B, H, W, C]; stats [B * H*W/32, C, 2] = (sum, centred M2) of 32 pixels:
 // a thread's kWinoRun = 8 tiles along one tile row are exactly one partial (2 rows x 16 pixels).
 // ------------------------------------------------------------------------------------------------
 struct WinoOutArgs {
@@ -261,8 +305,7 @@ TSNET_HD void wino_output_body(const WinoOutArgs& a, int block, int thread, int 
 #endif
     for (int t = 0; t < kWinoRun; ++t) {
       const int tx = run * kWinoRun + t;
-      const size_t tile = (static_cast<size_t>(b) * TH + ty) * TW + tx;
-      const float* mp = a.m + tile * a.C + c;
+      const float* mp = a.m + wino_m_index(a.B, a.C, TH * TW, 0, b, ty * TW + tx, c);
       f4 z[2][4];  // A^T M: rows a = 0, 1; columns j
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -313,27 +356,25 @@ TSNET_HD void wino_output_body(const WinoOutArgs& a, int block, int thread, int 
 // bridge pass "I+T": output transform of layer k, InstanceNorm, [ReLU | + residual], input transform of layer k+1 in ONE
 // pass over HBM -- M[k] is read once, V[k+1] is written once; the fp32 conv output, its statistics partials and the
 // separate instnorm_reduce launch disappear.  One CTA = one image x a slab of kBridgeCS channels: the whole H x W x CS
-// conv output lives in shared memory (96 KB at 32 x 32 x 16 with padding), so the per-(image, channel) statistics are
-// CTA-local.
+// conv output lives in shared memory (128 KB at 32 x 32 x 32), so the per-(image, channel) statistics are
+// CTA-local.  (A 16-channel variant with two CTAs per SM was measured slower: 204 vs 164 us on the 32-sample layer.)
 // Phases (block-wide barriers between them; the host emulation runs each phase for every thread in turn):
 //   A  y = A^T M A + bias (+ addend)                      -> shared memory
 //   S  per-channel sum / sum of squares in fp64, fixed order -> mean, 1/sqrt(var + eps)   (S1 partials, S2 merge)
 //   B  v = (y - mean) * rstd ; ReLU ; + residual ; act_out  -> shared memory (in place) and optional fp32 output
 //   C  reflect pad + B^T d B + hi/lo split                  -> the 16 operand planes of the next plane GEMMs
 // ------------------------------------------------------------------------------------------------
-constexpr int kBridgeCS = 16;  // channels per CTA: 64 KB image buffer -> two CTAs per SM, whose read-heavy (A) and
-                               // write-heavy (C) phases overlap (one CTA per SM with 32 channels ran at 3.8 TB/s)
-constexpr int kBridgePS = 24;  // shared-memory pixel stride in floats (16 channels + 8 pad): the 64-byte groups that the
-                               // lanes of a warp touch (pixels 2 apart in A / C, adjacent in B) alternate bank halves
+constexpr int kBridgeCS = kWinoMSlab;  // channels per CTA = one M slab: phase A streams 32 KB contiguous per plane
+constexpr int kBridgePS = 32;          // shared-memory pixel stride in floats (8 lanes per pixel cover all 32 banks)
 
 struct WinoBridgeArgs {
-  const float* m;         // fp32 [16][B * TH * TW][C]
+  const float* m;         // fp32, slab-major (wino_m_index)
   const float* bias;      // [C] or null
   const float* addend;    // fp32 [addend_rows, C] or null
   const float* residual;  // fp32 [B, H, W, C] or null
   float* act_out;         // fp32 [B, H, W, act_C_total] window [act_c_off, +C) or null
   float* mean_rstd_out;   // [B, C, 2] or null (tests / diagnostics)
-  uint16_t* hi;           // [B, 16, H/2, W/2, Cp_total] window [c_off, +C)
+  uint16_t* hi;           // V layout (wino_v_index), channel window [c_off, +C) of Cp_total
   uint16_t* lo;
   int B, H, W, C, relu, Cp_total, c_off, fmt, act_C_total, act_c_off;
   long long addend_rows;
@@ -356,7 +397,7 @@ TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread
     const int tile = u / CQ, cq = u - tile * CQ;
     const int ty = tile / TW, tx = tile - ty * TW;
     const int c = slab * kBridgeCS + cq * 4;
-    const float* mp = a.m + (static_cast<size_t>(b) * T + tile) * a.C + c;
+    const float* mp = a.m + wino_m_index(a.B, a.C, T, 0, b, tile, c);
     f4 bias = f4{0.f, 0.f, 0.f, 0.f};
     if (a.bias) bias = ld_f4(a.bias + c);
     f4 z[2][4];
@@ -441,22 +482,43 @@ TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread
   const int b = block / slabs, slab = block - b * slabs;
   const int HW = a.H * a.W;
   constexpr int CQ = kBridgeCS / 4;
-  for (int u = thread; u < HW * CQ; u += nthreads) {
-    const int pix = u / CQ, cq = u - pix * CQ;
-    float* sp = s_y + static_cast<size_t>(pix) * kBridgePS + cq * 4;
-    f4 v = ld_f4(sp);
-    const f4 m01 = ld_f4(s_mr + cq * 8), m23 = ld_f4(s_mr + cq * 8 + 4);  // (mean, rstd) x 4 channels
-    v.x = (v.x - m01.x) * m01.y; v.y = (v.y - m01.z) * m01.w;
-    v.z = (v.z - m23.x) * m23.y; v.w = (v.w - m23.z) * m23.w;
-    if (a.relu) {
-      v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
-      v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+  const int total = HW * CQ;
+  constexpr int kPB = 4;
+  // kPB units per trip: the (dependent-latency) residual loads of a trip are issued together
+  for (int u0 = thread; u0 < total; u0 += kPB * nthreads) {
+    f4 res[kPB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kPB; ++k) {
+      const int u = u0 + k * nthreads;
+      res[k] = f4{0.f, 0.f, 0.f, 0.f};
+      if (a.residual && u < total) {
+        const int pix = u / CQ, cq = u - pix * CQ;
+        res[k] = ld_f4(a.residual + (static_cast<size_t>(b) * HW + pix) * a.C + slab * kBridgeCS + cq * 4);
+      }
     }
-    const size_t gp = static_cast<size_t>(b) * HW + pix;
-    const int c = slab * kBridgeCS + cq * 4;
-    if (a.residual) v = f4_add(v, ld_f4(a.residual + gp * a.C + c));
-    st_f4(sp, v);
-    if (a.act_out) st_f4(a.act_out + gp * a.act_C_total + a.act_c_off + c, v);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < kPB; ++k) {
+      const int u = u0 + k * nthreads;
+      if (u >= total) continue;
+      const int pix = u / CQ, cq = u - pix * CQ;
+      float* sp = s_y + static_cast<size_t>(pix) * kBridgePS + cq * 4;
+      f4 v = ld_f4(sp);
+      const f4 m01 = ld_f4(s_mr + cq * 8), m23 = ld_f4(s_mr + cq * 8 + 4);  // (mean, rstd) x 4 channels
+      v.x = (v.x - m01.x) * m01.y; v.y = (v.y - m01.z) * m01.w;
+      v.z = (v.z - m23.x) * m23.y; v.w = (v.w - m23.z) * m23.w;
+      if (a.relu) {
+        v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+        v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+      }
+      if (a.residual) v = f4_add(v, res[k]);
+      st_f4(sp, v);
+      if (a.act_out)
+        st_f4(a.act_out + (static_cast<size_t>(b) * HW + pix) * a.act_C_total + a.act_c_off + slab * kBridgeCS + cq * 4, v);
+    }
   }
 }
 
@@ -486,17 +548,16 @@ TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread
       t[sx][2] = f4_sub(d2, d1);
       t[sx][3] = f4_sub(d1, d3);
     }
-    WinoInArgs w;  // only the fields wino_store_plane reads
-    w.hi = a.hi; w.lo = a.lo; w.scale = a.scale; w.fmt = a.fmt;
-    const size_t d0 = ((static_cast<size_t>(b) * 16 * TH + ty) * TW + tx) * a.Cp_total + a.c_off + slab * kBridgeCS + cq * 4;
+    const size_t d0 = wino_v_index(b, 0, T, a.Cp_total, tile, a.c_off + slab * kBridgeCS + cq * 4);
+    WinoPlaneWriter w{a.hi + d0, a.lo + d0, pstride, a.scale, a.fmt};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 4; ++i) {
-      wino_store_plane(w, d0 + (i * 4 + 0) * pstride, f4_sub(t[0][i], t[2][i]));
-      wino_store_plane(w, d0 + (i * 4 + 1) * pstride, f4_add(t[1][i], t[2][i]));
-      wino_store_plane(w, d0 + (i * 4 + 2) * pstride, f4_sub(t[2][i], t[1][i]));
-      wino_store_plane(w, d0 + (i * 4 + 3) * pstride, f4_sub(t[1][i], t[3][i]));
+    for (int i = 0; i < 4; ++i) {  // planes p = 4 i + j in order
+      wino_write_next(w, f4_sub(t[0][i], t[2][i]));
+      wino_write_next(w, f4_add(t[1][i], t[2][i]));
+      wino_write_next(w, f4_sub(t[2][i], t[1][i]));
+      wino_write_next(w, f4_sub(t[1][i], t[3][i]));
     }
   }
 }

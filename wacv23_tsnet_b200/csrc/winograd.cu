@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(256, 3) wino_output_kernel(const WinoOutArgs a
   wino_output_body(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
-constexpr int kBridgeThreads = 256;
-__global__ void __launch_bounds__(kBridgeThreads, 2) wino_bridge_kernel(const WinoBridgeArgs a) {
+constexpr int kBridgeThreads = 512;
+__global__ void __launch_bounds__(kBridgeThreads, 1) wino_bridge_kernel(const WinoBridgeArgs a) {
   extern __shared__ __align__(16) uint8_t bridge_smem[];
   float* s_y = reinterpret_cast<float*>(bridge_smem);
   double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * kBridgePS * 4);
@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kBridgeThreads, 2) wino_bridge_kernel(const Wi
 int launch_wino_input(const WinoInArgs& a, cudaStream_t stream) {
   TSNET_ARG_CHECK(a.H % 2 == 0 && a.W % 2 == 0 && a.H >= 4 && a.W >= 4, "build_taps(WINO): H, W must be even, >= 4");
   TSNET_ARG_CHECK(a.C % 4 == 0, "build_taps(WINO): C %d must be a multiple of 4", a.C);
+  TSNET_ARG_CHECK(a.Cp_total % 64 == 0, "build_taps(WINO): Cp_total %d must be a multiple of 64", a.Cp_total);
   TSNET_ARG_CHECK(a.hi && a.lo, "build_taps(WINO): needs the hi / lo destination");
   const unsigned rows = static_cast<unsigned>(a.B) * (a.H / 2);
   wino_input_kernel<<<rows, 256, 0, stream>>>(a);
@@ -65,7 +66,7 @@ extern "C" int tsnet_wino_output(const float* m, int B, int H, int W, int C, con
   TSNET_ARG_CHECK(m && y_raw, "wino_output: null argument");
   TSNET_ARG_CHECK(H % 2 == 0 && W % 2 == 0 && (W / 2) % kWinoRun == 0, "wino_output: W/2 = %d must be a multiple of %d",
                   W / 2, kWinoRun);
-  TSNET_ARG_CHECK(C % 4 == 0, "wino_output: C %d must be a multiple of 4", C);
+  TSNET_ARG_CHECK(C % kWinoMSlab == 0, "wino_output: C %d must be a multiple of %d", C, kWinoMSlab);
   TSNET_ARG_CHECK(!addend || addend_rows > 0, "wino_output: addend needs addend_rows > 0");
   WinoOutArgs a;
   a.m = m; a.bias = bias; a.addend = addend; a.y = y_raw; a.stats = stats_partial;
@@ -82,8 +83,8 @@ extern "C" int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m
   TSNET_ARG_CHECK(d && m && v_hi && v_lo, "wino_bridge: null argument");
   TSNET_ARG_CHECK(d->H % 2 == 0 && d->W % 2 == 0 && d->H >= 4 && d->W >= 4, "wino_bridge: H, W must be even, >= 4");
   TSNET_ARG_CHECK(d->C > 0 && d->C % kBridgeCS == 0, "wino_bridge: C %d must be a multiple of %d", d->C, kBridgeCS);
-  TSNET_ARG_CHECK(d->Cp_total % 4 == 0 && d->c_off % 4 == 0 && d->c_off + d->C <= d->Cp_total,
-                  "wino_bridge: operand channel window does not fit");
+  TSNET_ARG_CHECK(d->Cp_total % 64 == 0 && d->c_off % 4 == 0 && d->c_off + d->C <= d->Cp_total,
+                  "wino_bridge: operand channel window does not fit (Cp_total must be a multiple of 64)");
   TSNET_ARG_CHECK(!addend || d->addend_rows > 0, "wino_bridge: addend needs addend_rows > 0");
   const int actC = d->act_C_total > 0 ? d->act_C_total : d->C;
   TSNET_ARG_CHECK(!act_out || (actC % 4 == 0 && d->act_c_off % 4 == 0 && d->act_c_off + d->C <= actC),

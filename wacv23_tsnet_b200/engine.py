@@ -41,8 +41,10 @@ class ForwardEngine:
         # 2 -> 0.572 ms / 6.4e-7 of max|ref| vs an fp64 conv; 4 -> 0.503 ms / 1.1e-6; 8 (no promotion) -> 0.474 ms / 2.1e-6
         # Whole-forward parity (tools/parity_report.py, worst of the 7 goldens, tolerance 1e-3 / 5e-5): chunk 2 -> image
         # 8.7e-4, grids 2.4e-5 (the direct path: 9.3e-4 / 2.3e-5); chunk 4 -> 1.07e-3 / 2.6e-5; chunk 8 -> 1.3e-3 / 3.4e-5.
-        # The default is therefore 2, as in tsnet_conv_gemm_fwd; an int, or a dict {net name: chunk} with key "default".
-        self.wino_chunk_kb = 2
+        # The error is set by the 18-convolution img_enc chain: chunk 2 there and chunk 4 in FuseNet / decoder gives exactly
+        # the all-2 worst case (8.749e-4 / 2.44e-5), while chunk 4 in img_enc alone already gives 1.07e-3.  Default: that
+        # mix.  The value is an int, or a dict {net name: chunk} with key "default".
+        self.wino_chunk_kb = {"img_enc": 2, "default": 4}
         self._packs = {}
         self._coord = {}
         self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))

@@ -142,6 +142,13 @@ class PackedWino:
         _count()
 
 
+def wino_v_logical(t):
+    """Operand planes as stored by build_taps(TAPS_WINO) / wino_bridge -- K-block-major, [B*16][Cp/64][TH][TW][64], kept
+    in a tensor of bookkeeping shape [B*16, TH, TW, Cp] -- re-ordered to the logical [B*16, TH, TW, Cp] (tests)."""
+    B16, TH, TW, Cp = t.shape
+    return t.reshape(B16, Cp // 64, TH, TW, 64).permute(0, 2, 3, 1, 4).reshape(B16, TH, TW, Cp)
+
+
 def wino_ok(H, W, Cin, Cout):
     """Shapes the Winograd path covers: every ResnetBlock convolution of the network (32 x 32, 512 / 1024 channels)."""
     return (H % 2 == 0 and W % 2 == 0 and ((H // 2) * (W // 2)) % 128 == 0 and (W // 2) % 8 == 0 and
