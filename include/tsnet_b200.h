@@ -112,6 +112,8 @@ typedef struct {
 #define TSNET_CONV_NO_VR 1         /* kw-folded stems: plain implicit-GEMM kernel instead of the vertical-reuse one  */
 #define TSNET_CONV_NO_TAIL_SPLIT 2 /* no second launch with block_n / 2 for the last partial wave                    */
 #define TSNET_CONV_ONE_CTA 4       /* block_n = 256: 1-CTA kernel instead of the default cta_group::2 pair kernel     */
+#define TSNET_CONV_SMALL_FIRST 8   /* tsnet_wino_gemm_fwd only (changes rounding, not the function): per K block issue the
+                                      hi*lo and lo*hi MMAs before the hi*hi ones (truncation-error experiment)          */
 
 int tsnet_conv_gemm_fwd(const tsnet_conv_desc* d, const uint16_t* taps_hi, const uint16_t* taps_lo,
                         const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
@@ -136,7 +138,7 @@ typedef struct {
   int split, fmt;
   float out_scale;  /* 1 / (weight scale * activation scale) */
   int chunk_kb;     /* 0 = default (2 K blocks per TMEM chunk in split mode) */
-  int flags;        /* TSNET_CONV_ONE_CTA */
+  int flags;        /* TSNET_CONV_ONE_CTA, TSNET_CONV_SMALL_FIRST */
 } tsnet_wino_gemm_desc;
 
 int tsnet_wino_weight_transform(const float* w_oihw, int Cout, int Cin, float* u_out, void* stream);

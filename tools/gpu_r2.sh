@@ -43,6 +43,9 @@ for st in $STAGES; do
     parity_mix)
       timeout 700 python tools/parity_report.py --winograd bridge --chunk-kb 2 img_enc=2,default=4 img_enc=4,default=2 3 > $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
+    parity_sf)
+      timeout 900 python tools/parity_report.py --winograd bridge --small-first --chunk-kb img_enc=2,default=4 img_enc=3,default=4 4 > $OUT/parity_$TAG.log 2>&1
+      grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
     bench_c4)
       timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
       cut -c1-300 $OUT/bench_c4_$TAG.json ;;

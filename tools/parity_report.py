@@ -11,6 +11,7 @@ from wacv23_tsnet_b200.model.TSNet_pose import TSNet as TSNetPose
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--winograd", default="bridge")
+ap.add_argument("--small-first", dest="small_first", action="store_true")
 ap.add_argument("--chunk-kb", dest="chunk_kb", nargs="*", default=["2"],
                 help="ints, or per-net specs like img_enc=2,default=4")
 args = ap.parse_args()
@@ -25,6 +26,7 @@ for ck in args.chunk_kb:
         with contextlib.redirect_stdout(io.StringIO()):
             net = cls(is_train=False, label_nc=cfg["label_nc"], n_blocks=cfg["n_blocks"], n_downsampling=3,
                       n_source=cfg["n_source"], winograd=wino, **kw)
+        net._engine.wino_flags = 8 if args.small_first else 0
         net._engine.wino_chunk_kb = (int(ck) if ck.isdigit() else
                                      {kv.split("=")[0]: int(kv.split("=")[1]) for kv in ck.split(",")})
         for k in ("img_enc", "lbl_enc", "fuse_net", "dec"):
@@ -37,5 +39,5 @@ for ck in args.chunk_kb:
         ie = float((net.rec_tar_img.cpu() - t(gold["rec_tar_img"])).abs().max())
         ge = 0.0 if cfg["pose"] else float((torch.stack(net.warp_grid2d_list).cpu() - t(gold["grids"])).abs().max())
         worst_i, worst_g = max(worst_i, ie), max(worst_g, ge)
-        print(f"winograd={args.winograd} chunk_kb={ck} {name}: img {ie:.3e} grid {ge:.3e}", flush=True)
-    print(f"winograd={args.winograd} chunk_kb={ck} WORST: img {worst_i:.3e} (tol 1e-3) grid {worst_g:.3e} (tol 5e-5)", flush=True)
+        print(f"winograd={args.winograd} small_first={args.small_first} chunk_kb={ck} {name}: img {ie:.3e} grid {ge:.3e}", flush=True)
+    print(f"winograd={args.winograd} small_first={args.small_first} chunk_kb={ck} WORST: img {worst_i:.3e} (tol 1e-3) grid {worst_g:.3e} (tol 5e-5)", flush=True)

@@ -56,6 +56,11 @@ struct alignas(64) ConvGemmArgs {
   // tensor map), and M is written slab-major, [16][B][Cout / 32][tiles per image][32], so that the transform passes, which
   // own (image, channel slab) pairs, stream contiguous memory (y_slab_tiles = tiles per image; 0 = plain [M, Cout])
   int a_kblock_major, y_slab_tiles;
+  // MMA issue order inside a K block (split mode).  0: per k step hi*hi, hi*lo, lo*hi.  1 ("small terms first"): the
+  // four hi*lo, then the four lo*hi, then the four hi*hi MMAs: tcgen05 truncates the fp32 accumulator after every MMA,
+  // and the error of a truncation scales with the accumulator's magnitude at that moment -- the 2^-11-sized terms of
+  // the first K block of a chunk are then accumulated while the accumulator is still small.
+  int small_first;
   // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
   const float* f_residual;   // fp32 [B, H, W, Cout] or null
   float* f_act_out;          // fp32, channel window [f_act_c_off, +Cout) of f_act_C_total, or null
@@ -255,13 +260,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes);
             const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
             if (elect_one()) {  // one election per K block: the 12 MMAs are issued back to back by the leader
+              if (args.split && args.small_first) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint32_t off = k * kUmmaK * 2;
-                umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
-                if (args.split) {
-                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16(d_tmem, desc_advance_k(a_hi, k * kUmmaK * 2), desc_advance_k(b_lo, k * kUmmaK * 2), idesc,
+                           ((kb - kb0) | k) != 0);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16(d_tmem, desc_advance_k(a_lo, k * kUmmaK * 2), desc_advance_k(b_hi, k * kUmmaK * 2), idesc, 1);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16(d_tmem, desc_advance_k(a_hi, k * kUmmaK * 2), desc_advance_k(b_hi, k * kUmmaK * 2), idesc, 1);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  const uint32_t off = k * kUmmaK * 2;
+                  umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                  if (args.split) {
+                    umma_f16(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
                 }
               }
             }
@@ -618,13 +636,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
             const uint64_t b_hi = make_desc_kmajor_sw128(st + 2 * kG2ABytes);
             const uint64_t b_lo = make_desc_kmajor_sw128(st + 2 * kG2ABytes + kG2BBytes);
             if (elect_one()) {
+              if (args.split && args.small_first) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint32_t off = k * kUmmaK * 2;
-                umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
-                if (args.split) {
-                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
-                  umma_f16_2sm(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, k * kUmmaK * 2), desc_advance_k(b_lo, k * kUmmaK * 2), idesc,
+                               ((kb - kb0) | k) != 0);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_lo, k * kUmmaK * 2), desc_advance_k(b_hi, k * kUmmaK * 2), idesc, 1);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, k * kUmmaK * 2), desc_advance_k(b_hi, k * kUmmaK * 2), idesc, 1);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  const uint32_t off = k * kUmmaK * 2;
+                  umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_hi, off), idesc, ((kb - kb0) | k) != 0);
+                  if (args.split) {
+                    umma_f16_2sm(d_tmem, desc_advance_k(a_hi, off), desc_advance_k(b_lo, off), idesc, 1);
+                    umma_f16_2sm(d_tmem, desc_advance_k(a_lo, off), desc_advance_k(b_hi, off), idesc, 1);
+                  }
                 }
               }
               umma_commit_2sm(&empty_bar[stage]);  // frees the stage in BOTH CTAs once these MMAs have read it
@@ -1266,6 +1297,7 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   a.y_plane_stride = static_cast<long long>(d->B) * tiles * d->Cout;
   a.a_kblock_major = 1;
   a.y_slab_tiles = tiles;
+  a.small_first = (d->flags & TSNET_CONV_SMALL_FIRST) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return two_cta ? launch_conv_gemm2(a, s) : launch_conv_gemm<256>(a, s);
 }

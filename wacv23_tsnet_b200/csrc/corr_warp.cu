@@ -3,7 +3,7 @@
 //
 // Three kernels, all enqueued on the caller's stream:
 //
-//  P  corr_sort_kernel (one block per mask) + corr_plan_kernel (one block per sample)
+//  P  corr_prepare_kernel (one block per sample: class sort of its n_src + 1 masks, then the work list)
 //     masks -> class-sorted order + tile classes + work list
 //     The reference's similarity is (T.S) * (mt*ms + (1-mt)(1-ms)): for the {0,1} bbox masks every pair whose classes
 //     differ has logit EXACTLY 0.  Positions of every map are therefore stably sorted by mask class (1, soft, 0); a
@@ -112,15 +112,15 @@ struct PrepArgs {
   int pair;  // 1: work items cover 256 target rows (two adjacent 128-row tiles) -- the 2-CTA tile kernel
 };
 
-// one block per (map, sample): grid = (B, n_src + 1); blockIdx.y = 0 is the target map
-__global__ void __launch_bounds__(1024) corr_sort_kernel(const PrepArgs a) {
+// class sort of ONE map (q = 0: target, q >= 1: source q - 1) of sample b by the 1024 threads of a block
+__device__ __forceinline__ void corr_sort_map(const PrepArgs& a, const int b, const int q) {
   __shared__ int wc[3][32];
   __shared__ float sv[kCorrMaxHW];
   __shared__ uint16_t sp[kCorrMaxHW];
   __shared__ float wsx[32], wsy[32];
   __shared__ uint8_t w1[32], w0[32];
 
-  const int b = blockIdx.x, q = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int hw = a.hw, runs = hw / kCorrM;
   const bool active = t < hw;  // hw % 256 == 0: warps are entirely active or entirely idle
   const uint32_t lt = (1u << lane) - 1u;
@@ -189,12 +189,14 @@ __global__ void __launch_bounds__(1024) corr_sort_kernel(const PrepArgs a) {
   }
 }
 
-// one block per sample: work list + closed-form states of the skipped (row tile, column chunk) pairs
-__global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
+// work list + closed-form states of the skipped (row tile, column chunk) pairs of sample b (whole block)
+__device__ __forceinline__ void corr_plan_sample(const PrepArgs& a, const int b) {
   __shared__ uint8_t skip_sm[kCorrMaxSrc * 32];
-  __shared__ int kc[12];
+  __shared__ int kc[32];
   __shared__ float2 sums_sm[kCorrMaxSrc * 8];  // (sum x, sum y) of every 128-run of every source map of this sample
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t < 32) kc[t] = 0;
+  __syncthreads();
   const int hw = a.hw, runs = hw / kCorrM, chunks = hw / kCorrN, NS = 2 * chunks;
   const uint32_t lt = (1u << lane) - 1u;
   const int rtiles = a.pair ? runs / 2 : runs;                    // row tiles (pairs of 128-row tiles in pair mode)
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
   if (lane == 0) kc[warp] = __popc(km);
   __syncthreads();
   int kbefore = 0, ktot = 0;
-  for (int ww = 0; ww < 12; ++ww) {
+  for (int ww = 0; ww < 32; ++ww) {
     if (ww < warp) kbefore += kc[ww];
     ktot += kc[ww];
   }
@@ -240,6 +242,18 @@ __global__ void __launch_bounds__(384) corr_plan_kernel(const PrepArgs a) {
       a.state[r * NS + 2 * ch + half] = make_float4(0.f, static_cast<float>(kCorrNC), sm.x, sm.y);
     }
   }
+}
+
+// ONE launch per forward: block b sorts the n_src + 1 maps of sample b one after the other (each sort is a handful of
+// block scans) and then builds the sample's work list.  (Two launches -- a (B, n_src + 1) sort grid and a plan grid --
+// cost 8 + 13 us of device time plus the launch gap for 1 MB of data.)
+__global__ void __launch_bounds__(1024) corr_prepare_kernel(const PrepArgs a) {
+  const int b = blockIdx.x;
+  for (int q = 0; q <= a.n_src; ++q) {
+    corr_sort_map(a, b, q);
+    __syncthreads();  // shared scratch is reused by the next map; cls / sums of this map are visible to the block
+  }
+  corr_plan_sample(a, b);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -813,7 +827,7 @@ __global__ void __launch_bounds__(256) warp_mean_taps_kernel(const WarpTapsArgs 
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
         sy += __shfl_xor_sync(0xffffffffu, sy, o);
       }
-      gxr[grp] = sx / l;
+      gxr[grp] = sx / l;  // (kept as true divisions: the warp grid is an output, warp_grid2d_list)
       gyr[grp] = sy / l;
       if (a.out_grids && slab == 0 && k8 == 0 && i < a.n_src)
         *reinterpret_cast<float2*>(a.out_grids + (static_cast<size_t>(i) * a.B * hw + gpos) * 2) =
@@ -864,11 +878,13 @@ __global__ void __launch_bounds__(256) warp_mean_taps_kernel(const WarpTapsArgs 
       }
     }
   }
-  const float nf = static_cast<float>(a.n_src);
+  // mean over sources (torch.stack(...).mean(1), model/TSNet.py:392) as a multiplication by 1/n: exact for n = 2^k,
+  // within 1 ulp of the reference's division otherwise (8 IEEE division sequences per lane made this kernel issue-bound)
+  const float rn = 1.f / static_cast<float>(a.n_src);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k < nk) {
-      const float v[4] = {accv[k].x / nf, accv[k].y / nf, accv[k].z / nf, accv[k].w / nf};
+      const float v[4] = {accv[k].x * rn, accv[k].y * rn, accv[k].z * rn, accv[k].w * rn};
       const int c = cbase + k * 128;
       if (a.out_mean) *reinterpret_cast<float4*>(a.out_mean + gpos * a.C + c) = make_float4(v[0], v[1], v[2], v[3]);
       if (a.hi) {
@@ -946,9 +962,7 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
   a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
   a.sort = d->sort;
   a.pair = corr_use_2cta(d) ? 1 : 0;
-  corr_sort_kernel<<<dim3(d->B, d->n_src + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_LAUNCH_CHECK();
-  corr_plan_kernel<<<d->B, 384, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  corr_prepare_kernel<<<d->B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
   return 0;
 }

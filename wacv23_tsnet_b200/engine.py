@@ -45,6 +45,7 @@ class ForwardEngine:
         # the all-2 worst case (8.749e-4 / 2.44e-5), while chunk 4 in img_enc alone already gives 1.07e-3.  Default: that
         # mix.  The value is an int, or a dict {net name: chunk} with key "default".
         self.wino_chunk_kb = {"img_enc": 2, "default": 4}
+        self.wino_flags = 0      # tsnet_wino_gemm_desc.flags (experiments: L.CONV_SMALL_FIRST)
         self._packs = {}
         self._coord = {}
         self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))
@@ -111,7 +112,7 @@ class ForwardEngine:
         if taps[2][0] == 16:
             pw = self._pack_wino(net, wkey, cin_range=cin_range, with_bias=with_bias)
             y, stats = ops.wino_conv(taps, pw, B, H, W, self.mode, self.mode.act_scale, want_stats=norm, addend=addend,
-                                     chunk_kb=self._chunk(net))
+                                     chunk_kb=self._chunk(net), flags=self.wino_flags)
             mr = ops.instnorm_reduce(stats, B, H * W, pw.Cout) if norm else None
             return y, mr
         pc = self._pack(net, wkey, cin_range=cin_range, with_bias=with_bias)
@@ -143,7 +144,7 @@ class ForwardEngine:
         if is3 and self.bridge and taps[2][0] == 16 and tmode == L.TAPS_WINO and want_taps:
             # Winograd layer feeding a Winograd layer: GEMM + ONE bridge pass (no y_raw / statistics round trip)
             pw = self._pack_wino(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
-            mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self._chunk(pc[0]))
+            mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self._chunk(pc[0]), flags=self.wino_flags)
             t = ops.wino_bridge(mbuf, pw, B, H, W, m, relu=relu, addend=addend, residual=residual, act_out=act_out,
                                 act_c_off=act_c_off, taps=dest, c_off=c_off)
             return t, act_out

@@ -13,7 +13,7 @@ FMT_FP16, FMT_BF16 = 0, 1
 TAPS_SAME, TAPS_REFLECT1, TAPS_S2ZERO, TAPS_UP2REFLECT1, TAPS_WINO = 0, 1, 2, 3, 4
 MAX_TAPS = 49
 ABI_VERSION = 3
-CONV_NO_VR, CONV_NO_TAIL_SPLIT, CONV_ONE_CTA = 1, 2, 4   # tsnet_conv_desc.flags (launch-plan switches, tests only)
+CONV_NO_VR, CONV_NO_TAIL_SPLIT, CONV_ONE_CTA, CONV_SMALL_FIRST = 1, 2, 4, 8   # tsnet_conv_desc.flags (launch-plan switches, tests only)
 TAPS_GENERIC_UP2 = 1                                     # tsnet_taps_desc.flags
 
 vp = C.c_void_p
