@@ -3,7 +3,7 @@
 //
 // Three kernels, all enqueued on the caller's stream:
 //
-//  P  corr_prepare_kernel (one block per sample: class sort of its n_src + 1 masks, then the work list)
+//  P  corr_prepare_kernel (one block per mask: class sort; the last block of a sample builds its work list)
 //     masks -> class-sorted order + tile classes + work list
 //     The reference's similarity is (T.S) * (mt*ms + (1-mt)(1-ms)): for the {0,1} bbox masks every pair whose classes
 //     differ has logit EXACTLY 0.  Positions of every map are therefore stably sorted by mask class (1, soft, 0); a
@@ -55,7 +55,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 // workspace
 // ---------------------------------------------------------------------------------------------------------------
 struct CorrWs {
-  size_t rank, maskv, cxs, cys, cls, sums, items, counts, state, total;
+  size_t rank, maskv, cxs, cys, cls, sums, items, counts, done, state, total;
 };
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 static CorrWs corr_ws_layout(int B, int n, int hw) {
@@ -70,6 +70,7 @@ static CorrWs corr_ws_layout(int B, int n, int hw) {
   L.sums = o;   o = align256(o + NM * runs * 2 * sizeof(float));                // (sum x, sum y) of every 128-run
   L.items = o;  o = align256(o + static_cast<size_t>(B) * n * runs * chunks * 4);
   L.counts = o; o = align256(o + static_cast<size_t>(B) * 4);
+  L.done = o;   o = align256(o + static_cast<size_t>(B) * 4);             // sorted-map counter per sample (prepare)
   L.state = o;  o = align256(o + static_cast<size_t>(n) * B * hw * 2 * chunks * sizeof(float4));
   L.total = o;
   return L;
@@ -107,6 +108,7 @@ struct PrepArgs {
   float* sums;
   int* items;
   int* counts;
+  int* done;
   float4* state;
   int B, n_src, h, w, hw, bbox_h, bbox_w, bbox_dtype, sort;
   int pair;  // 1: work items cover 256 target rows (two adjacent 128-row tiles) -- the 2-CTA tile kernel
@@ -204,16 +206,16 @@ __device__ __forceinline__ void corr_plan_sample(const PrepArgs& a, const int b)
   if (t < a.n_src * runs) {  // one coalesced read instead of a dependent global load per skipped tile below
     const int i = t / runs, u = t - i * runs;
     const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
-    sums_sm[i * 8 + u] = *reinterpret_cast<const float2*>(a.sums + (smap * runs + u) * 2);
+    sums_sm[i * 8 + u] = __ldcg(reinterpret_cast<const float2*>(a.sums + (smap * runs + u) * 2));  // written by other blocks
   }
   bool keep = false;
   int code = 0;
   if (t < ncand) {  // candidates (source, row tile, column chunk) in lexicographic order
     const int i = t / per_src, rem = t - i * per_src, mt = rem / chunks, ch = rem - mt * chunks;
     const size_t smap = static_cast<size_t>(a.B) + static_cast<size_t>(i) * a.B + b;
-    int rowc = a.cls[static_cast<size_t>(b) * runs + (a.pair ? 2 * mt : mt)];
-    if (a.pair && a.cls[static_cast<size_t>(b) * runs + 2 * mt + 1] != rowc) rowc = 2;
-    const int c0 = a.cls[smap * runs + 2 * ch], c1 = a.cls[smap * runs + 2 * ch + 1];
+    int rowc = __ldcg(a.cls + static_cast<size_t>(b) * runs + (a.pair ? 2 * mt : mt));
+    if (a.pair && __ldcg(a.cls + static_cast<size_t>(b) * runs + 2 * mt + 1) != rowc) rowc = 2;
+    const int c0 = __ldcg(a.cls + smap * runs + 2 * ch), c1 = __ldcg(a.cls + smap * runs + 2 * ch + 1);
     const int colc = c0 == c1 ? c0 : 2;
     const bool skip = (rowc == 1 && colc == 0) || (rowc == 0 && colc == 1);
     skip_sm[t] = skip;
@@ -244,15 +246,24 @@ __device__ __forceinline__ void corr_plan_sample(const PrepArgs& a, const int b)
   }
 }
 
-// ONE launch per forward: block b sorts the n_src + 1 maps of sample b one after the other (each sort is a handful of
-// block scans) and then builds the sample's work list.  (Two launches -- a (B, n_src + 1) sort grid and a plan grid --
-// cost 8 + 13 us of device time plus the launch gap for 1 MB of data.)
+// ONE launch per forward: grid (B, n_src + 1), block (b, q) sorts map q of sample b; the block that finishes LAST for a
+// sample (a per-sample counter in the workspace, zeroed by a memset node ahead of the launch and reset here) builds that
+// sample's work list.  The result does not depend on which block that is.  (A second plan launch cost 13 us of device
+// time plus the launch gap for 1 MB of data; one block per sample sorting its maps serially was slower still: 40 us.)
 __global__ void __launch_bounds__(1024) corr_prepare_kernel(const PrepArgs a) {
+  __shared__ int is_last;
   const int b = blockIdx.x;
-  for (int q = 0; q <= a.n_src; ++q) {
-    corr_sort_map(a, b, q);
-    __syncthreads();  // shared scratch is reused by the next map; cls / sums of this map are visible to the block
+  corr_sort_map(a, b, blockIdx.y);
+  __threadfence();   // this block's rank / class / sum tables are visible device-wide before the counter moves
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&a.done[b], 1);
+    is_last = prev == a.n_src;
+    if (is_last) a.done[b] = 0;
   }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();   // acquire side: the other blocks' tables
   corr_plan_sample(a, b);
 }
 
@@ -957,12 +968,14 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
   a.sums = reinterpret_cast<float*>(ws + L.sums);
   a.items = reinterpret_cast<int*>(ws + L.items);
   a.counts = reinterpret_cast<int*>(ws + L.counts);
+  a.done = reinterpret_cast<int*>(ws + L.done);
   a.state = reinterpret_cast<float4*>(ws + L.state);
   a.B = d->B; a.n_src = d->n_src; a.h = d->h; a.w = d->w; a.hw = hw;
   a.bbox_h = d->bbox_h; a.bbox_w = d->bbox_w; a.bbox_dtype = d->bbox_dtype;
   a.sort = d->sort;
   a.pair = corr_use_2cta(d) ? 1 : 0;
-  corr_prepare_kernel<<<d->B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TSNET_CUDA_CHECK(cudaMemsetAsync(a.done, 0, static_cast<size_t>(d->B) * sizeof(int), static_cast<cudaStream_t>(stream)));
+  corr_prepare_kernel<<<dim3(d->B, d->n_src + 1), 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   TSNET_LAUNCH_CHECK();
   return 0;
 }
