@@ -62,6 +62,8 @@ long long tsnet_launch_count(void);
  * fold_kw = 0: taps = KH*KW (row-major r,s), K per tap = Cp >= Cin, channel c at column tap*Cp + c.
  * fold_kw = 1: taps = KH, K per tap = Cp >= KW*Cin, column tap*Cp + s*Cin + c  (7x7 stems, see
  *              tsnet_stem_taps).  Rows >= Cout and unused columns are zero.
+ * fold_kw = F > 1: as fold_kw = 1 with the channels of every horizontal tap padded to F >= Cin: column
+ *              tap*Cp + s*F + c (tsnet_stem_conv_fwd: F = 8, one 16-byte chunk per tap).
  * scale: weights are multiplied by `scale` (power of two; FP16 mode range management) before the split. */
 int tsnet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, int fold_kw, int Cp,
                            int Cout_pad, float scale, int fmt, uint16_t* w_hi, uint16_t* w_lo, void* stream);
@@ -223,6 +225,26 @@ int tsnet_build_taps(const tsnet_taps_desc* d, const float* raw, const float* me
 int tsnet_stem_taps(const void* img_nchw, int Cimg, int img_kind, const float* img_mean3_host, float img_div,
                     const void* lbl, int Clbl, int lbl_kind, int B, int H, int W, int Cp, int fmt, float scale,
                     uint16_t* taps_hi, uint16_t* taps_lo, void* stream);
+
+/* ---- encoder stem without a materialised operand -----------------------------------------------------------------
+ * ReflectionPad2d(3) + Conv2d(Cin, 64, 7) (model/TSNet.py:66) of both encoders straight from the raw NCHW network inputs:
+ * the kw-folded operand tile of every 8 x 16 output tile is generated in shared memory by producer warps of the
+ * tcgen05 kernel -- torch.cat([img / 255, lbl]) (:312), the datasets' uint8 -> float / mean-subtract / one-hot staging
+ * and Encoder.coord_conv (:107-125) never exist in HBM (tsnet_stem_taps materialises a 1.65 GB operand at bs = 32,
+ * n_source = 3).  Needs Cimg + Clbl + 3 <= 8 (the face configuration: 3 + 2 + 3 and 0 + 2 + 3); the weight is packed
+ * with tsnet_pack_conv_weight(fold_kw = 8).  Larger label sets (pose: 25 classes) use tsnet_stem_taps +
+ * tsnet_conv_gemm_fwd.  img_kind / lbl_kind / img_mean / img_div as in tsnet_stem_taps.  Outputs as tsnet_conv_gemm_fwd. */
+typedef struct {
+  int B, H, W;
+  int Cimg, Clbl, img_kind, lbl_kind;
+  float img_mean[3], img_div;
+  int Cout;          /* 64 */
+  int split, fmt;
+  float act_scale;   /* power-of-two pre-scale of the generated operands */
+  float out_scale;   /* 1 / (weight scale * act_scale) */
+} tsnet_stem_conv_desc;
+int tsnet_stem_conv_fwd(const tsnet_stem_conv_desc* d, const void* img_nchw, const void* lbl, const uint16_t* w_hi,
+                        const uint16_t* w_lo, const float* bias, float* y_raw, float* stats_partial, void* stream);
 
 /* ---- correlation: masks -> class-sorted order, operands, tensor-core tiles, warp + mean -----------------------
  * model/TSNet.py:319-323 (normalise, target mask), :339-366 (per source: normalise, mask, two masked bmm,

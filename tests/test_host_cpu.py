@@ -35,14 +35,15 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_header(built):
     # sizes the C compiler gives the descriptor structs (catches ctypes / header drift without a GPU)
-    src = '#include "tsnet_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(tsnet_conv_desc),' \
+    src = '#include "tsnet_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tsnet_conv_desc),' \
           ' sizeof(tsnet_taps_desc), sizeof(tsnet_corr_desc), sizeof(tsnet_wino_gemm_desc),' \
-          ' sizeof(tsnet_wino_bridge_desc));return 0;}'
+          ' sizeof(tsnet_wino_bridge_desc), sizeof(tsnet_stem_conv_desc));return 0;}'
     exe = "/tmp/tsnet_sizeof"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(built.ConvDesc), ctypes.sizeof(built.TapsDesc), ctypes.sizeof(built.CorrDesc),
-                     ctypes.sizeof(built.WinoGemmDesc), ctypes.sizeof(built.WinoBridgeDesc)]
+                     ctypes.sizeof(built.WinoGemmDesc), ctypes.sizeof(built.WinoBridgeDesc),
+                     ctypes.sizeof(built.StemConvDesc)]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-box behaviour")

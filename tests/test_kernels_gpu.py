@@ -738,3 +738,46 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
     torch.cuda.synchronize()
     assert torch.equal(h2[16:32], h1) and torch.equal(l2[16:32], l1)
     assert torch.equal(vl(h2), vl(hf)[..., 64:]) and torch.equal(vl(l2), vl(lf)[..., 64:])
+
+
+def test_stem_conv_direct_input():
+    """tsnet_stem_conv_fwd: the kw-folded operand tile is generated in shared memory from the raw NCHW inputs (no tap
+    source in HBM).  img_enc (3 + 2 + 3 = 8 channels: the layout equals the materialised one) must be bit-identical to
+    tsnet_stem_taps + the vertical-reuse kernel; lbl_enc (2 + 3 channels padded to 8) is checked against an fp64 conv;
+    uint8 frames + class-index labels give the same bits as their fp32 expansions."""
+    from oracle import tsnet_oracle as O
+    from wacv23_tsnet_b200 import ops
+    m = ops.MathMode("fp16x3")
+    torch.manual_seed(21)
+    B, H, W, Lc = 3, 64, 96, 2
+    u8 = torch.randint(0, 256, (B, 3, H, W), device="cuda", dtype=torch.uint8)
+    mean = (101.848, 112.108, 111.66)
+    img = u8.float() - torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
+    cls = torch.randint(0, Lc, (B, H, W), device="cuda", dtype=torch.uint8)
+    lbl = torch.stack([(cls == c).float() for c in range(Lc)], 1).contiguous()
+    # ---- img_enc stem
+    w = torch.randn(64, 3 + Lc + 3, 7, 7, device="cuda") * 0.02
+    b = torch.randn(64, device="cuda") * 0.1
+    pc_old = ops.PackedConv(w, b, m, fold_kw=True)
+    hi, lo, g = ops.stem_taps(img, 255.0, lbl, pc_old.Cp, m)
+    y_old, st_old = ops.conv_gemm(hi, lo, g, pc_old, "7x1", B, H, W, m, m.act_scale)
+    pc = ops.PackedConv(w, b, m, fold_kw=True, fold_cin=ops.STEM_FOLD)
+    y, st = ops.stem_conv(img, 255.0, lbl, pc, m)
+    y8, st8 = ops.stem_conv(u8, 255.0, cls, pc, m, label_nc=Lc, img_mean=mean)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_old) and torch.equal(st, st_old)
+    assert torch.equal(y8, y) and torch.equal(st8, st)
+    full = O.coord_channels(torch.cat([img.cpu() / 255.0, lbl.cpu()], 1)).cuda()
+    ref = F.conv2d(F.pad(full, (3, 3, 3, 3), mode="reflect").double(), w.double(), b.double()).permute(0, 2, 3, 1).float()
+    assert _relerr(y, ref) < CONV_TOL["fp16x3"]
+    # ---- lbl_enc stem (no image; 5 channels padded to the 8-channel folded tap)
+    w2 = torch.randn(64, Lc + 3, 7, 7, device="cuda") * 0.02
+    pc2 = ops.PackedConv(w2, b, m, fold_kw=True, fold_cin=ops.STEM_FOLD)
+    y2, st2 = ops.stem_conv(None, 1.0, lbl, pc2, m)
+    y2c, _ = ops.stem_conv(None, 1.0, cls, pc2, m, label_nc=Lc)
+    torch.cuda.synchronize()
+    full2 = O.coord_channels(lbl.cpu()).cuda()
+    ref2 = F.conv2d(F.pad(full2, (3, 3, 3, 3), mode="reflect").double(), w2.double(), b.double()).permute(0, 2, 3, 1).float()
+    assert _relerr(y2, ref2) < CONV_TOL["fp16x3"] and torch.equal(y2c, y2)
+    mr = ops.instnorm_reduce(st2, B, H * W, 64)
+    assert _relerr(mr[..., 0], ref2.mean((1, 2))) < 2e-5

@@ -61,6 +61,12 @@ struct alignas(64) ConvGemmArgs {
   // and the error of a truncation scales with the accumulator's magnitude at that moment -- the 2^-11-sized terms of
   // the first K block of a chunk are then accumulated while the accumulator is still small.
   int small_first;
+  // direct stem input (conv_gemm_vr_kernel<true>, tsnet_stem_conv_fwd): the kw-folded halo tile is GENERATED in shared
+  // memory by three producer warps from the raw NCHW network inputs (no tap source in HBM)
+  const void* in_img;
+  const void* in_lbl;
+  int in_Cimg, in_Clbl, in_img_kind, in_lbl_kind;
+  float in_mean[3], in_div, in_scale;
   // fused InstanceNorm epilogue (FUSED kernel variant; needs 8 tiles per image = one 8-CTA cluster per image)
   const float* f_residual;   // fp32 [B, H, W, Cout] or null
   float* f_act_out;          // fp32, channel window [f_act_c_off, +Cout) of f_act_C_total, or null
@@ -797,6 +803,78 @@ constexpr int kVrBTap = kVrN * kBlockK * 2;  // 8 KB: one tap of the packed weig
 // their per-tile epilogue (store + statistics) overlaps tensor work instead of stalling it after 2 chunks
 constexpr int kVrTmemBufs = 8;
 
+constexpr int kStemFold = 8;  // direct mode: channels per folded horizontal tap (Cin <= 8, zero padded): one 16-byte chunk
+
+// Direct-input producer of conv_gemm_vr_kernel<true>: 96 threads (warps 0, 2, 3) build the (8 + 6) x 16 pixel halo tile of
+// one output tile in the 128-byte-swizzled K-major layout a TMA box {64, 16, 14} of the materialised tap source would
+// have produced.  Row R = r * 16 + px of the tile holds, for s = 0..6, the 8-channel vector of source pixel
+// (reflect(y0 - 3 + r), reflect(x0 - 3 + px + s)) in 16-byte chunk s ^ (R & 7); chunk 7 ^ (R & 7) stays zero.  Every
+// source pixel vector (torch.cat([img / 255, lbl]) + CoordConv channels, model/TSNet.py:107-125, :312; same rounding
+// sequence as stem_taps_kernel) is computed once and stored to the <= 7 rows that use it.
+__device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8_t* a_hi, uint8_t* a_lo, int img, int y0,
+                                                 int x0, int pt) {
+  const int H = args.f_H, W = args.f_W;
+  const size_t plane = static_cast<size_t>(H) * W;
+  constexpr int SW = kVrW + 6, SR = kVrRows + 6;
+  for (int idx = pt; idx < SR * SW; idx += 96) {
+    const int r = idx / SW, sx = idx - r * SW;
+    int ys = y0 - 3 + r, xs = x0 - 3 + sx;
+    ys = ys < 0 ? -ys : ys; ys = ys >= H ? 2 * H - 2 - ys : ys;
+    xs = xs < 0 ? -xs : xs; xs = xs >= W ? 2 * W - 2 - xs : xs;
+    const size_t pix = static_cast<size_t>(ys) * W + xs;
+    // Encoder.coord_conv: t = idx / (n - 1); 2 t - 1; r = sqrt(x^2 + y^2), separate roundings
+    const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
+    const float xx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
+    const float rr = __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy)));
+    const int n_img = args.in_Cimg, n_il = args.in_Cimg + args.in_Clbl;
+    int cls = 0;
+    if (args.in_lbl_kind != 0) cls = static_cast<const uint8_t*>(args.in_lbl)[static_cast<size_t>(img) * plane + pix];
+    float v[kStemFold];
+#pragma unroll
+    for (int c = 0; c < kStemFold; ++c) {  // channel c of cat[img / div, lbl, x, y, r, 0...] (warp-uniform branches)
+      float q = 0.f;
+      if (c < n_img) {
+        const size_t off = (static_cast<size_t>(img) * n_img + c) * plane + pix;
+        float x;
+        if (args.in_img_kind == 0) x = static_cast<const float*>(args.in_img)[off];
+        else x = __fadd_rn(static_cast<float>(static_cast<const uint8_t*>(args.in_img)[off]), -args.in_mean[c < 3 ? c : 2]);
+        q = __fdiv_rn(x, args.in_div);
+      } else if (c < n_il) {
+        if (args.in_lbl_kind == 0)
+          q = static_cast<const float*>(args.in_lbl)[(static_cast<size_t>(img) * args.in_Clbl + (c - n_img)) * plane + pix];
+        else
+          q = cls == c - n_img ? 1.f : 0.f;
+      } else if (c == n_il) {
+        q = xx;
+      } else if (c == n_il + 1) {
+        q = yy;
+      } else if (c == n_il + 2) {
+        q = rr;
+      }
+      v[c] = q;
+    }
+    uint16_t h[kStemFold], l[kStemFold];
+#pragma unroll
+    for (int j = 0; j < kStemFold; ++j) split16(v[j] * args.in_scale, args.fmt, h[j], l[j]);
+    uint4 ph, pl;
+    ph.x = h[0] | (uint32_t(h[1]) << 16); ph.y = h[2] | (uint32_t(h[3]) << 16);
+    ph.z = h[4] | (uint32_t(h[5]) << 16); ph.w = h[6] | (uint32_t(h[7]) << 16);
+    pl.x = l[0] | (uint32_t(l[1]) << 16); pl.y = l[2] | (uint32_t(l[3]) << 16);
+    pl.z = l[4] | (uint32_t(l[5]) << 16); pl.w = l[6] | (uint32_t(l[7]) << 16);
+#pragma unroll
+    for (int sft = 0; sft < 7; ++sft) {
+      const int px = sx - sft;
+      if (px >= 0 && px < kVrW) {
+        const int R = r * kVrW + px;
+        const int off = R * 128 + ((sft ^ (R & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = ph;
+        if (args.split) *reinterpret_cast<uint4*>(a_lo + off) = pl;
+      }
+    }
+  }
+}
+
+template <bool DIRECT>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __grid_constant__ ConvGemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -817,17 +895,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
   const int tiles_x = args.wtiles_per_row;  // W / 16
 
   if (warp == 0 && lane_id() == 0) {
-    tma_prefetch_desc(&args.a_hi);
+    if (!DIRECT) tma_prefetch_desc(&args.a_hi);
     tma_prefetch_desc(&args.b_hi);
     if (args.split) {
-      tma_prefetch_desc(&args.a_lo);
+      if (!DIRECT) tma_prefetch_desc(&args.a_lo);
       tma_prefetch_desc(&args.b_lo);
     }
   }
   if (warp == 1 && lane_id() == 0) {
     mbar_init(b_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1);
+      mbar_init(&a_full[i], DIRECT ? 3 : 1);  // direct mode: one arrive per producer warp (0, 2, 3)
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < kVrTmemBufs; ++i) {
@@ -843,8 +921,41 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
+    // control warp group: 40 registers per thread; the direct-input producers (loads + conversions) get 96 -- the
+    // accumulate warps of this N = 64 kernel hold only 32 accumulators and make do with 200 instead of 224
+    if constexpr (DIRECT) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (DIRECT && warp != 1) {
+      // ===================== direct-input producers (warps 0, 2, 3) =====================
+      const int pt = (warp == 0 ? 0 : (warp - 1) * 32) + static_cast<int>(lane_id());
+      if (warp == 0 && lane_id() == 0) {
+        mbar_arrive_expect_tx(b_full, (args.split ? 2u : 1u) * taps * kVrBTap);
+        for (int t = 0; t < taps; ++t) {
+          tma_load_2d(b_sm + t * kVrBTap, &args.b_hi, b_full, t * kBlockK, 0);
+          if (args.split) tma_load_2d(b_sm + (taps + t) * kVrBTap, &args.b_lo, b_full, t * kBlockK, 0);
+        }
+      }
+      // the unused 8th chunk of every row (folded channels 56..63) is zero for the whole kernel, in all four tiles
+      for (int i = pt; i < 4 * (kVrRows + 6) * kVrW; i += 96) {
+        const int tile_i = i / ((kVrRows + 6) * kVrW), R = i - tile_i * ((kVrRows + 6) * kVrW);
+        *reinterpret_cast<uint4*>(a_sm + tile_i * a_bytes + R * 128 + ((7 ^ (R & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int m_tile = args.m_tile_begin + tile;
+        const int img = m_tile / args.tiles_per_img;
+        const int t = m_tile - img * args.tiles_per_img;
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        mbar_wait(&a_empty[buf], ph ^ 1);   // the MMAs of the tile that used this buffer have read it
+        uint8_t* st = a_sm + buf * 2 * a_bytes;
+        stem_direct_fill(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&a_full[buf]);
+      }
+    } else if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane_id() == 0) {
         mbar_arrive_expect_tx(b_full, (args.split ? 2u : 1u) * taps * kVrBTap);
@@ -917,7 +1028,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (DIRECT) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== accumulate + epilogue =====================
     constexpr int NC = kVrN / 2;
     const int q = warp & 3;
@@ -994,13 +1106,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
   }
 }
 
-static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream) {
+static int launch_conv_gemm_vr(const ConvGemmArgs& a, cudaStream_t stream, bool direct = false) {
   const int a_bytes = (kVrRows + a.num_taps - 1) * kVrW * 128;
   const int smem_bytes = 2 * a.num_taps * kVrBTap + 4 * a_bytes + 1024 + 256;
-  static int smem_attr[kMaxDevices] = {0};
-  TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_vr_kernel, smem_bytes, smem_attr));
   const int grid = a.num_m_tiles < num_sms() ? a.num_m_tiles : num_sms();
-  conv_gemm_vr_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(a);
+  if (direct) {
+    static int smem_attr_d[kMaxDevices] = {0};
+    TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_vr_kernel<true>, smem_bytes, smem_attr_d));
+    conv_gemm_vr_kernel<true><<<grid, kGemmThreads, smem_bytes, stream>>>(a);
+  } else {
+    static int smem_attr[kMaxDevices] = {0};
+    TSNET_CUDA_CHECK(ensure_dyn_smem(conv_gemm_vr_kernel<false>, smem_bytes, smem_attr));
+    conv_gemm_vr_kernel<false><<<grid, kGemmThreads, smem_bytes, stream>>>(a);
+  }
   TSNET_LAUNCH_CHECK();
   return 0;
 }
@@ -1300,4 +1418,63 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   a.small_first = (d->flags & TSNET_CONV_SMALL_FIRST) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return two_cta ? launch_conv_gemm2(a, s) : launch_conv_gemm<256>(a, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder stem without a materialised operand: ReflectionPad2d(3) + Conv2d(Cin, 64, 7) (model/TSNet.py:66) straight
+// from the raw NCHW network inputs.  The kw-folded halo tile of every 8 x 16 output tile is built in shared memory by
+// producer warps (conv_gemm_vr_kernel<true>): torch.cat([img / 255, lbl]) (:312), the uint8 -> float / mean-subtract /
+// one-hot staging of the datasets, and Encoder.coord_conv (:107-125) never exist in HBM.
+// ------------------------------------------------------------------------------------------------
+extern "C" int tsnet_stem_conv_fwd(const tsnet_stem_conv_desc* d, const void* img_nchw, const void* lbl,
+                                   const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, float* y_raw,
+                                   float* stats_partial, void* stream) {
+  TSNET_ARG_CHECK(d && lbl && w_hi && y_raw, "stem_conv: null argument");
+  TSNET_ARG_CHECK(!d->split || w_lo, "stem_conv: split mode needs the lo weights");
+  TSNET_ARG_CHECK((img_nchw != nullptr) == (d->Cimg > 0), "stem_conv: img pointer / Cimg mismatch");
+  TSNET_ARG_CHECK(d->Cimg >= 0 && d->Clbl >= 1 && d->Cimg + d->Clbl + 3 <= kStemFold,
+                  "stem_conv: Cimg + Clbl + 3 = %d channels do not fit the %d-channel folded tap (use tsnet_stem_taps + "
+                  "tsnet_conv_gemm_fwd)", d->Cimg + d->Clbl + 3, kStemFold);
+  TSNET_ARG_CHECK(d->img_kind == 0 || (d->img_kind == 1 && d->Cimg == 3), "stem_conv: img_kind %d", d->img_kind);
+  TSNET_ARG_CHECK(d->lbl_kind == 0 || d->lbl_kind == 1, "stem_conv: lbl_kind %d", d->lbl_kind);
+  TSNET_ARG_CHECK(d->Cout == kVrN, "stem_conv: Cout %d (the stem has %d output channels)", d->Cout, kVrN);
+  TSNET_ARG_CHECK(d->H % kVrRows == 0 && d->W % kVrW == 0 && d->H >= 4 && d->W >= 4,
+                  "stem_conv: H %d / W %d must be multiples of %d / %d", d->H, d->W, kVrRows, kVrW);
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  {  // packed weight [64, 7 * 64]: column r * 64 + s * 8 + c (tsnet_pack_conv_weight with fold_kw = 8)
+    const uint64_t K = 7ull * 64;
+    const uint64_t dims[2] = {K, (uint64_t)kVrN};
+    const uint64_t str[1] = {K * 2};
+    const uint32_t box[2] = {64, (uint32_t)kVrN};
+    int r = encode_tmap_u16_sw128(&a.b_hi, w_hi, 2, dims, str, box);
+    if (r) return r;
+    if (d->split && (r = encode_tmap_u16_sw128(&a.b_lo, w_lo, 2, dims, str, box))) return r;
+  }
+  a.bias = bias;
+  a.y = y_raw;
+  a.stats = stats_partial;
+  a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
+  a.tiles_per_img = (d->H / kVrRows) * (d->W / kVrW);
+  a.num_m_tiles = d->B * a.tiles_per_img;
+  a.num_n_tiles = 1;
+  a.wtiles_per_row = d->W / kVrW;
+  a.Cout = d->Cout;
+  a.num_taps = 7;
+  a.kc_per_tap = 1;
+  a.planes = 1;
+  a.split = d->split;
+  a.fmt = d->fmt;
+  a.chunk_kb = d->split ? 2 : 6;
+  a.batch_planes = 1;
+  for (int t = 0; t < 7; ++t) a.tap_dy[t] = static_cast<int8_t>(t);
+  a.f_H = d->H;
+  a.f_W = d->W;
+  a.in_img = img_nchw;
+  a.in_lbl = lbl;
+  a.in_Cimg = d->Cimg; a.in_Clbl = d->Clbl; a.in_img_kind = d->img_kind; a.in_lbl_kind = d->lbl_kind;
+  a.in_mean[0] = d->img_mean[0]; a.in_mean[1] = d->img_mean[1]; a.in_mean[2] = d->img_mean[2];
+  a.in_div = d->img_div == 0.f ? 1.f : d->img_div;
+  a.in_scale = d->act_scale == 0.f ? 1.f : d->act_scale;
+  return launch_conv_gemm_vr(a, static_cast<cudaStream_t>(stream), true);
 }

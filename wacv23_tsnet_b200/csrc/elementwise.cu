@@ -35,7 +35,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
     int r, s, c;
     bool valid;
     if (fold_kw) {
-      r = tap; s = j / Cin; c = j - s * Cin; valid = s < KW;
+      const int fc = fold_kw > 1 ? fold_kw : Cin;  // channel stride of a folded horizontal tap
+      r = tap; s = j / fc; c = j - s * fc; valid = s < KW && c < Cin;
     } else {
       r = tap / KW; s = tap - r * KW; c = j; valid = c < Cin;
     }
@@ -673,7 +674,9 @@ extern "C" int tsnet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, in
                                       int Cout_pad, float scale, int fmt, uint16_t* w_hi, uint16_t* w_lo,
                                       void* stream) {
   TSNET_ARG_CHECK(w_oihw && w_hi && w_lo, "pack_conv_weight: null argument");
-  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= (fold_kw ? KW * Cin : Cin), "pack_conv_weight: Cp %d too small", Cp);
+  TSNET_ARG_CHECK(fold_kw <= 1 || fold_kw >= Cin, "pack_conv_weight: fold_kw %d < Cin %d", fold_kw, Cin);
+  TSNET_ARG_CHECK(Cp % 64 == 0 && Cp >= (fold_kw ? KW * (fold_kw > 1 ? fold_kw : Cin) : Cin),
+                  "pack_conv_weight: Cp %d too small", Cp);
   TSNET_ARG_CHECK(Cout_pad >= Cout, "pack_conv_weight: Cout_pad");
   const size_t total = static_cast<size_t>(Cout_pad) * (fold_kw ? KH : KH * KW) * Cp;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -49,6 +49,9 @@ class ForwardEngine:
         self._packs = {}
         self._coord = {}
         self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))
+        # encoder stems straight from the raw network inputs (tsnet_stem_conv_fwd) wherever the channels fit one
+        # 8-channel folded tap (face configuration); False keeps the materialised tap source (tsnet_stem_taps)
+        self.direct_stem = True
 
     def invalidate(self):
         """Drop every packed weight.  Needed after parameter writes that do not bump the tensor version
@@ -58,17 +61,17 @@ class ForwardEngine:
         self._src_cache = None
 
     # ------------------------------------------------------------------ weights
-    def _pack(self, net, wkey, fold_kw=False, block_n=None, cin_range=None, with_bias=True):
+    def _pack(self, net, wkey, fold_kw=False, block_n=None, cin_range=None, with_bias=True, fold_cin=None):
         """Packed weight for parameter `wkey` of sub-net `net`; re-packed when the parameter changed
         (load_state_dict / optimizer step bump the tensor version)."""
         sd = self.nets[net].state_dict(keep_vars=True)
         w, b = sd[wkey + ".weight"], sd[wkey + ".bias"]
         sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, self.mode.name)
-        key = (net, wkey, cin_range, with_bias)
+        key = (net, wkey, cin_range, with_bias, fold_cin)
         hit = self._packs.get(key)
         if hit is None or hit[0] != sig:
             hit = (sig, PackedConv(w, b if with_bias else None, self.mode, fold_kw=fold_kw, block_n=block_n,
-                                   cin_range=cin_range))
+                                   cin_range=cin_range, fold_cin=fold_cin))
             self._packs[key] = hit
         return hit[1]
 
@@ -171,9 +174,16 @@ class ForwardEngine:
         residual stream."""
         m = self.mode
         X, H, W = lbl.shape[0], lbl.shape[-2], lbl.shape[-1]
-        pc = self._pack(net, "model.1", fold_kw=True)
-        t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc, img_mean=img_mean)
-        y, mr = self._conv(t, pc, "7x1", X, H, W)
+        Cimg = 0 if img is None else img.shape[1]
+        Clbl = self.label_nc if lbl.dtype == torch.uint8 else lbl.shape[1]
+        if self.direct_stem and ops.stem_conv_ok(Cimg, Clbl, H, W, 64):
+            pc = self._pack(net, "model.1", fold_kw=True, fold_cin=ops.STEM_FOLD)
+            y, stats = ops.stem_conv(img, img_div, lbl, pc, m, label_nc=self.label_nc, img_mean=img_mean)
+            mr = ops.instnorm_reduce(stats, X, H * W, pc.Cout)
+        else:
+            pc = self._pack(net, "model.1", fold_kw=True)
+            t = ops.stem_taps(img, img_div, lbl, pc.Cp, m, label_nc=self.label_nc, img_mean=img_mean)
+            y, mr = self._conv(t, pc, "7x1", X, H, W)
         for k, idx in enumerate((4, 7)):
             t = ops.build_taps(y, m, L.TAPS_S2ZERO, mean_rstd=mr, relu=True)
             pc = self._pack(net, f"model.{idx}")
@@ -246,6 +256,7 @@ class ForwardEngine:
         cache_sig = None
         if src_key is not None:
             cache_sig = (src_key, n, B, tuple(img_divs), m.name, self.winograd, self.bridge, str(self.wino_chunk_kb),
+                         self.direct_stem,
                          tuple((p.data_ptr(), p._version) for p in self.nets["img_enc"].parameters()))
         if cache_sig is not None and self._src_cache is not None and self._src_cache[0] == cache_sig:
             src_fea, fuse_taps = self._src_cache[1]

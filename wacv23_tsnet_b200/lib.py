@@ -59,6 +59,13 @@ class WinoBridgeDesc(C.Structure):
                 ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("addend_rows", C.c_longlong)]
 
 
+class StemConvDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cimg", C.c_int), ("Clbl", C.c_int),
+                ("img_kind", C.c_int), ("lbl_kind", C.c_int), ("img_mean", C.c_float * 3), ("img_div", C.c_float),
+                ("Cout", C.c_int), ("split", C.c_int), ("fmt", C.c_int), ("act_scale", C.c_float),
+                ("out_scale", C.c_float)]
+
+
 _SIGNATURES = {
     "tsnet_abi_version": (C.c_int, []),
     "tsnet_last_error": (C.c_char_p, []),
@@ -71,6 +78,7 @@ _SIGNATURES = {
     "tsnet_wino_gemm_fwd": (C.c_int, [C.POINTER(WinoGemmDesc), vp, vp, vp, vp, vp, vp]),
     "tsnet_wino_output": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_longlong, vp, vp, vp]),
     "tsnet_wino_bridge": (C.c_int, [C.POINTER(WinoBridgeDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "tsnet_stem_conv_fwd": (C.c_int, [C.POINTER(StemConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_instnorm_reduce": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp]),
     "tsnet_build_taps": (C.c_int, [C.POINTER(TapsDesc), vp, vp, vp, vp, vp, vp, vp]),
     "tsnet_stem_taps": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, vp, C.c_int, C.c_int, C.c_int,

@@ -88,7 +88,7 @@ class MathMode:
 class PackedConv:
     """A conv weight packed for tsnet_conv_gemm_fwd (K-major hi/lo, zero padded)."""
 
-    def __init__(self, weight, bias, mode, fold_kw=False, Cp=None, block_n=None, cin_range=None):
+    def __init__(self, weight, bias, mode, fold_kw=False, Cp=None, block_n=None, cin_range=None, fold_cin=None):
         L.require_device()
         w = weight.detach()
         if cin_range is not None:  # a slice of the input channels (conv over a channel-concatenation, split by operand)
@@ -96,7 +96,10 @@ class PackedConv:
         w = _f32(w)
         Cout, Cin, KH, KW = w.shape
         self.Cout, self.Cin, self.KH, self.KW, self.fold_kw = Cout, Cin, KH, KW, bool(fold_kw)
-        need = KW * Cin if fold_kw else Cin
+        # fold_cin: channels of every folded horizontal tap padded to fold_cin >= Cin (tsnet_stem_conv_fwd: 8)
+        self.fold_cin = fold_cin if (fold_kw and fold_cin) else None
+        assert self.fold_cin is None or self.fold_cin >= Cin
+        need = KW * (self.fold_cin or Cin) if fold_kw else Cin
         self.Cp = Cp if Cp is not None else (need + 63) // 64 * 64
         assert self.Cp >= need and self.Cp % 64 == 0
         self.num_taps = KH if fold_kw else KH * KW
@@ -109,7 +112,8 @@ class PackedConv:
         self.w_hi = torch.empty((self.Cout_pad, K), dtype=torch.int16, device=w.device)
         self.w_lo = torch.empty_like(self.w_hi)
         self.bias = None if bias is None else _f32(bias.detach())
-        L.check(L.load().tsnet_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW, int(self.fold_kw), self.Cp, self.Cout_pad,
+        L.check(L.load().tsnet_pack_conv_weight(_ptr(w), Cout, Cin, KH, KW,
+                                                (self.fold_cin or 1) if self.fold_kw else 0, self.Cp, self.Cout_pad,
                                                 C.c_float(self.scale), mode.fmt, _ptr(self.w_hi), _ptr(self.w_lo),
                                                 _stream()))
         _count()
@@ -407,6 +411,49 @@ def stem_taps(img, img_div, lbl, Cp, mode, label_nc=None, img_mean=None):
                                          _stream()))
     _count()
     return hi, lo, (1, H + 6, W)
+
+
+STEM_FOLD = 8   # channels per folded tap of tsnet_stem_conv_fwd
+
+
+def stem_conv_ok(Cimg, Clbl, H, W, Cout):
+    """Shapes the direct-input stem kernel covers (the face configuration of both encoders)."""
+    return Cimg + Clbl + 3 <= STEM_FOLD and Cout == 64 and H % 8 == 0 and W % 16 == 0
+
+
+def stem_conv(img, img_div, lbl, pc, mode, label_nc=None, img_mean=None, want_stats=True):
+    """ReflectionPad2d(3) + 7x7 conv of an encoder stem straight from the raw NCHW inputs (tsnet_stem_conv_fwd): no
+    tap source is materialised.  Arguments as stem_taps; pc = PackedConv(..., fold_kw=True, fold_cin=STEM_FOLD).
+    Returns (y_raw [B, H, W, 64], stats_partial or None)."""
+    assert pc.fold_kw and pc.fold_cin == STEM_FOLD and pc.Cp == 64 and pc.Cout_pad == 64
+    d = L.StemConvDesc()
+    if lbl.dtype == torch.uint8:
+        assert lbl.dim() == 3 and label_nc is not None and lbl.is_contiguous()
+        (B, H, W), d.Clbl, d.lbl_kind = lbl.shape, label_nc, 1
+    else:
+        (B, d.Clbl, H, W), d.lbl_kind = _f32(lbl).shape, 0
+    d.B, d.H, d.W = B, H, W
+    d.Cimg, d.img_kind = 0, 0
+    if img is not None:
+        d.Cimg = img.shape[1]
+        assert img.is_cuda and img.is_contiguous() and img.shape == (B, d.Cimg, H, W)
+        if img.dtype == torch.uint8:
+            assert img_mean is not None and d.Cimg == 3, "uint8 images need the 3 channel means"
+            d.img_kind = 1
+            for k in range(3):
+                d.img_mean[k] = float(img_mean[k])
+        else:
+            _f32(img)
+    d.img_div = float(img_div)
+    d.Cout, d.split, d.fmt = pc.Cout, mode.split, mode.fmt
+    d.act_scale, d.out_scale = mode.act_scale, 1.0 / (pc.scale * mode.act_scale)
+    y = torch.empty((B, H, W, pc.Cout), dtype=torch.float32, device=lbl.device)
+    stats = torch.empty((B * H * W // 32, pc.Cout, 2), dtype=torch.float32, device=lbl.device) if want_stats else None
+    with _Prof(("conv_gemm", "7x1", B, H, W, (d.Cimg + d.Clbl + 3) * 7, pc.Cout, 7)):
+        L.check(L.load().tsnet_stem_conv_fwd(C.byref(d), _ptr(img), _ptr(lbl), _ptr(pc.w_hi), _ptr(pc.w_lo),
+                                             _ptr(pc.bias), _ptr(y), _ptr(stats), _stream()))
+    _count()
+    return y, stats
 
 
 class CorrPlan:
