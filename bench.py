@@ -265,6 +265,7 @@ def run_b200(args):
     net.eval()
     if args.wino_chunk_kb > 0:
         net._engine.wino_chunk_kb = args.wino_chunk_kb
+    net._engine.direct_stem = bool(args.direct_stem)
     log("model built")
 
     from oracle.synth import IMG_MEAN as _MEAN
@@ -449,8 +450,10 @@ def run_b200(args):
                 "ms": layer_ms, "gemm_ms": t / c, "passes_ms_per_layer": t_pass / n_gemm, "launches_per_step": n_l,
                 "conv_equivalent_tflops": conv_flops / (layer_ms * 1e-3) / 1e12,
                 "conv_equivalent_frac_of_peak": conv_flops / (layer_ms * 1e-3) / 1e12 / peak}
-        chain = ("corr_prepare", "l2norm_split", "corr_tiles", "corr_finish")
-        if all((k,) in kern for k in chain):
+        # every kernel of the chain that ran: prepare, operand pass(es), [norm finalisation], tiles, finish
+        chain = tuple(k for k in ("corr_prepare", "corr_operands", "corr_norms", "l2norm_split", "corr_tiles",
+                                  "corr_finish") if (k,) in kern)
+        if all(k in chain for k in ("corr_prepare", "corr_tiles", "corr_finish")):
             # the reference's corr+warp (model/TSNet.py:319-366, :392) = ALL four kernels of the chain: mask sort / work
             # list, F.normalize + operand split, tensor-core similarity tiles + softmax, merge + grid_sample + mean
             per = {k: kern[(k,)][0] / args.steps * 1e3 for k in chain}       # us per forward
@@ -458,9 +461,11 @@ def run_b200(args):
             byts = ALGO_BYTES_CORR_PER_FRAME.get(n, 4 * 512 * 1024 * (n + 2) + 4 * 1024 * (n + 1)) * bs
             ach = byts / (t_us * 1e-6) / 1e9
             tiles_ach = byts / (per["corr_tiles"] * 1e-6) / 1e9
-            roof_corr = {"kernel": "correlation chain: corr_prepare (mask class sort + work list) + l2norm_split x2 + "
-                                   "corr_tiles (tcgen05 similarity + softmax states) + corr_finish (merge + grid_sample"
-                                   " + source mean written as map_conv's operand)", "bound": "hbm", "achieved": ach,
+            roof_corr = {"kernel": "correlation chain: corr_prepare (mask class sort + work list, one launch) + operand "
+                                   "pass(es) (un-normalised hi/lo rows + reciprocal norms; the sources' rows come from the"
+                                   " img_enc bridge pass when it is on) + corr_tiles (tcgen05 similarity, F.normalize as a"
+                                   " row x column scale, softmax states) + corr_finish (merge + grid_sample + source mean "
+                                   "written as map_conv's operand)", "kernels": list(chain), "bound": "hbm", "achieved": ach,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                          "traffic": traffic.get("corr_chain_b32_n3") if (bs, n) == (32, 3) else None,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_launch": byts,
@@ -524,7 +529,7 @@ def run_b200(args):
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
                            "math_mode": args.math, "winograd_f2x2_3x3": (args.winograd if isinstance(args.winograd, str) else bool(args.winograd)),
-                           "wino_chunk_kb": net._engine.wino_chunk_kb,
+                           "wino_chunk_kb": net._engine.wino_chunk_kb, "direct_stem": net._engine.direct_stem,
                            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
@@ -578,6 +583,8 @@ def main():
     ap.add_argument("--wino-chunk-kb", dest="wino_chunk_kb", type=int, default=0,
                     help="experiment: K blocks accumulated in TMEM per promotion in the Winograd GEMMs (default: the "
                          "engine's parity-validated 2; 4 is faster but misses the image tolerance on one golden)")
+    ap.add_argument("--no-direct-stem", dest="direct_stem", action="store_false",
+                    help="materialise the stem operand (tsnet_stem_taps) instead of generating it inside the stem kernel")
     ap.add_argument("--winograd-unfused", dest="winograd", action="store_const", const="unfused",
                     help="Winograd with separate transform passes instead of the fused bridge pass (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -165,6 +165,15 @@ typedef struct {
   float scale, eps;             /* operand pre-scale (power of two); InstanceNorm eps (0 = 1e-5) */
   int act_C_total, act_c_off;   /* act_out channel window (0 = C) */
   long long addend_rows;
+  /* optional (all four or none): the activations also leave as the un-normalised operand rows of the correlation --
+   * corr_hi / corr_lo [B * H*W, C] at the row's sorted rank (corr_rank [B, H*W], from tsnet_corr_rank_table), values
+   * scaled by corr_scale, and corr_ssq [B][C / 32][H*W] = per-slab partial sums of squares (-> tsnet_corr_norms).
+   * Used by the last ResnetBlock of img_enc: the source features never make a separate trip through an operand pass. */
+  uint16_t* corr_hi;
+  uint16_t* corr_lo;
+  const uint16_t* corr_rank;
+  float* corr_ssq;
+  float corr_scale;
 } tsnet_wino_bridge_desc;
 int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m, const float* bias, const float* addend,
                       const float* residual, float* act_out, float* mean_rstd_out, uint16_t* v_hi, uint16_t* v_lo,
@@ -293,22 +302,35 @@ const uint16_t* tsnet_corr_rank_table(const tsnet_corr_desc* d, const void* work
 int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fmt, float scale, const uint16_t* rank,
                        uint16_t* out_hi, uint16_t* out_lo, void* stream);
 
-/*   tar_hi/lo   [B*hw, C]          normalised target operands, sorted rows
- *   src_hi/lo   [n_src, B*hw, C]   normalised operands of all sources (ONE buffer, source-major), sorted rows
+/* Operands WITHOUT the normalisation (the default path since round 2): x * scale split into hi / lo at the row's
+ * sorted rank plus rnorm = 1 / max(||x||_2, 1e-12) at the same rank; tsnet_corr_tiles applies rnorm_t[row] * rnorm_s[col]
+ * to the similarity inside the softmax FMA (F.normalize of model/TSNet.py:319, :339 as a scale of the dot product: no
+ * per-element division, and the operands of the SOURCES can be written by the pass that produces the features:
+ * tsnet_wino_bridge's corr_* outputs + tsnet_corr_norms).  tsnet_corr_desc.operand_scale = scale * scale. */
+int tsnet_corr_operands(const float* fea, int B, int HW, int C, int fmt, float scale, const uint16_t* rank,
+                        uint16_t* out_hi, uint16_t* out_lo, float* rnorm, void* stream);
+/* ssq_part [B][slabs][HW] (per-slab partial sums of squares from tsnet_wino_bridge) -> rnorm [B * HW] at the sorted rank */
+int tsnet_corr_norms(const float* ssq_part, int B, int HW, int slabs, const uint16_t* rank, float* rnorm, void* stream);
+
+/*   tar_hi/lo   [B*hw, C]          target operands, sorted rows (normalised if rnorm_* are NULL, else un-normalised)
+ *   rnorm_t/s   NULL, or [B*hw] / [n_src*B*hw] reciprocal norms at the sorted ranks (see tsnet_corr_operands)
+ *   src_hi/lo   [n_src, B*hw, C]   operands of all sources (ONE buffer, source-major), sorted rows
  *   src_fea     n_src pointers (host array) to fp32 NHWC un-normalised source features (sampled by grid_sample)
  *   out_mean    NULL or fp32 NHWC [B, hw, C] = mean_i grid_sample(src_fea_i, G_i)
  *   out_grids   NULL or [n_src, B, h, w, 2] (x, y) -- the reference's warp_grid2d_list (:369-370)
  *   taps_hi/lo  NULL or the hi/lo tap source [B, h, w, Cp_total] of the 1x1 conv that consumes the mean: channel
  *               window [c_off, c_off + C), values scaled by taps_scale ("grid_sample fused with the next conv's load") */
 int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
-                        const uint16_t* src_hi, const uint16_t* src_lo, const float* const* src_fea, float* out_mean,
-                        float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off,
-                        float taps_scale, void* workspace, size_t workspace_bytes, void* stream);
+                        const uint16_t* src_hi, const uint16_t* src_lo, const float* rnorm_t, const float* rnorm_s,
+                        const float* const* src_fea, float* out_mean, float* out_grids, uint16_t* taps_hi,
+                        uint16_t* taps_lo, int Cp_total, int c_off, float taps_scale, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* the two halves of tsnet_corr_warp_fwd, separately launchable (profiling, grids-only use).  tsnet_corr_tiles runs
  * the 2-CTA tile kernel (tcgen05.mma.cta_group::2, work items of 256 target rows) unless tsnet_corr_desc.one_cta
  * selects the 1-CTA kernel. */
 int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo, const uint16_t* src_hi,
-                     const uint16_t* src_lo, void* workspace, size_t workspace_bytes, void* stream);
+                     const uint16_t* src_lo, const float* rnorm_t, const float* rnorm_s, void* workspace,
+                     size_t workspace_bytes, void* stream);
 int tsnet_corr_finish(const tsnet_corr_desc* d, const float* const* src_fea, float* out_mean, float* out_grids,
                       uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off, float taps_scale, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -302,7 +302,7 @@ def _corr_inputs(B, n, kind, seed):
     return tar, srcs, tb, sbs
 
 
-def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True, one_cta=False):
+def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True, one_cta=False, normalized=False):
     from wacv23_tsnet_b200 import ops
     B, n = tar.shape[0], len(srcs)
     tar_d = tar.permute(0, 2, 3, 1).contiguous().cuda().view(B, 1024, 512)
@@ -310,7 +310,7 @@ def _run_corr(tar, srcs, tb, sbs, m, sort=True, want_mean=True, one_cta=False):
     coord = torch.cat([torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32)]).cuda()
     out, grids = ops.corr_chain(tar_d, src_d, tb.squeeze(1).contiguous().cuda(),
                                 [s.squeeze(1).contiguous().cuda() for s in sbs], coord, m, want_grids=True,
-                                want_mean=want_mean, sort=sort, one_cta=one_cta)
+                                want_mean=want_mean, sort=sort, one_cta=one_cta, normalized=normalized)
     torch.cuda.synchronize()
     return out, grids
 
@@ -356,6 +356,11 @@ def test_corr_two_cta_and_one_cta_tile_kernels_agree():
         tar, srcs, tb, sbs = _corr_inputs(B, n, kind, seed=31)
         out2, grids2 = _run_corr(tar, srcs, tb, sbs, m)
         out1, grids1 = _run_corr(tar, srcs, tb, sbs, m, one_cta=True)
+        # operands normalised up front (tsnet_l2norm_split) vs the default: un-normalised operands + reciprocal norms
+        # applied to the similarity in the softmax FMA -- the same function up to fp32 rounding
+        outn, gridsn = _run_corr(tar, srcs, tb, sbs, m, normalized=True)
+        assert float((grids2 - gridsn).abs().max()) < 1e-5, kind
+        assert _relerr(out2, outn) < 3e-4, kind
         assert float((grids2 - grids1).abs().max()) < 5e-6, kind
         assert _relerr(out2, out1) < 2e-4, kind
 
@@ -729,6 +734,18 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
     vl = ops.wino_v_logical   # operand planes are stored K-block-major
     assert _relerr(_recon(vl(hf), vl(lf), m.fmt)[..., 64:], _recon(vl(hs), vl(ls), m.fmt)) < 4e-6
     assert int(vl(hf)[..., :64].abs().max()) == 0
+    # correlation operand emission (the last img_enc block): rows at a rank permutation + partial sums of squares must
+    # equal what the stand-alone operand pass makes of the same activations
+    rank = torch.stack([torch.randperm(1024) for _ in range(B)]).to(torch.int16).cuda()
+    corr = dict(hi=torch.zeros(B * 1024, Cout, dtype=torch.int16, device="cuda"), rank=rank.data_ptr(),
+                ssq=torch.zeros(B, Cout // 32, 1024, device="cuda"))
+    corr["lo"] = torch.zeros_like(corr["hi"])
+    ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, corr=corr)
+    rn_b = ops.corr_norms(corr["ssq"], B, 1024, Cout // 32, rank.data_ptr())
+    oh, ol, rn_o = ops.corr_operands(act_f[..., 64:].contiguous().view(B, 1024, Cout), m, rank=rank.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(corr["hi"], oh) and torch.equal(corr["lo"], ol)
+    assert _relerr(rn_b, rn_o) < 1e-6
     # deterministic, and a sample does not depend on the batch it rides in
     h2, l2, _ = ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res)
     t1 = ops.build_taps(x[1:2].contiguous(), m, L.TAPS_WINO)
@@ -749,7 +766,7 @@ def test_stem_conv_direct_input():
     from wacv23_tsnet_b200 import ops
     m = ops.MathMode("fp16x3")
     torch.manual_seed(21)
-    B, H, W, Lc = 3, 64, 96, 2
+    B, H, W, Lc = 3, 64, 128, 2
     u8 = torch.randint(0, 256, (B, 3, H, W), device="cuda", dtype=torch.uint8)
     mean = (101.848, 112.108, 111.66)
     img = u8.float() - torch.tensor(mean, device="cuda").view(1, 3, 1, 1)

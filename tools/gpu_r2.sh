@@ -46,6 +46,12 @@ for st in $STAGES; do
     parity_sf)
       timeout 900 python tools/parity_report.py --winograd bridge --small-first --chunk-kb img_enc=2,default=4 img_enc=3,default=4 4 > $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
+    bench_nostem)
+      timeout 400 python bench.py --steps 10 --warmup 3 --no-direct-stem --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_nostem_$TAG.json 2> $OUT/bench_nostem_$TAG.err
+      cut -c1-300 $OUT/bench_nostem_$TAG.json ;;
+    tests_corr)
+      timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "corr or stem or bridge or golden or train_mode or cache or full_batch" > $OUT/pytest_corr_$TAG.log 2>&1
+      echo "pytest exit $?" >> $OUT/pytest_corr_$TAG.log; tail -25 $OUT/pytest_corr_$TAG.log ;;
     bench_c4)
       timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
       cut -c1-300 $OUT/bench_c4_$TAG.json ;;
@@ -60,6 +66,9 @@ for st in $STAGES; do
           -f -o $OUT/prof_bridge_$TAG $FWD > /dev/null 2>&1 ;;
     winobench)
       timeout 300 python tools/wino_bench.py > $OUT/winobench_$TAG.log 2>&1; cat $OUT/winobench_$TAG.log ;;
+    ncu_stem)
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_vr_kernel -s 4 -c 1 \
+          -f -o $OUT/prof_stem_$TAG $FWD > /dev/null 2>&1 ;;
     ncu_corr)
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:"corr_|l2norm|warp_mean" -s 6 -c 6 \
           -f -o $OUT/prof_corr_$TAG $FWD > /dev/null 2>&1 ;;

@@ -816,34 +816,62 @@ __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8
   const int H = args.f_H, W = args.f_W;
   const size_t plane = static_cast<size_t>(H) * W;
   constexpr int SW = kVrW + 6, SR = kVrRows + 6;
-  for (int idx = pt; idx < SR * SW; idx += 96) {
+  constexpr int NP = (SR * SW + 95) / 96;  // source pixels per producer thread (4)
+  constexpr int NRAW = kStemFold - 3;      // image + label channels (<= 5)
+  const int n_img = args.in_Cimg, n_il = args.in_Cimg + args.in_Clbl;
+  // ---- all global loads of this thread's pixels first (one exposed latency per tile instead of one per pixel)
+  float raw[NP][NRAW];
+  int ysv[NP], xsv[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int idx = pt + k * 96;
     const int r = idx / SW, sx = idx - r * SW;
     int ys = y0 - 3 + r, xs = x0 - 3 + sx;
     ys = ys < 0 ? -ys : ys; ys = ys >= H ? 2 * H - 2 - ys : ys;
     xs = xs < 0 ? -xs : xs; xs = xs >= W ? 2 * W - 2 - xs : xs;
+    ysv[k] = ys; xsv[k] = xs;
     const size_t pix = static_cast<size_t>(ys) * W + xs;
+    int cls = -1;
+    if (idx < SR * SW && args.in_lbl_kind != 0)
+      cls = static_cast<const uint8_t*>(args.in_lbl)[static_cast<size_t>(img) * plane + pix];
+#pragma unroll
+    for (int c = 0; c < NRAW; ++c) {
+      float q = 0.f;
+      if (idx < SR * SW) {
+        if (c < n_img) {
+          const size_t off = (static_cast<size_t>(img) * n_img + c) * plane + pix;
+          if (args.in_img_kind == 0) q = static_cast<const float*>(args.in_img)[off];
+          else q = static_cast<float>(static_cast<const uint8_t*>(args.in_img)[off]);
+        } else if (c < n_il) {
+          if (args.in_lbl_kind == 0)
+            q = static_cast<const float*>(args.in_lbl)[(static_cast<size_t>(img) * args.in_Clbl + (c - n_img)) * plane + pix];
+          else
+            q = cls == c - n_img ? 1.f : 0.f;
+        }
+      }
+      raw[k][c] = q;
+    }
+  }
+  // ---- channel vector, split, stores
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int idx = pt + k * 96;
+    if (idx >= SR * SW) break;
+    const int r = idx / SW, sx = idx - r * SW;
     // Encoder.coord_conv: t = idx / (n - 1); 2 t - 1; r = sqrt(x^2 + y^2), separate roundings
-    const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ys), static_cast<float>(H - 1))), -1.f);
-    const float xx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xs), static_cast<float>(W - 1))), -1.f);
+    const float yy = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(ysv[k]), static_cast<float>(H - 1))), -1.f);
+    const float xx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(static_cast<float>(xsv[k]), static_cast<float>(W - 1))), -1.f);
     const float rr = __fsqrt_rn(__fadd_rn(__fmul_rn(xx, xx), __fmul_rn(yy, yy)));
-    const int n_img = args.in_Cimg, n_il = args.in_Cimg + args.in_Clbl;
-    int cls = 0;
-    if (args.in_lbl_kind != 0) cls = static_cast<const uint8_t*>(args.in_lbl)[static_cast<size_t>(img) * plane + pix];
     float v[kStemFold];
 #pragma unroll
     for (int c = 0; c < kStemFold; ++c) {  // channel c of cat[img / div, lbl, x, y, r, 0...] (warp-uniform branches)
       float q = 0.f;
-      if (c < n_img) {
-        const size_t off = (static_cast<size_t>(img) * n_img + c) * plane + pix;
-        float x;
-        if (args.in_img_kind == 0) x = static_cast<const float*>(args.in_img)[off];
-        else x = __fadd_rn(static_cast<float>(static_cast<const uint8_t*>(args.in_img)[off]), -args.in_mean[c < 3 ? c : 2]);
+      if (c < NRAW && c < n_img) {
+        float x = raw[k][c < NRAW ? c : 0];
+        if (args.in_img_kind != 0) x = __fadd_rn(x, -args.in_mean[c < 3 ? c : 2]);
         q = __fdiv_rn(x, args.in_div);
-      } else if (c < n_il) {
-        if (args.in_lbl_kind == 0)
-          q = static_cast<const float*>(args.in_lbl)[(static_cast<size_t>(img) * args.in_Clbl + (c - n_img)) * plane + pix];
-        else
-          q = cls == c - n_img ? 1.f : 0.f;
+      } else if (c < NRAW && c < n_il) {
+        q = raw[k][c < NRAW ? c : 0];
       } else if (c == n_il) {
         q = xx;
       } else if (c == n_il + 1) {
@@ -921,9 +949,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp < 4) {
-    // control warp group: 40 registers per thread; the direct-input producers (loads + conversions) get 96 -- the
-    // accumulate warps of this N = 64 kernel hold only 32 accumulators and make do with 200 instead of 224
-    if constexpr (DIRECT) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    // control warp group: 40 registers per thread; the direct-input producers (loads + conversions) get 128 -- the
+    // accumulate warps of this N = 64 kernel hold only 32 accumulators and make do with 192 instead of 224
+    if constexpr (DIRECT) asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (DIRECT && warp != 1) {
       // ===================== direct-input producers (warps 0, 2, 3) =====================
@@ -1028,7 +1056,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
       }
     }
   } else {
-    if constexpr (DIRECT) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    if constexpr (DIRECT) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== accumulate + epilogue =====================
     constexpr int NC = kVrN / 2;

@@ -278,6 +278,11 @@ struct alignas(64) CorrArgs {
   const int* items;
   const int* counts;
   float4* state;
+  // un-normalised operands (tsnet_corr_operands / tsnet_wino_bridge): 1 / max(||x||, 1e-12) of every target row and
+  // source column at its sorted rank; F.normalize (model/TSNet.py:319, :339) is then applied as a per-row x per-column
+  // scale of the similarity inside the softmax FMA.  Null = the operands are already normalised (tsnet_l2norm_split).
+  const float* rn_t;
+  const float* rn_s;
   int B, n_src, C, hw, ncand, NS;
   int split, fmt, chunk_kb;
   float k2;  // temperature / operand_scale * log2(e)
@@ -287,7 +292,8 @@ struct CorrSmemTail {
   uint64_t full_bar[3], empty_bar[3], tmem_full[2], tmem_empty[2];  // (3 = max stages of the two tile kernels)
   uint32_t tmem_base;
   uint32_t pad[15];
-  alignas(16) float tab[2][3][kCorrN];  // per item (double-buffered): source mask, x, y of the 256 columns
+  // per item (double-buffered), for the 256 source columns: mask * rnorm, x, y, rnorm
+  alignas(16) float tab[2][4][kCorrN];
   int pref[kCorrMaxB + 1];              // exclusive prefix of the per-sample work-list lengths
 };
 
@@ -460,15 +466,20 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
       //      writing buffer `par` again at item k+2 is safe)
       {
         const size_t sb = (static_cast<size_t>(i) * args.B + b) * args.hw + ch * kCorrN + et;
-        tl.tab[par][0][et] = args.maskv[static_cast<size_t>(args.B) * args.hw + sb];
+        const float rs = args.rn_s ? args.rn_s[sb] : 1.f;
+        tl.tab[par][0][et] = args.maskv[static_cast<size_t>(args.B) * args.hw + sb] * rs;
         tl.tab[par][1][et] = args.cxs[sb];
         tl.tab[par][2][et] = args.cys[sb];
+        tl.tab[par][3][et] = rs;
       }
       const float m_t = args.maskv[static_cast<size_t>(b) * args.hw + mt * kCorrM + row];
+      const float r_t = args.rn_t ? args.rn_t[static_cast<size_t>(b) * args.hw + mt * kCorrM + row] : 1.f;
       // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)) = (T.S) * (wa*ms + wb);
       // exact for binary masks (mismatched pairs get logit 0, not -inf, as in the reference).  k2 folds the temperature,
       // the operand scale and log2(e): logits are kept in log2 units.
-      const float wa = (2.f * m_t - 1.f) * args.k2, wb = (1.f - m_t) * args.k2;
+      // with un-normalised operands the weight of column j is r_t * r_s[j] * (wa' * ms_j + wb') =
+      // wa * (ms_j * r_s[j]) + wb * r_s[j]  (tables 0 and 3)
+      const float wa = (2.f * m_t - 1.f) * args.k2 * r_t, wb = (1.f - m_t) * args.k2 * r_t;
       epi_bar_sync();
 
       // ---- accumulator -> registers (one TMEM read when the whole K is accumulated in TMEM)
@@ -504,14 +515,16 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile_kernel(const __grid
       const float* tmask = &tl.tab[par][0][half * kCorrNC];
       const float* tcx = &tl.tab[par][1][half * kCorrNC];
       const float* tcy = &tl.tab[par][2][half * kCorrNC];
+      const float* trn = &tl.tab[par][3][half * kCorrNC];
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < kCorrNC; j += 4) {
         const float4 mk = *reinterpret_cast<const float4*>(tmask + j);
-        acc[j + 0] *= fmaf(wa, mk.x, wb);
-        acc[j + 1] *= fmaf(wa, mk.y, wb);
-        acc[j + 2] *= fmaf(wa, mk.z, wb);
-        acc[j + 3] *= fmaf(wa, mk.w, wb);
+        const float4 rk = *reinterpret_cast<const float4*>(trn + j);
+        acc[j + 0] *= fmaf(wa, mk.x, wb * rk.x);
+        acc[j + 1] *= fmaf(wa, mk.y, wb * rk.y);
+        acc[j + 2] *= fmaf(wa, mk.z, wb * rk.z);
+        acc[j + 3] *= fmaf(wa, mk.w, wb * rk.w);
         mx = fmaxf(mx, fmaxf(fmaxf(acc[j], acc[j + 1]), fmaxf(acc[j + 2], acc[j + 3])));
       }
       // ---- softmax partial state with the source coordinates as V
@@ -685,16 +698,21 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
       //      writing buffer `par` again at item k+2 is safe)
       {
         const size_t sb = (static_cast<size_t>(i) * args.B + b) * args.hw + ch * kCorrN + et;
-        tl.tab[par][0][et] = args.maskv[static_cast<size_t>(args.B) * args.hw + sb];
+        const float rs = args.rn_s ? args.rn_s[sb] : 1.f;
+        tl.tab[par][0][et] = args.maskv[static_cast<size_t>(args.B) * args.hw + sb] * rs;
         tl.tab[par][1][et] = args.cxs[sb];
         tl.tab[par][2][et] = args.cys[sb];
+        tl.tab[par][3][et] = rs;
       }
       const int mrow = (2 * mt + static_cast<int>(rank)) * kCorrM + row;  // this CTA's 128 of the item's 256 rows
       const float m_t = args.maskv[static_cast<size_t>(b) * args.hw + mrow];
+      const float r_t = args.rn_t ? args.rn_t[static_cast<size_t>(b) * args.hw + mrow] : 1.f;
       // (T*mt).(S*ms) + (T*(1-mt)).(S*(1-ms)) == (T.S) * (mt*ms + (1-mt)*(1-ms)) = (T.S) * (wa*ms + wb);
       // exact for binary masks (mismatched pairs get logit 0, not -inf, as in the reference).  k2 folds the temperature,
       // the operand scale and log2(e): logits are kept in log2 units.
-      const float wa = (2.f * m_t - 1.f) * args.k2, wb = (1.f - m_t) * args.k2;
+      // with un-normalised operands the weight of column j is r_t * r_s[j] * (wa' * ms_j + wb') =
+      // wa * (ms_j * r_s[j]) + wb * r_s[j]  (tables 0 and 3)
+      const float wa = (2.f * m_t - 1.f) * args.k2 * r_t, wb = (1.f - m_t) * args.k2 * r_t;
       epi_bar_sync();
 
       // ---- accumulator -> registers (one TMEM read when the whole K is accumulated in TMEM)
@@ -733,14 +751,16 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
       const float* tmask = &tl.tab[par][0][half * kCorrNC];
       const float* tcx = &tl.tab[par][1][half * kCorrNC];
       const float* tcy = &tl.tab[par][2][half * kCorrNC];
+      const float* trn = &tl.tab[par][3][half * kCorrNC];
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < kCorrNC; j += 4) {
         const float4 mk = *reinterpret_cast<const float4*>(tmask + j);
-        acc[j + 0] *= fmaf(wa, mk.x, wb);
-        acc[j + 1] *= fmaf(wa, mk.y, wb);
-        acc[j + 2] *= fmaf(wa, mk.z, wb);
-        acc[j + 3] *= fmaf(wa, mk.w, wb);
+        const float4 rk = *reinterpret_cast<const float4*>(trn + j);
+        acc[j + 0] *= fmaf(wa, mk.x, wb * rk.x);
+        acc[j + 1] *= fmaf(wa, mk.y, wb * rk.y);
+        acc[j + 2] *= fmaf(wa, mk.z, wb * rk.z);
+        acc[j + 3] *= fmaf(wa, mk.w, wb * rk.w);
         mx = fmaxf(mx, fmaxf(fmaxf(acc[j], acc[j + 1]), fmaxf(acc[j + 2], acc[j + 3])));
       }
       // ---- softmax partial state with the source coordinates as V
@@ -981,11 +1001,12 @@ extern "C" int tsnet_corr_prepare(const tsnet_corr_desc* d, const void* tar_bbox
 }
 
 extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
-                                const uint16_t* src_hi, const uint16_t* src_lo, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                const uint16_t* src_hi, const uint16_t* src_lo, const float* rnorm_t,
+                                const float* rnorm_s, void* workspace, size_t workspace_bytes, void* stream) {
   if (int r = corr_desc_check(d)) return r;
   TSNET_ARG_CHECK(tar_hi && src_hi && workspace, "corr_tiles: null argument");
   TSNET_ARG_CHECK(!d->split || (tar_lo && src_lo), "corr_tiles: split mode needs the lo operands");
+  TSNET_ARG_CHECK((rnorm_t == nullptr) == (rnorm_s == nullptr), "corr_tiles: rnorm_t / rnorm_s come together");
   const int hw = d->h * d->w;
   const CorrWs L = corr_ws_layout(d->B, d->n_src, hw);
   TSNET_ARG_CHECK(workspace_bytes >= L.total, "corr_tiles: workspace %zu B < %zu B", workspace_bytes, L.total);
@@ -1016,6 +1037,8 @@ extern "C" int tsnet_corr_tiles(const tsnet_corr_desc* d, const uint16_t* tar_hi
   a.items = reinterpret_cast<const int*>(ws + L.items);
   a.counts = reinterpret_cast<const int*>(ws + L.counts);
   a.state = reinterpret_cast<float4*>(ws + L.state);
+  a.rn_t = rnorm_t;
+  a.rn_s = rnorm_s;
   a.B = d->B; a.n_src = d->n_src; a.C = d->C; a.hw = hw;
   a.ncand = d->n_src * (hw / kCorrM) * (hw / kCorrN) / (two_cta ? 2 : 1);
   a.NS = 2 * (hw / kCorrN);
@@ -1107,11 +1130,12 @@ extern "C" int tsnet_corr_finish(const tsnet_corr_desc* d, const float* const* s
 }
 
 extern "C" int tsnet_corr_warp_fwd(const tsnet_corr_desc* d, const uint16_t* tar_hi, const uint16_t* tar_lo,
-                                   const uint16_t* src_hi, const uint16_t* src_lo, const float* const* src_fea,
-                                   float* out_mean, float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo,
-                                   int Cp_total, int c_off, float taps_scale, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
-  if (int r = tsnet_corr_tiles(d, tar_hi, tar_lo, src_hi, src_lo, workspace, workspace_bytes, stream)) return r;
+                                   const uint16_t* src_hi, const uint16_t* src_lo, const float* rnorm_t,
+                                   const float* rnorm_s, const float* const* src_fea, float* out_mean,
+                                   float* out_grids, uint16_t* taps_hi, uint16_t* taps_lo, int Cp_total, int c_off,
+                                   float taps_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = tsnet_corr_tiles(d, tar_hi, tar_lo, src_hi, src_lo, rnorm_t, rnorm_s, workspace, workspace_bytes, stream))
+    return r;
   return tsnet_corr_finish(d, src_fea, out_mean, out_grids, taps_hi, taps_lo, Cp_total, c_off, taps_scale, workspace,
                            workspace_bytes, stream);
 }

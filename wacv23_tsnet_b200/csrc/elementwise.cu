@@ -488,6 +488,60 @@ __global__ void __launch_bounds__(256) l2norm_split_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Correlation operands WITHOUT the normalisation: x * scale split into hi / lo at the row's sorted rank, plus
+// rnorm = 1 / max(||x||_2, 1e-12) (F.normalize's clamp) at the same rank; the tile kernel applies rnorm_t * rnorm_s as
+// a scale of the similarity.  One warp = one pixel; no per-element division (l2norm_split was issue-bound on them).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) corr_operands_kernel(const float* __restrict__ fea, size_t npix, int HW, int C,
+                                                            int fmt, float scale, const uint16_t* __restrict__ rank,
+                                                            uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                            float* __restrict__ rnorm) {
+  const size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x / 32) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = fea + pix * C;
+  float4 v[8];
+  float ss = 0.f;
+  const int nk = C / 128;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < nk) {
+      v[k] = *reinterpret_cast<const float4*>(p + k * 128 + lane * 4);
+      ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const size_t drow = rank ? (pix / HW) * HW + rank[pix] : pix;
+  if (lane == 0) rnorm[drow] = __fdiv_rn(1.f, fmaxf(__fsqrt_rn(ss), 1e-12f));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < nk) {
+      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split16(e[j] * scale, fmt, h[j], l[j]);
+      const size_t d = drow * C + k * 128 + lane * 4;
+      *reinterpret_cast<uint2*>(hi + d) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+      *reinterpret_cast<uint2*>(lo + d) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
+    }
+  }
+}
+
+// rnorm of the sources from the per-slab partial sums of squares the bridge pass wrote: [B][slabs][HW] -> [B * HW] at the
+// sorted rank.  One thread per pixel, fixed summation order.
+__global__ void __launch_bounds__(256) corr_norms_kernel(const float* __restrict__ ssq_part, size_t npix, int HW,
+                                                         int slabs, const uint16_t* __restrict__ rank,
+                                                         float* __restrict__ rnorm) {
+  const size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (pix >= npix) return;
+  const size_t b = pix / HW, p = pix - b * HW;
+  float ss = 0.f;
+  for (int k = 0; k < slabs; ++k) ss += ssq_part[(b * slabs + k) * HW + p];
+  rnorm[b * HW + (rank ? rank[pix] : p)] = __fdiv_rn(1.f, fmaxf(__fsqrt_rn(ss), 1e-12f));
+}
+
+// ------------------------------------------------------------------------------------------------
 // output head: reflect-pad 3, 7x7 conv Cin -> 3, tanh, optional pose compositing, NCHW store.
 // block = 32 x 16 output pixels, 128 threads; thread = 4 vertically adjacent pixels x 3 outputs.
 // Channels go through shared memory in chunks of 8 (pixel stride 12 floats: conflict-free LDS.128).  For every
@@ -789,6 +843,27 @@ extern "C" int tsnet_l2norm_split(const float* fea, int B, int HW, int C, int fm
   const size_t npix = static_cast<size_t>(B) * HW;
   l2norm_split_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       fea, npix, HW, C, fmt, scale == 0.f ? 1.f : scale, rank, out_hi, out_lo);
+  TSNET_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsnet_corr_operands(const float* fea, int B, int HW, int C, int fmt, float scale, const uint16_t* rank,
+                                   uint16_t* out_hi, uint16_t* out_lo, float* rnorm, void* stream) {
+  TSNET_ARG_CHECK(fea && out_hi && out_lo && rnorm, "corr_operands: null argument");
+  TSNET_ARG_CHECK(C % 128 == 0 && C <= 1024, "corr_operands: C %d must be a multiple of 128, <= 1024", C);
+  const size_t npix = static_cast<size_t>(B) * HW;
+  corr_operands_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fea, npix, HW, C, fmt, scale == 0.f ? 1.f : scale, rank, out_hi, out_lo, rnorm);
+  TSNET_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsnet_corr_norms(const float* ssq_part, int B, int HW, int slabs, const uint16_t* rank, float* rnorm,
+                                void* stream) {
+  TSNET_ARG_CHECK(ssq_part && rnorm && slabs > 0, "corr_norms: bad argument");
+  const size_t npix = static_cast<size_t>(B) * HW;
+  corr_norms_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ssq_part, npix, HW, slabs, rank, rnorm);
   TSNET_LAUNCH_CHECK();
   return 0;
 }

@@ -379,6 +379,14 @@ struct WinoBridgeArgs {
   int B, H, W, C, relu, Cp_total, c_off, fmt, act_C_total, act_c_off;
   long long addend_rows;
   float scale, eps;
+  // optional: the activations also leave as the UN-NORMALISED operand rows of the correlation (tsnet_corr_tiles with
+  // rnorm): hi / lo [B * H*W, C] at the row's sorted rank (corr_rank: [B, H*W] position -> rank) plus this slab's partial
+  // sum of squares per pixel, corr_ssq [B][C / 32][H*W] (summed and inverted by tsnet_corr_norms)
+  uint16_t* corr_hi;
+  uint16_t* corr_lo;
+  const uint16_t* corr_rank;
+  float* corr_ssq;
+  float corr_scale;
 };
 
 // shared-memory layout: float y[H * W * PS]; double part[nseg * CS * 2]; float mr[CS * 2]
@@ -518,7 +526,30 @@ TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread
       st_f4(sp, v);
       if (a.act_out)
         st_f4(a.act_out + (static_cast<size_t>(b) * HW + pix) * a.act_C_total + a.act_c_off + slab * kBridgeCS + cq * 4, v);
+      if (a.corr_hi) {
+        const size_t row = static_cast<size_t>(b) * HW + a.corr_rank[static_cast<size_t>(b) * HW + pix];
+        WinoPlaneWriter w{a.corr_hi + row * a.C + slab * kBridgeCS + cq * 4, a.corr_lo + row * a.C + slab * kBridgeCS + cq * 4,
+                          0, a.corr_scale, a.fmt};
+        wino_write_next(w, v);
+      }
     }
+  }
+}
+
+// phase N (after B; reads only): this slab's sum of squares of every pixel, channel order rotated by the pixel index so
+// that the lanes of a warp (consecutive pixels, 128 bytes apart) hit different banks
+TSNET_HD void wino_bridge_phase_n(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y) {
+  if (!a.corr_ssq) return;
+  const int slabs = a.C / kBridgeCS;
+  const int b = block / slabs, slab = block - b * slabs;
+  const int HW = a.H * a.W;
+  for (int pix = thread; pix < HW; pix += nthreads) {
+    float ss = 0.f;
+    for (int k = 0; k < kBridgeCS; ++k) {
+      const float v = s_y[static_cast<size_t>(pix) * kBridgePS + ((k + pix) & (kBridgeCS - 1))];
+      ss += v * v;
+    }
+    a.corr_ssq[(static_cast<size_t>(b) * slabs + slab) * HW + pix] = ss;
   }
 }
 

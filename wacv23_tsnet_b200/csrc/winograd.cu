@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kBridgeThreads, 1) wino_bridge_kernel(const Wi
   __syncthreads();
   wino_bridge_phase_b(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y, s_mr);
   __syncthreads();
+  wino_bridge_phase_n(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
   wino_bridge_phase_c(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
 }
 
@@ -98,6 +99,11 @@ extern "C" int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m
   a.fmt = d->fmt; a.act_C_total = actC; a.act_c_off = d->act_c_off; a.addend_rows = d->addend_rows;
   a.scale = d->scale == 0.f ? 1.f : d->scale;
   a.eps = d->eps == 0.f ? 1e-5f : d->eps;
+  TSNET_ARG_CHECK((d->corr_hi == nullptr) == (d->corr_lo == nullptr) && (d->corr_hi == nullptr) == (d->corr_rank == nullptr) &&
+                      (d->corr_hi == nullptr) == (d->corr_ssq == nullptr),
+                  "wino_bridge: corr_hi / corr_lo / corr_rank / corr_ssq come together");
+  a.corr_hi = d->corr_hi; a.corr_lo = d->corr_lo; a.corr_rank = d->corr_rank; a.corr_ssq = d->corr_ssq;
+  a.corr_scale = d->corr_scale == 0.f ? 1.f : d->corr_scale;
   static int smem_attr[kMaxDevices] = {0};
   TSNET_CUDA_CHECK(ensure_dyn_smem(wino_bridge_kernel, static_cast<int>(smem), smem_attr));
   const unsigned blocks = static_cast<unsigned>(d->B) * (d->C / kBridgeCS);

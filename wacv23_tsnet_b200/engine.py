@@ -122,7 +122,7 @@ class ForwardEngine:
         return self._conv(taps, pc, "3x3", B, H, W, norm=norm, addend=addend)
 
     def _conv_in(self, taps, pc, kind, B, H, W, tmode, relu=False, residual=None, need_act=False, dest=None, c_off=0,
-                 want_taps=True, addend=None, act_out=None, act_c_off=0):
+                 want_taps=True, addend=None, act_out=None, act_c_off=0, corr_out=None):
         """conv -> InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> tap source of the next layer (tmode).
         `pc` is a PackedConv, or (net, wkey[, cin_range]) for a ResnetBlock 3x3 convolution (direct or Winograd,
         decided by the operand format of `taps`).
@@ -149,7 +149,7 @@ class ForwardEngine:
             pw = self._pack_wino(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
             mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self._chunk(pc[0]), flags=self.wino_flags)
             t = ops.wino_bridge(mbuf, pw, B, H, W, m, relu=relu, addend=addend, residual=residual, act_out=act_out,
-                                act_c_off=act_c_off, taps=dest, c_off=c_off)
+                                act_c_off=act_c_off, taps=dest, c_off=c_off, corr=corr_out)
             return t, act_out
         if is3:
             y, mr = self._conv3(taps, pc[0], pc[1], B, H, W, addend=addend, cin_range=pc[2] if len(pc) > 2 else None)
@@ -160,15 +160,15 @@ class ForwardEngine:
         return (t if want_taps else None), act_out
 
     def _resblock(self, net, prefix, taps, x_res, B, H, W, dim, need_act=True, want_taps=True,
-                  tmode_out=L.TAPS_REFLECT1):
+                  tmode_out=L.TAPS_REFLECT1, corr_out=None):
         """ResnetBlock (model/TSNet.py:10-49). taps = operand of conv_block.1 built from x (REFLECT1 or Winograd
         planes), x_res = fp32 x (residual).  Returns (taps of the output in tmode_out, fp32 output or None)."""
         t1, _ = self._conv_in(taps, (net, prefix + "conv_block.1"), "3x3", B, H, W, self._tmode3(H, W, dim, dim),
                               relu=True)
         return self._conv_in(t1, (net, prefix + "conv_block.5"), "3x3", B, H, W, tmode_out, residual=x_res,
-                             need_act=need_act, want_taps=want_taps)
+                             need_act=need_act, want_taps=want_taps, corr_out=corr_out)
 
-    def _encoder(self, net, img, img_div, lbl, n_blocks, final_tmode=None, img_mean=None):
+    def _encoder(self, net, img, img_div, lbl, n_blocks, final_tmode=None, img_mean=None, corr_out=None):
         """Encoder.forward (model/TSNet.py:52-125). Returns (fp32 NHWC feature [X,32,32,512], taps of it in
         final_tmode or None).  For n_blocks = 0 (lbl_enc) the feature is relu(IN(conv)), for img_enc it is the
         residual stream."""
@@ -200,7 +200,8 @@ class ForwardEngine:
         for blk in range(n_blocks):
             last = blk == n_blocks - 1
             t, x = self._resblock(net, f"model.{13 + blk}.", t, x, X, H, W, dim,
-                                  tmode_out=final_tmode if last else self._tmode3(H, W, dim, dim))
+                                  tmode_out=final_tmode if last else self._tmode3(H, W, dim, dim),
+                                  corr_out=corr_out if last else None)
         return x, t
 
     # ------------------------------------------------------------------ whole forward
@@ -253,6 +254,16 @@ class ForwardEngine:
             # use_prev mixes /255 and raw sources (model/TSNet.py:270-276): divide before the batched kernel
             src_imgs = [im if dv == 1.0 else im / dv for im, dv in zip(src_imgs, img_divs)]
             img_divs = [1.0] * n
+        # ---- transformation branch, step 1 (model/TSNet.py:322-323, :347-348): the masks -> class-sorted order + work
+        # list.  Needs only the bboxes, and the rank tables must exist before the last img_enc block writes the sources'
+        # correlation operands.
+        plan = ops.corr_prepare(tar_bbox.contiguous(), [bb.contiguous() for bb in src_bboxes],
+                                self._coord_table(h, w, dev), B, Cf, h, w, m)
+        corr_out = None
+        if self.bridge and self._tmode3(h, w, Cf, 2 * Cf) == L.TAPS_WINO:
+            s_hi = torch.empty((n * B * hw, Cf), dtype=torch.int16, device=dev)
+            corr_out = dict(hi=s_hi, lo=torch.empty_like(s_hi), rank=plan.rank_s,
+                            ssq=torch.empty((n * B, Cf // 32, hw), dtype=torch.float32, device=dev), done=False)
         cache_sig = None
         if src_key is not None:
             cache_sig = (src_key, n, B, tuple(img_divs), m.name, self.winograd, self.bridge, str(self.wino_chunk_kb),
@@ -260,12 +271,13 @@ class ForwardEngine:
                          tuple((p.data_ptr(), p._version) for p in self.nets["img_enc"].parameters()))
         if cache_sig is not None and self._src_cache is not None and self._src_cache[0] == cache_sig:
             src_fea, fuse_taps = self._src_cache[1]
+            corr_out = None   # cached features: their operand rows are re-ranked for this frame's masks below
         else:
             img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
             lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
             src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]),
                                                lbl_cat.contiguous(), 9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf),
-                                               img_mean=img_mean)                          # [n*B, h, w, 512]
+                                               img_mean=img_mean, corr_out=corr_out)       # [n*B, h, w, 512]
             self._src_cache = (cache_sig, (src_fea, fuse_taps)) if cache_sig is not None else None
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
@@ -273,10 +285,12 @@ class ForwardEngine:
         # prepare: masks -> class-sorted order + work list; operands are written in that order; the tensor-core tiles
         # emit partial softmax states; the finish kernel merges them, gathers the 4 bilinear taps, averages the sources
         # and writes the decoder's map_conv operand directly (torch.cat([pg, sg]) channels [0, 512), model/TSNet.py:163)
-        plan = ops.corr_prepare(tar_bbox.contiguous(), [bb.contiguous() for bb in src_bboxes],
-                                self._coord_table(h, w, dev), B, Cf, h, w, m)
-        tar_ops = ops.l2norm_split(tar_fea.view(B, hw, Cf), m, rank=plan.rank_t)
-        src_ops = ops.l2norm_split(src_fea.view(n * B, hw, Cf), m, rank=plan.rank_s)
+        tar_ops = ops.corr_operands(tar_fea.view(B, hw, Cf), m, rank=plan.rank_t)
+        if corr_out is not None and corr_out["done"]:
+            # the last img_enc bridge pass wrote the sources' operand rows + partial sums of squares
+            src_ops = (corr_out["hi"], corr_out["lo"], ops.corr_norms(corr_out["ssq"], n * B, hw, Cf // 32, plan.rank_s))
+        else:
+            src_ops = ops.corr_operands(src_fea.view(n * B, hw, Cf), m, rank=plan.rank_s)
         src_fea_v = src_fea.view(n, B, hw, Cf)
         dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
         dec_lo = torch.empty_like(dec_hi)

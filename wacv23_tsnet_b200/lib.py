@@ -56,7 +56,9 @@ class WinoGemmDesc(C.Structure):
 class WinoBridgeDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("relu", C.c_int),
                 ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int), ("scale", C.c_float), ("eps", C.c_float),
-                ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("addend_rows", C.c_longlong)]
+                ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("addend_rows", C.c_longlong),
+                ("corr_hi", C.c_void_p), ("corr_lo", C.c_void_p), ("corr_rank", C.c_void_p), ("corr_ssq", C.c_void_p),
+                ("corr_scale", C.c_float)]
 
 
 class StemConvDesc(C.Structure):
@@ -87,9 +89,11 @@ _SIGNATURES = {
     "tsnet_corr_workspace_bytes": (C.c_size_t, [C.POINTER(CorrDesc)]),
     "tsnet_corr_prepare": (C.c_int, [C.POINTER(CorrDesc), vp, C.POINTER(vp), vp, vp, C.c_size_t, vp]),
     "tsnet_corr_rank_table": (vp, [C.POINTER(CorrDesc), vp, C.c_int]),
-    "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp, C.c_int,
-                                      C.c_int, C.c_float, vp, C.c_size_t, vp]),
-    "tsnet_corr_tiles": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "tsnet_corr_warp_fwd": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, vp, vp, C.POINTER(vp), vp, vp, vp, vp,
+                                      C.c_int, C.c_int, C.c_float, vp, C.c_size_t, vp]),
+    "tsnet_corr_tiles": (C.c_int, [C.POINTER(CorrDesc), vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "tsnet_corr_operands": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]),
+    "tsnet_corr_norms": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "tsnet_corr_finish": (C.c_int, [C.POINTER(CorrDesc), C.POINTER(vp), vp, vp, vp, vp, C.c_int, C.c_int, C.c_float,
                                     vp, C.c_size_t, vp]),
     "tsnet_warp_mean_taps": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,

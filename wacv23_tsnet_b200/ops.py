@@ -202,9 +202,11 @@ def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, 
 
 
 def wino_bridge(m_buf, pw, B, H, W, mode, relu=False, addend=None, residual=None, act_out=None, act_c_off=0, taps=None,
-                c_off=0, mean_rstd_out=None, act_scale=None):
+                c_off=0, mean_rstd_out=None, act_scale=None, corr=None):
     """Fused layer boundary between two Winograd convolutions (tsnet_wino_bridge): output transform + bias (+ addend) ->
-    InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> input transform.  Returns (hi, lo, (16, H/2, W/2))."""
+    InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> input transform.  Returns (hi, lo, (16, H/2, W/2)).
+    corr = dict(hi, lo [B*H*W, C] int16, rank = device pointer of the [B, H*W] rank table, ssq fp32 [B, C/32, H*W]): the
+    activations are also written as the un-normalised operand rows of the correlation (corr_norms finishes the norms)."""
     Cc = pw.Cout
     dev = m_buf.device
     if taps is None:
@@ -227,6 +229,11 @@ def wino_bridge(m_buf, pw, B, H, W, mode, relu=False, addend=None, residual=None
         d.act_C_total, d.act_c_off = act_out.shape[-1], act_c_off
     if residual is not None:
         assert _f32(residual).shape == (B, H, W, Cc)
+    if corr is not None:
+        assert corr["hi"].shape == (B * H * W, Cc) and corr["ssq"].shape == (B, Cc // 32, H * W)
+        d.corr_hi, d.corr_lo = corr["hi"].data_ptr(), corr["lo"].data_ptr()
+        d.corr_rank, d.corr_ssq, d.corr_scale = corr["rank"], corr["ssq"].data_ptr(), mode.act_scale
+        corr["done"] = True
     with _Prof(("wino_bridge",)):
         L.check(L.load().tsnet_wino_bridge(C.byref(d), _ptr(m_buf), _ptr(pw.bias), _ptr(addend), _ptr(residual),
                                            _ptr(act_out), _ptr(mean_rstd_out), _ptr(hi), _ptr(lo), _stream()))
@@ -466,7 +473,7 @@ class CorrPlan:
 
 
 def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=100.0, sort=True,
-                 one_cta=False, chunk_kb=0):
+                 one_cta=False, chunk_kb=0, normalized=False):
     """model/TSNet.py:322-323, :347-348 (nearest down-sampling of the bbox masks) + the class-sorted work plan of the
     correlation kernel.  bboxes [B, Hb, Wb] uint8 or fp32 (full resolution)."""
     n = len(src_bbox_list)
@@ -477,7 +484,9 @@ def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, tempe
     d.bbox_h, d.bbox_w = tar_bbox.shape[-2], tar_bbox.shape[-1]
     d.bbox_dtype = 0 if tar_bbox.dtype == torch.uint8 else 1
     d.temperature, d.split, d.fmt = temperature, mode.split, mode.fmt
-    d.operand_scale = mode.corr_scale * mode.corr_scale
+    # operands: un-normalised features at the activation scale + reciprocal norms (default, corr_operands / the bridge
+    # pass), or L2-normalised unit vectors at corr_scale (l2norm_split)
+    d.operand_scale = mode.corr_scale * mode.corr_scale if normalized else mode.act_scale * mode.act_scale
     d.sort = 1 if sort else 0
     d.one_cta, d.chunk_kb = int(one_cta), chunk_kb
     lib = L.load()
@@ -493,6 +502,7 @@ def corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, tempe
     rank_t = lib.tsnet_corr_rank_table(C.byref(d), _ptr(ws), 0)
     rank_s = lib.tsnet_corr_rank_table(C.byref(d), _ptr(ws), 1)
     plan = CorrPlan(d, ws, rank_t, rank_s, B, n, Cch, h, w)
+    plan.normalized = normalized
     plan._keep = (tar_bbox, src_bbox_list, coord_table)
     return plan
 
@@ -513,9 +523,37 @@ def l2norm_split(fea, mode, out=None, rank=None):
     return hi, lo
 
 
+def corr_operands(fea, mode, rank=None, out=None):
+    """fea fp32 [B, hw, C] -> (hi, lo, rnorm): un-normalised operands x * act_scale as int16 hi/lo [B*hw, C] and
+    rnorm [B*hw] = 1 / max(||x||, 1e-12), rows at their sorted rank (tsnet_corr_operands)."""
+    B, HW, Cch = fea.shape
+    if out is None:
+        hi = torch.empty((B * HW, Cch), dtype=torch.int16, device=fea.device)
+        lo = torch.empty_like(hi)
+        rn = torch.empty((B * HW,), dtype=torch.float32, device=fea.device)
+    else:
+        hi, lo, rn = out
+    with _Prof(("corr_operands",)):
+        L.check(L.load().tsnet_corr_operands(_ptr(_f32(fea)), B, HW, Cch, mode.fmt, C.c_float(mode.act_scale),
+                                             C.c_void_p(rank) if rank else None, _ptr(hi), _ptr(lo), _ptr(rn), _stream()))
+    _count()
+    return hi, lo, rn
+
+
+def corr_norms(ssq_part, B, HW, slabs, rank):
+    """[B, slabs, HW] partial sums of squares (tsnet_wino_bridge) -> rnorm [B*HW] at the sorted rank."""
+    rn = torch.empty((B * HW,), dtype=torch.float32, device=ssq_part.device)
+    with _Prof(("corr_norms",)):
+        L.check(L.load().tsnet_corr_norms(_ptr(_f32(ssq_part)), B, HW, slabs, C.c_void_p(rank) if rank else None,
+                                          _ptr(rn), _stream()))
+    _count()
+    return rn
+
+
 def corr_warp(plan, tar_ops, src_ops, src_fea_list, mode, want_grids=False, want_mean=True, taps=None, c_off=0):
-    """plan = corr_prepare(...); tar_ops = (hi, lo) [B*hw, C] and src_ops = (hi, lo) [n*B*hw, C] from l2norm_split with
-    the plan's rank tables; src_fea_list n x fp32 [B, hw, C].  Returns (out_mean fp32 [B, hw, C] or None,
+    """plan = corr_prepare(...); tar_ops = (hi, lo[, rnorm]) [B*hw, C] and src_ops = (hi, lo[, rnorm]) [n*B*hw, C] from
+    corr_operands (or l2norm_split for a `normalized` plan) with the plan's rank tables; src_fea_list n x fp32
+    [B, hw, C].  Returns (out_mean fp32 [B, hw, C] or None,
     grids [n, B, h, w, 2] or None); `taps` = (hi, lo) [B, h, w, Cp]: the mean is also written as hi/lo operands into
     the channel window [c_off, c_off + C)."""
     n, B, h, w, Cch = plan.n, plan.B, plan.h, plan.w, plan.C
@@ -527,9 +565,13 @@ def corr_warp(plan, tar_ops, src_ops, src_fea_list, mode, want_grids=False, want
     need_fea = want_mean or taps is not None
     fea_ptrs = (C.c_void_p * n)(*[_f32(f).data_ptr() for f in src_fea_list]) if need_fea else None
     lib = L.load()
+    rn_t = tar_ops[2] if len(tar_ops) > 2 else None
+    rn_s = src_ops[2] if len(src_ops) > 2 else None
+    assert (rn_t is None) == (rn_s is None) == bool(getattr(plan, "normalized", False)), "operand kind / plan mismatch"
     with _Prof(("corr_tiles",)):
         L.check(lib.tsnet_corr_tiles(C.byref(plan.desc), _ptr(tar_ops[0]), _ptr(tar_ops[1]), _ptr(src_ops[0]),
-                                     _ptr(src_ops[1]), _ptr(plan.ws), plan.ws.numel(), _stream()))
+                                     _ptr(src_ops[1]), _ptr(rn_t), _ptr(rn_s), _ptr(plan.ws), plan.ws.numel(),
+                                     _stream()))
     _count()
     with _Prof(("corr_finish",)):
         L.check(lib.tsnet_corr_finish(C.byref(plan.desc), fea_ptrs, _ptr(out), _ptr(grids), _ptr(hi), _ptr(lo),
@@ -540,15 +582,16 @@ def corr_warp(plan, tar_ops, src_ops, src_fea_list, mode, want_grids=False, want
 
 
 def corr_chain(tar_fea, src_fea, tar_bbox, src_bbox_list, coord_table, mode, temperature=100.0, want_grids=True,
-               want_mean=False, taps=None, c_off=0, sort=True, one_cta=False):
+               want_mean=False, taps=None, c_off=0, sort=True, one_cta=False, normalized=False):
     """The whole transformation branch on raw features (model/TSNet.py:319-366, :392): tar_fea fp32 [B, hw, C],
     src_fea fp32 [n, B, hw, C] -> (mean of the warped sources [B, hw, C] or None, warp grids [n, B, h, w, 2] or None)."""
     n, B, hw, Cch = src_fea.shape
     h = w = int(round(hw ** 0.5))
     plan = corr_prepare(tar_bbox, src_bbox_list, coord_table, B, Cch, h, w, mode, temperature=temperature, sort=sort,
-                        one_cta=one_cta)
-    tar_ops = l2norm_split(tar_fea, mode, rank=plan.rank_t)
-    src_ops = l2norm_split(src_fea.view(n * B, hw, Cch), mode, rank=plan.rank_s)
+                        one_cta=one_cta, normalized=normalized)
+    prep = l2norm_split if normalized else corr_operands
+    tar_ops = prep(tar_fea, mode, rank=plan.rank_t)
+    src_ops = prep(src_fea.view(n * B, hw, Cch), mode, rank=plan.rank_s)
     return corr_warp(plan, tar_ops, src_ops, [src_fea[i] for i in range(n)], mode, want_grids=want_grids,
                      want_mean=want_mean, taps=taps, c_off=c_off)
 
