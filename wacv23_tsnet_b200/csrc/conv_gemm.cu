@@ -811,6 +811,10 @@ constexpr int kStemFold = 8;  // direct mode: channels per folded horizontal tap
 // (reflect(y0 - 3 + r), reflect(x0 - 3 + px + s)) in 16-byte chunk s ^ (R & 7); chunk 7 ^ (R & 7) stays zero.  Every
 // source pixel vector (torch.cat([img / 255, lbl]) + CoordConv channels, model/TSNet.py:107-125, :312; same rounding
 // sequence as stem_taps_kernel) is computed once and stored to the <= 7 rows that use it.
+// SPEC = true: the channel layout (NIMG image + NLBL label channels, input kinds IK / LK) is a compile-time constant, so
+// the per-channel selection below folds away -- the generic version executed ~940 instructions per source pixel and made
+// the producers, not the tensor pipe, the bound of the kernel.
+template <bool SPEC, int NIMG, int NLBL, int IK, int LK>
 __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8_t* a_hi, uint8_t* a_lo, int img, int y0,
                                                  int x0, int pt) {
   const int H = args.f_H, W = args.f_W;
@@ -818,7 +822,8 @@ __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8
   constexpr int SW = kVrW + 6, SR = kVrRows + 6;
   constexpr int NP = (SR * SW + 95) / 96;  // source pixels per producer thread (4)
   constexpr int NRAW = kStemFold - 3;      // image + label channels (<= 5)
-  const int n_img = args.in_Cimg, n_il = args.in_Cimg + args.in_Clbl;
+  const int n_img = SPEC ? NIMG : args.in_Cimg, n_lbl = SPEC ? NLBL : args.in_Clbl, n_il = n_img + n_lbl;
+  const int img_kind = SPEC ? IK : args.in_img_kind, lbl_kind = SPEC ? LK : args.in_lbl_kind;
   // ---- all global loads of this thread's pixels first (one exposed latency per tile instead of one per pixel)
   float raw[NP][NRAW];
   int ysv[NP], xsv[NP];
@@ -832,7 +837,7 @@ __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8
     ysv[k] = ys; xsv[k] = xs;
     const size_t pix = static_cast<size_t>(ys) * W + xs;
     int cls = -1;
-    if (idx < SR * SW && args.in_lbl_kind != 0)
+    if (idx < SR * SW && lbl_kind != 0)
       cls = static_cast<const uint8_t*>(args.in_lbl)[static_cast<size_t>(img) * plane + pix];
 #pragma unroll
     for (int c = 0; c < NRAW; ++c) {
@@ -840,11 +845,11 @@ __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8
       if (idx < SR * SW) {
         if (c < n_img) {
           const size_t off = (static_cast<size_t>(img) * n_img + c) * plane + pix;
-          if (args.in_img_kind == 0) q = static_cast<const float*>(args.in_img)[off];
+          if (img_kind == 0) q = static_cast<const float*>(args.in_img)[off];
           else q = static_cast<float>(static_cast<const uint8_t*>(args.in_img)[off]);
         } else if (c < n_il) {
-          if (args.in_lbl_kind == 0)
-            q = static_cast<const float*>(args.in_lbl)[(static_cast<size_t>(img) * args.in_Clbl + (c - n_img)) * plane + pix];
+          if (lbl_kind == 0)
+            q = static_cast<const float*>(args.in_lbl)[(static_cast<size_t>(img) * n_lbl + (c - n_img)) * plane + pix];
           else
             q = cls == c - n_img ? 1.f : 0.f;
         }
@@ -868,7 +873,7 @@ __device__ __forceinline__ void stem_direct_fill(const ConvGemmArgs& args, uint8
       float q = 0.f;
       if (c < NRAW && c < n_img) {
         float x = raw[k][c < NRAW ? c : 0];
-        if (args.in_img_kind != 0) x = __fadd_rn(x, -args.in_mean[c < 3 ? c : 2]);
+        if (img_kind != 0) x = __fadd_rn(x, -args.in_mean[c < 3 ? c : 2]);
         q = __fdiv_rn(x, args.in_div);
       } else if (c < NRAW && c < n_il) {
         q = raw[k][c < NRAW ? c : 0];
@@ -949,9 +954,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
   const uint32_t tmem_base = *tmem_base_smem;
 
   if (warp < 4) {
-    // control warp group: 40 registers per thread; the direct-input producers (loads + conversions) get 128 -- the
+    // control warp group: 40 registers per thread; the direct-input producers (loads + conversions) get 120 (4 x 32 x 120 + 8 x 32 x 192 = the 64512 registers the CTA was launched with) -- the
     // accumulate warps of this N = 64 kernel hold only 32 accumulators and make do with 192 instead of 224
-    if constexpr (DIRECT) asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    if constexpr (DIRECT) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (DIRECT && warp != 1) {
       // ===================== direct-input producers (warps 0, 2, 3) =====================
@@ -978,7 +983,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_vr_kernel(const __g
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         mbar_wait(&a_empty[buf], ph ^ 1);   // the MMAs of the tile that used this buffer have read it
         uint8_t* st = a_sm + buf * 2 * a_bytes;
-        stem_direct_fill(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        // (warp-uniform dispatch on the input description; the two face-configuration encoders are specialised)
+        const int key = args.in_Cimg * 100 + args.in_Clbl * 10 + args.in_img_kind * 2 + args.in_lbl_kind;
+        if (key == 320) stem_direct_fill<true, 3, 2, 0, 0>(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        else if (key == 323) stem_direct_fill<true, 3, 2, 1, 1>(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        else if (key == 20) stem_direct_fill<true, 0, 2, 0, 0>(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        else if (key == 21) stem_direct_fill<true, 0, 2, 0, 1>(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
+        else stem_direct_fill<false, 0, 0, 0, 0>(args, st, st + a_bytes, img, ty * kVrRows, tx * kVrW, pt);
         fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane_id() == 0) mbar_arrive(&a_full[buf]);
