@@ -583,8 +583,9 @@ def main():
     ap.add_argument("--wino-chunk-kb", dest="wino_chunk_kb", type=int, default=0,
                     help="experiment: K blocks accumulated in TMEM per promotion in the Winograd GEMMs (default: the "
                          "engine's parity-validated 2; 4 is faster but misses the image tolerance on one golden)")
-    ap.add_argument("--no-direct-stem", dest="direct_stem", action="store_false",
-                    help="materialise the stem operand (tsnet_stem_taps) instead of generating it inside the stem kernel")
+    ap.add_argument("--direct-stem", dest="direct_stem", action="store_true",
+                    help="generate the stem operand inside the stem kernel (tsnet_stem_conv_fwd) instead of materialising "
+                         "it with tsnet_stem_taps (less DRAM traffic, measured slower: opt-in)")
     ap.add_argument("--winograd-unfused", dest="winograd", action="store_const", const="unfused",
                     help="Winograd with separate transform passes instead of the fused bridge pass (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

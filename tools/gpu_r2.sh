@@ -41,13 +41,13 @@ for st in $STAGES; do
       timeout 300 python tools/parity_report.py --winograd off >> $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
     parity_mix)
-      timeout 700 python tools/parity_report.py --winograd bridge --chunk-kb 2 img_enc=2,default=4 img_enc=4,default=2 3 > $OUT/parity_$TAG.log 2>&1
+      timeout 700 python tools/parity_report.py --winograd bridge --chunk-kb img_enc=2,default=4 > $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
     parity_sf)
       timeout 900 python tools/parity_report.py --winograd bridge --small-first --chunk-kb img_enc=2,default=4 img_enc=3,default=4 4 > $OUT/parity_$TAG.log 2>&1
       grep -E "WORST|Error|error" $OUT/parity_$TAG.log ;;
     bench_nostem)
-      timeout 400 python bench.py --steps 10 --warmup 3 --no-direct-stem --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_nostem_$TAG.json 2> $OUT/bench_nostem_$TAG.err
+      timeout 400 python bench.py --steps 10 --warmup 3 --direct-stem --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_nostem_$TAG.json 2> $OUT/bench_nostem_$TAG.err
       cut -c1-300 $OUT/bench_nostem_$TAG.json ;;
     tests_corr)
       timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "corr or stem or bridge or golden or train_mode or cache or full_batch" > $OUT/pytest_corr_$TAG.log 2>&1

@@ -50,8 +50,11 @@ class ForwardEngine:
         self._coord = {}
         self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))
         # encoder stems straight from the raw network inputs (tsnet_stem_conv_fwd) wherever the channels fit one
-        # 8-channel folded tap (face configuration); False keeps the materialised tap source (tsnet_stem_taps)
-        self.direct_stem = True
+        # 8-channel folded tap (face configuration) instead of the materialised tap source (tsnet_stem_taps).  Measured on
+        # the B200 (bs=32, n=3): layer DRAM traffic 4.96 GB -> 1.78 GB, but the three producer warps are latency-bound on
+        # their scattered plane loads: 2.42 + 0.71 ms against 1.43 + 0.45 + 0.70 ms (stem_taps) for the materialised
+        # path.  Opt-in until the producers are software-pipelined across tiles.
+        self.direct_stem = False
 
     def invalidate(self):
         """Drop every packed weight.  Needed after parameter writes that do not bump the tensor version
