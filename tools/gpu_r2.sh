@@ -52,6 +52,8 @@ for st in $STAGES; do
     tests_corr)
       timeout 900 python -m pytest tests -m gpu -q --durations=5 -k "corr or stem or bridge or golden or train_mode or cache or full_batch" > $OUT/pytest_corr_$TAG.log 2>&1
       echo "pytest exit $?" >> $OUT/pytest_corr_$TAG.log; tail -25 $OUT/pytest_corr_$TAG.log ;;
+    demo)
+      timeout 300 python tools/demo_point.py > $OUT/demo_$TAG.log 2>&1; tail -6 $OUT/demo_$TAG.log ;;
     bench_c4)
       timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
       cut -c1-300 $OUT/bench_c4_$TAG.json ;;

@@ -273,15 +273,22 @@ class ForwardEngine:
                          self.direct_stem,
                          tuple((p.data_ptr(), p._version) for p in self.nets["img_enc"].parameters()))
         if cache_sig is not None and self._src_cache is not None and self._src_cache[0] == cache_sig:
-            src_fea, fuse_taps = self._src_cache[1]
+            src_fea, fuse_taps, cached_ssq = self._src_cache[1]
             corr_out = None   # cached features: their operand rows are re-ranked for this frame's masks below
         else:
+            cached_ssq = None
             img_cat = torch.cat(src_imgs, 0) if n > 1 else src_imgs[0]
             lbl_cat = torch.cat(src_lbls, 0) if n > 1 else src_lbls[0]
             src_fea, fuse_taps = self._encoder("img_enc", img_cat.contiguous(), float(img_divs[0]),
                                                lbl_cat.contiguous(), 9, final_tmode=self._tmode3(h, w, Cf, 2 * Cf),
                                                img_mean=img_mean, corr_out=corr_out)       # [n*B, h, w, 512]
-            self._src_cache = (cache_sig, (src_fea, fuse_taps)) if cache_sig is not None else None
+            if cache_sig is not None:
+                # the per-pixel partial sums of squares are position-indexed (independent of this frame's mask ranks): a
+                # later cache hit rebuilds bit-identical reciprocal norms from them
+                ssq = corr_out["ssq"] if (corr_out is not None and corr_out["done"]) else None
+                self._src_cache = (cache_sig, (src_fea, fuse_taps, ssq))
+            else:
+                self._src_cache = None
         tar_fea, _ = self._encoder("lbl_enc", None, 1.0, tar_lbl.contiguous(), 0)        # [B, h, w, 512]
 
         # ---- transformation branch (model/TSNet.py:319-366, 392)
@@ -294,6 +301,8 @@ class ForwardEngine:
             src_ops = (corr_out["hi"], corr_out["lo"], ops.corr_norms(corr_out["ssq"], n * B, hw, Cf // 32, plan.rank_s))
         else:
             src_ops = ops.corr_operands(src_fea.view(n * B, hw, Cf), m, rank=plan.rank_s)
+            if cached_ssq is not None:   # cache hit after a bridge-emitting miss: same norms as the miss computed
+                src_ops = (src_ops[0], src_ops[1], ops.corr_norms(cached_ssq, n * B, hw, Cf // 32, plan.rank_s))
         src_fea_v = src_fea.view(n, B, hw, Cf)
         dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
         dec_lo = torch.empty_like(dec_hi)
