@@ -276,6 +276,9 @@ int tsnet_stem_conv_fwd(const tsnet_stem_conv_desc* d, const void* img_nchw, con
  * is integer indexing inside tsnet_corr_prepare.  coord_table = h + w floats: torch.linspace(-1,1,h) then
  * torch.linspace(-1,1,w) (:301-302).  The workspace (tsnet_corr_workspace_bytes, 256 B aligned, caller-owned) carries
  * everything between the calls; it may be reused by the next forward on the same stream. */
+/* Limits of one call (checked; the message is in tsnet_last_error()): n_src <= 12 (the reference's callers use 1..8;
+ * split a larger source set over several calls and average the means), B <= 1024, h*w a multiple of 256 and <= 1024,
+ * C a multiple of 128 and <= 1024.  The reference geometry is h = w = 32, C = 512. */
 typedef struct {
   int B, n_src, C, h, w;
   int bbox_h, bbox_w, bbox_dtype; /* 0 = uint8, 1 = fp32 */

@@ -27,7 +27,7 @@ for st in $STAGES; do
     ncu_wino)
       # Winograd GEMM (2-CTA kernel; the first conv_gemm2 launches of a forward are the 64->128/128->256 stride-2 convs:
       # skip into the ResnetBlock region), input and output transform passes
-      timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm2_kernel -s 60 -c 1 \
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm2_kernel -s 45 -c 1 \
           -f -o $OUT/prof_winogemm_$TAG $FWD > /dev/null 2>&1
       timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_input_kernel -s 30 -c 1 \
           -f -o $OUT/prof_winoin_$TAG $FWD > /dev/null 2>&1
@@ -54,6 +54,19 @@ for st in $STAGES; do
       echo "pytest exit $?" >> $OUT/pytest_corr_$TAG.log; tail -25 $OUT/pytest_corr_$TAG.log ;;
     demo)
       timeout 300 python tools/demo_point.py > $OUT/demo_$TAG.log 2>&1; tail -6 $OUT/demo_$TAG.log ;;
+    bench_c3)
+      timeout 400 python - > $OUT/bench_c3_$TAG.json 2> $OUT/bench_c3_$TAG.err <<'PY'
+import sys, runpy
+sys.argv = ["bench.py", "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-torch-cuda-baseline", "--no-fast-point"]
+import wacv23_tsnet_b200.engine as E
+_orig = E.ForwardEngine.__init__
+def _init(self, *a, **k):
+    _orig(self, *a, **k)
+    self.wino_chunk_kb = {"img_enc": 3, "default": 4}
+E.ForwardEngine.__init__ = _init
+runpy.run_path("bench.py", run_name="__main__")
+PY
+      cut -c1-300 $OUT/bench_c3_$TAG.json ;;
     bench_c4)
       timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
       cut -c1-300 $OUT/bench_c4_$TAG.json ;;
@@ -64,7 +77,7 @@ for st in $STAGES; do
       timeout 400 python bench.py --steps 10 --warmup 3 --winograd-unfused --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_unfused_$TAG.json 2> $OUT/bench_unfused_$TAG.err
       cut -c1-300 $OUT/bench_unfused_$TAG.json ;;
     ncu_bridge)
-      timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_bridge_kernel -s 20 -c 1 \
+      timeout 300 ncu --set full --clock-control none --import-source on -k regex:wino_bridge_kernel -s 30 -c 2 \
           -f -o $OUT/prof_bridge_$TAG $FWD > /dev/null 2>&1 ;;
     winobench)
       timeout 300 python tools/wino_bench.py > $OUT/winobench_$TAG.log 2>&1; cat $OUT/winobench_$TAG.log ;;

@@ -23,7 +23,7 @@ RAW_KEYS = [
     "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
-    "smsp__inst_executed.sum",
+    "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
 ]
 
 
@@ -70,58 +70,71 @@ def launches_summary(tag):
 
 
 def raw_metrics(rep):
+    """every kernel of an ncu report as {metric: (value, unit)} dicts"""
     r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
     rows = list(csv.reader(io.StringIO(r.stdout)))
     if len(rows) < 3:
-        return None
-    h, units, v = rows[0], rows[1], rows[2]
-    d = {}
-    for i, n in enumerate(h):
-        d[n] = (v[i], units[i])
-    return d
+        return []
+    h, units = rows[0], rows[1]
+    return [{n: (v[i], units[i]) for i, n in enumerate(h)} for v in rows[2:]]
+
+
+_UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 
 
 def kernel_summary(tag, which, title, algo_note):
     rep = os.path.join(OUT, f"prof_{which}_{tag}.ncu-rep")
     if not os.path.isfile(rep):
         return None
-    d = raw_metrics(rep)
-    if d is None:
+    ks = raw_metrics(rep)
+    if not ks:
         return None
-    out = [f"# {title} ({tag})", "", f"`ncu --set full --clock-control none --import-source on` — report `prof_{which}_{tag}.ncu-rep` "
-           "(kept in gpurun_out/, not tracked: binary).", "", f"Kernel: `{d.get('Kernel Name', ('?', ''))[0]}`", "",
-           "| metric | value | unit |", "|---|---|---|"]
-    for k in RAW_KEYS:
-        if k in d:
-            out.append(f"| `{k}` | {d[k][0]} | {d[k][1]} |")
-    try:
-        rd = float(d["dram__bytes_read.sum"][0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_read.sum"][1]]
-        wr = float(d["dram__bytes_write.sum"][0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_write.sum"][1]]
-        out += ["", f"DRAM traffic per launch (read + write) = **{(rd + wr) / 1e6:.1f} MB**. {algo_note}"]
-    except (KeyError, ValueError):
-        pass
-    out.append("")
+    out = [f"# {title} ({tag})", "", f"`ncu --set full --clock-control none --import-source on` -- report "
+           f"`prof_{which}_{tag}.ncu-rep` (kept in gpurun_out/, not tracked: binary).", ""]
+    total = 0.0
+    for d in ks:
+        out += [f"Kernel: `{d.get('Kernel Name', ('?', ''))[0]}`  grid {d.get('Grid Size', ('?', ''))[0]}", "",
+                "| metric | value | unit |", "|---|---|---|"]
+        for k in RAW_KEYS:
+            if k in d:
+                out.append(f"| `{k}` | {d[k][0]} | {d[k][1]} |")
+        try:
+            rd = float(d["dram__bytes_read.sum"][0]) * _UNIT[d["dram__bytes_read.sum"][1]]
+            wr = float(d["dram__bytes_write.sum"][0]) * _UNIT[d["dram__bytes_write.sum"][1]]
+            total += rd + wr
+            out += ["", f"DRAM traffic of this launch (read + write) = **{(rd + wr) / 1e6:.1f} MB**.", ""]
+        except (KeyError, ValueError):
+            out.append("")
+    if len(ks) > 1:
+        out += [f"DRAM traffic of all {len(ks)} launches = **{total / 1e6:.1f} MB**.", ""]
+    out += [algo_note, ""]
     return "\n".join(out)
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
     os.makedirs(PROF, exist_ok=True)
     for name, text in (
         (f"{tag}_launches.md", launches_summary(tag)),
-        (f"{tag}_conv_gemm.md", kernel_summary(tag, "conv", "conv_gemm_kernel<256>, 512->512 3x3 @32x32, 96 samples",
-                                               "Algorithmic bytes: A tap source 2 x 96*34*34*512*2 B = 227 MB + raw output "
-                                               "96*1024*512*4 B = 201 MB + weights 9.4 MB.")),
-        (f"{tag}_corr_tiles.md", kernel_summary(tag, "corr", "corr_tile_kernel (tcgen05 similarity tiles + softmax partial states)",
-                                                "Algorithmic bytes of the whole correlation chain (SURVEY section 8d): "
-                                                "10,502,144 B/frame x 32 frames = 336.1 MB; this kernel reads the 16-bit "
-                                                "hi/lo operands (268 MB) through L2 several times and writes 12.6 MB of states.")),
-        (f"{tag}_corr_finish.md", kernel_summary(tag, "finish", "warp_mean_taps_kernel<true> = corr_finish (state merge + "
-                                                 "4-tap grid_sample + source mean -> map_conv operand)",
-                                                 "Reads the fp32 source features (201 MB, 4 taps each: L2-amplified) and "
-                                                 "writes the 67 MB hi/lo operand.")),
-        (f"{tag}_stem_vr.md", kernel_summary(tag, "stem", "conv_gemm_vr_kernel (kw-folded 7x7 stem, 96 x 256 x 256, Cout 64)",
-                                             "Algorithmic bytes: tap source 1.65 GB + raw output 1.61 GB + statistics 0.1 GB.")),
+        (f"{tag}_wino_gemm.md", kernel_summary(
+            tag, "winogemm", "conv_gemm2_kernel in batched-plane mode = the 16 Winograd plane GEMMs of one layer",
+            "Algorithmic bytes of the 512->512 layer over 96 samples: V 96*16*256*512*4 B = 805 MB read (each A tile is read "
+            "by two channel slabs: the second read is an L2 hit) + M 805 MB written + 16 MB of weights; the 1024->1024 layer "
+            "is twice that in each direction.  Executed FLOPs = 16/36 of the 3x3 convolution's.")),
+        (f"{tag}_bridge.md", kernel_summary(
+            tag, "bridge", "wino_bridge_kernel (output transform + InstanceNorm + ReLU / residual + input transform)",
+            "Algorithmic bytes per launch over X samples of C channels: M X*16*256*C*4 B read + V the same written "
+            "(+ X*1024*C*4 B residual read and act_out written on the second convolution of a ResnetBlock).")),
+        (f"{tag}_wino_input.md", kernel_summary(tag, "winoin", "wino_input_kernel (pass T: norm + pad + B^T d B + split)", "")),
+        (f"{tag}_wino_output.md", kernel_summary(tag, "winoout", "wino_output_kernel (pass I: A^T M A + bias + statistics)", "")),
+        (f"{tag}_corr_chain_dram.md", kernel_summary(
+            tag, "corr", "every kernel of the correlation chain of one forward (bs=32, n_source=3)",
+            "Algorithmic bytes of the chain (SURVEY section 8d): 10,502,144 B/frame x 32 frames = 336.1 MB.  The sources' "
+            "operand rows (201 MB) are written by the last img_enc bridge pass and are not part of these launches.")),
+        (f"{tag}_stem_direct.md", kernel_summary(
+            tag, "stem", "conv_gemm_vr_kernel<true> (direct-input stem, 96 x 256 x 256, Cout 64; opt-in)",
+            "Algorithmic bytes: raw inputs 96*5*65536*4 B = 126 MB + raw output 1.61 GB + statistics; the materialised "
+            "path reads a 1.65 GB tap source on top (3.31 GB per launch, plus the 1.65 GB stem_taps write).")),
     ):
         if text:
             open(os.path.join(PROF, name), "w").write(text)

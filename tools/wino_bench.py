@@ -33,7 +33,7 @@ for (B, Cin, Cout) in ((96, 512, 512), (96, 1024, 1024), (32, 512, 512)):
     xs = x[:2].permute(0, 3, 1, 2)
     ref = F.conv2d(F.pad(xs, (1, 1, 1, 1), mode="reflect").double(), w.double(), b.double()).permute(0, 2, 3, 1)
     mbuf = torch.empty(16 * B * 256 * Cout, dtype=torch.float32, device="cuda")
-    for ck in (2, 4, 8):
+    for ck in (2, 3, 4, 8):
         y, _ = ops.wino_conv(taps, pw, B, 32, 32, m, m.act_scale, chunk_kb=ck, m_buf=mbuf)
         err = float((y[:2].double() - ref).abs().max() / ref.abs().max())
         d = L.WinoGemmDesc()
