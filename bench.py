@@ -266,6 +266,8 @@ def run_b200(args):
     if args.wino_chunk_kb > 0:
         net._engine.wino_chunk_kb = args.wino_chunk_kb
     net._engine.direct_stem = bool(args.direct_stem)
+    if args.bridge_variant >= 0:
+        net._engine.bridge_variant = args.bridge_variant
     log("model built")
 
     from oracle.synth import IMG_MEAN as _MEAN
@@ -529,7 +531,7 @@ def run_b200(args):
                                        f"n_blocks={nb}, uint8 rectangular bbox, random-init weights",
                            "global_batch": bs * world, "parallelism": f"dp{world} (batch rows sharded, no collective)",
                            "math_mode": args.math, "winograd_f2x2_3x3": (args.winograd if isinstance(args.winograd, str) else bool(args.winograd)),
-                           "wino_chunk_kb": net._engine.wino_chunk_kb, "direct_stem": net._engine.direct_stem,
+                           "wino_chunk_kb": net._engine.wino_chunk_kb, "direct_stem": net._engine.direct_stem, "bridge_variant": net._engine.bridge_variant,
                            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                         "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
@@ -586,6 +588,8 @@ def main():
     ap.add_argument("--direct-stem", dest="direct_stem", action="store_true",
                     help="generate the stem operand inside the stem kernel (tsnet_stem_conv_fwd) instead of materialising "
                          "it with tsnet_stem_taps (less DRAM traffic, measured slower: opt-in)")
+    ap.add_argument("--bridge-variant", dest="bridge_variant", type=int, default=-1,
+                    help="experiment: tsnet_wino_bridge_desc.variant (0 = 32-channel slabs, 1 = 16-channel slabs, 2 CTAs/SM)")
     ap.add_argument("--winograd-unfused", dest="winograd", action="store_const", const="unfused",
                     help="Winograd with separate transform passes instead of the fused bridge pass (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

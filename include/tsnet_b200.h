@@ -174,6 +174,8 @@ typedef struct {
   const uint16_t* corr_rank;
   float* corr_ssq;
   float corr_scale;
+  int variant;                  /* 0: 32-channel slabs, 1 CTA per SM (128 KB image buffer); 1: 16-channel slabs, 2 CTAs per SM
+                                   (corr_ssq then has C / 16 slabs).  Same function, different launch geometry. */
 } tsnet_wino_bridge_desc;
 int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m, const float* bias, const float* addend,
                       const float* residual, float* act_out, float* mean_rstd_out, uint16_t* v_hi, uint16_t* v_lo,

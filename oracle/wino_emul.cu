@@ -33,30 +33,37 @@ extern "C" void wino_emul_output(const float* m, const float* bias, const float*
     for (int t = 0; t < nthreads; ++t) wino_output_body(a, blk, t, nthreads);
 }
 
+template <int CS, int PS>
+static void emul_bridge(const WinoBridgeArgs& a, int nthreads) {
+  const size_t bytes = wino_bridge_smem_bytes<CS, PS>(a.H, a.W, nthreads);
+  uint8_t* smem = new uint8_t[bytes + 16];
+  float* s_y = reinterpret_cast<float*>(smem);
+  double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(a.H) * a.W * PS * 4);
+  float* s_mr = reinterpret_cast<float*>(s_part + (nthreads / CS) * CS * 2);
+  const int blocks = a.B * (a.C / CS);
+  for (int blk = 0; blk < blocks; ++blk) {   // phases separated by block-wide barriers in the kernel
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_a<CS, PS>(a, blk, t, nthreads, s_y);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s1<CS, PS>(a, t, nthreads, s_y, s_part);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s2<CS, PS>(a, blk, t, nthreads, s_part, s_mr);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_b<CS, PS>(a, blk, t, nthreads, s_y, s_mr);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_n<CS, PS>(a, blk, t, nthreads, s_y);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_c<CS, PS>(a, blk, t, nthreads, s_y);
+  }
+  delete[] smem;
+}
+
 extern "C" void wino_emul_bridge(const float* m, const float* bias, const float* addend, long long addend_rows,
                                  const float* residual, float* act_out, float* mean_rstd_out, uint16_t* hi, uint16_t* lo,
                                  int B, int H, int W, int C, int relu, int Cp_total, int c_off, int fmt, int act_C_total,
                                  int act_c_off, float scale, float eps, int nthreads, uint16_t* corr_hi,
-                                 uint16_t* corr_lo, const uint16_t* corr_rank, float* corr_ssq, float corr_scale) {
+                                 uint16_t* corr_lo, const uint16_t* corr_rank, float* corr_ssq, float corr_scale,
+                                 int variant) {
   WinoBridgeArgs a;
   a.corr_hi = corr_hi; a.corr_lo = corr_lo; a.corr_rank = corr_rank; a.corr_ssq = corr_ssq; a.corr_scale = corr_scale;
   a.m = m; a.bias = bias; a.addend = addend; a.residual = residual; a.act_out = act_out; a.mean_rstd_out = mean_rstd_out;
   a.hi = hi; a.lo = lo; a.B = B; a.H = H; a.W = W; a.C = C; a.relu = relu; a.Cp_total = Cp_total; a.c_off = c_off;
   a.fmt = fmt; a.act_C_total = act_C_total; a.act_c_off = act_c_off; a.addend_rows = addend_rows; a.scale = scale;
   a.eps = eps;
-  const size_t bytes = wino_bridge_smem_bytes(H, W, nthreads);
-  uint8_t* smem = new uint8_t[bytes + 16];
-  float* s_y = reinterpret_cast<float*>(smem);
-  double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(H) * W * kBridgePS * 4);
-  float* s_mr = reinterpret_cast<float*>(s_part + (nthreads / kBridgeCS) * kBridgeCS * 2);
-  const int blocks = B * (C / kBridgeCS);
-  for (int blk = 0; blk < blocks; ++blk) {   // phases separated by block-wide barriers in the kernel
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_a(a, blk, t, nthreads, s_y);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s1(a, t, nthreads, s_y, s_part);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s2(a, blk, t, nthreads, s_part, s_mr);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_b(a, blk, t, nthreads, s_y, s_mr);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_n(a, blk, t, nthreads, s_y);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_c(a, blk, t, nthreads, s_y);
-  }
-  delete[] smem;
+  if (variant == 1) emul_bridge<16, 24>(a, nthreads);
+  else emul_bridge<32, 32>(a, nthreads);
 }

@@ -700,8 +700,9 @@ def test_wino_passes_equal_host_emulation():
     assert _relerr(st_g.cpu(), st_c) < 1e-6
 
 
+@pytest.mark.parametrize("variant", [0, 1])   # 32-channel slabs (1 CTA / SM) and 16-channel slabs (2 CTAs / SM)
 @pytest.mark.parametrize("relu,with_res,with_addend", [(True, False, False), (False, True, False), (True, False, True)])
-def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
+def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend, variant):
     """tsnet_wino_bridge (output transform + InstanceNorm + ReLU / residual + input transform in one pass, statistics
     CTA-local in fp64) against the separate passes tsnet_wino_output -> tsnet_instnorm_reduce -> tsnet_build_taps(WINO)."""
     from wacv23_tsnet_b200 import lib as L, ops
@@ -727,7 +728,7 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
     hf = torch.zeros(B * 16, 16, 16, Cout + 64, dtype=torch.int16, device="cuda")
     lf = torch.zeros_like(hf)
     ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, act_out=act_f, act_c_off=64,
-                    taps=(hf, lf), c_off=64, mean_rstd_out=mr_f)
+                    taps=(hf, lf), c_off=64, mean_rstd_out=mr_f, variant=variant)
     torch.cuda.synchronize()
     assert _relerr(mr_f[..., 0], mr[..., 0]) < 1e-5 and _relerr(mr_f[..., 1], mr[..., 1]) < 1e-5
     assert _relerr(act_f[..., 64:], act_s) < 2e-6 and float(act_f[..., :64].abs().max()) == 0.0
@@ -738,20 +739,20 @@ def test_wino_bridge_vs_separate_passes(relu, with_res, with_addend):
     # equal what the stand-alone operand pass makes of the same activations
     rank = torch.stack([torch.randperm(1024) for _ in range(B)]).to(torch.int16).cuda()
     corr = dict(hi=torch.zeros(B * 1024, Cout, dtype=torch.int16, device="cuda"), rank=rank.data_ptr(),
-                ssq=torch.zeros(B, Cout // 32, 1024, device="cuda"))
+                ssq=torch.zeros(B, Cout // (16 if variant else 32), 1024, device="cuda"))
     corr["lo"] = torch.zeros_like(corr["hi"])
-    ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, corr=corr)
-    rn_b = ops.corr_norms(corr["ssq"], B, 1024, Cout // 32, rank.data_ptr())
+    ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, corr=corr, variant=variant)
+    rn_b = ops.corr_norms(corr["ssq"], B, 1024, corr["ssq"].shape[1], rank.data_ptr())
     oh, ol, rn_o = ops.corr_operands(act_f[..., 64:].contiguous().view(B, 1024, Cout), m, rank=rank.data_ptr())
     torch.cuda.synchronize()
     assert torch.equal(corr["hi"], oh) and torch.equal(corr["lo"], ol)
     assert _relerr(rn_b, rn_o) < 1e-6
     # deterministic, and a sample does not depend on the batch it rides in
-    h2, l2, _ = ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res)
+    h2, l2, _ = ops.wino_bridge(mbuf, pw, B, 32, 32, m, relu=relu, addend=addend, residual=res, variant=variant)
     t1 = ops.build_taps(x[1:2].contiguous(), m, L.TAPS_WINO)
     m1 = ops.wino_gemm(t1, pw, 1, 32, 32, m, m.act_scale)
     h1, l1, _ = ops.wino_bridge(m1, pw, 1, 32, 32, m, relu=relu, addend=addend,
-                                residual=None if res is None else res[1:2].contiguous())
+                                residual=None if res is None else res[1:2].contiguous(), variant=variant)
     torch.cuda.synchronize()
     assert torch.equal(h2[16:32], h1) and torch.equal(l2[16:32], l1)
     assert torch.equal(vl(h2), vl(hf)[..., 64:]) and torch.equal(vl(l2), vl(lf)[..., 64:])

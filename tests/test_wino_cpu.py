@@ -178,14 +178,15 @@ def test_whole_chain_equals_reflect_pad_conv(emul):
     assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-6
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("H,W,Cc,relu,with_res,nthreads", [(32, 32, 64, True, False, 512), (32, 32, 32, False, True, 512),
                                                            (8, 16, 32, True, True, 64), (4, 4, 64, False, False, 32)])
-def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_res, nthreads):
+def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_res, nthreads, variant):
     """The fused bridge (csrc/wino_passes.cuh: phases A, S, B, C) == output transform + bias + addend -> InstanceNorm ->
     [ReLU | + residual] -> reflect pad + input transform, evaluated in torch fp64."""
     vp = C.c_void_p
     emul.wino_emul_bridge.argtypes = [vp, vp, vp, C.c_longlong, vp, vp, vp, vp, vp] + [C.c_int] * 10 + \
-                                     [C.c_float, C.c_float, C.c_int, vp, vp, vp, vp, C.c_float]
+                                     [C.c_float, C.c_float, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int]
     torch.manual_seed(8)
     B = 2
     T = (H // 2) * (W // 2)
@@ -203,15 +204,17 @@ def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_r
     rank = torch.stack([torch.randperm(H * W) for _ in range(B)]).to(torch.int16)
     c_hi = torch.zeros(B * H * W, Cc, dtype=torch.int16)
     c_lo = torch.zeros_like(c_hi)
-    ssq = torch.zeros(B, Cc // 32, H * W)
+    CS = 16 if variant else 32
+    ssq = torch.zeros(B, Cc // CS, H * W)
     emul.wino_emul_bridge(_p(ms), _p(bias), _p(addend), H * W, _p(res), _p(act), _p(mr), _p(hi), _p(lo), B, H, W, Cc,
-                          int(relu), Cp, 32, 0, Cc + 8, 8, 16.0, 1e-5, nthreads, _p(c_hi), _p(c_lo), _p(rank), _p(ssq), 16.0)
+                          int(relu), Cp, 32, 0, Cc + 8, 8, 16.0, 1e-5, nthreads, _p(c_hi), _p(c_lo), _p(rank), _p(ssq), 16.0,
+                          variant)
     hi, lo = v_logical(hi), v_logical(lo)
     a_out = act[..., 8:]
     idx = (rank.long() & 0xFFFF).view(B, H * W, 1).expand(B, H * W, Cc)
     rows = _recon(c_hi, c_lo).view(B, H * W, Cc).gather(1, idx)                # row at rank[pix] -> position pix
     assert float((rows - a_out.double().view(B, H * W, Cc) * 16.0).abs().max() / (a_out.abs().max() * 16.0)) < 2e-6
-    ssq_ref = (a_out.double() ** 2).view(B, H * W, Cc // 32, 32).sum(-1).permute(0, 2, 1)
+    ssq_ref = (a_out.double() ** 2).view(B, H * W, Cc // CS, CS).sum(-1).permute(0, 2, 1)
     assert float((ssq.double() - ssq_ref).abs().max() / ssq_ref.max()) < 1e-6
     M = m.double().view(4, 4, B, H // 2, W // 2, Cc)
     y = torch.einsum("ai,ijbxyc,ej->bxayec", AT, M, AT).reshape(B, H, W, Cc) + bias.double() + \

@@ -67,6 +67,9 @@ E.ForwardEngine.__init__ = _init
 runpy.run_path("bench.py", run_name="__main__")
 PY
       cut -c1-300 $OUT/bench_c3_$TAG.json ;;
+    bench_bv1)
+      timeout 400 python bench.py --steps 10 --warmup 3 --bridge-variant 1 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_bv1_$TAG.json 2> $OUT/bench_bv1_$TAG.err
+      cut -c1-300 $OUT/bench_bv1_$TAG.json ;;
     bench_c4)
       timeout 400 python bench.py --steps 10 --warmup 3 --wino-chunk-kb 4 --no-cpu-baseline --no-torch-cuda-baseline --no-fast-point > $OUT/bench_c4_$TAG.json 2> $OUT/bench_c4_$TAG.err
       cut -c1-300 $OUT/bench_c4_$TAG.json ;;

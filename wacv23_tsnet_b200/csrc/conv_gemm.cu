@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
             const int cx = x0 + args.tap_dx[tap];
             const int cn = img * args.planes + args.tap_plane[tap] + plane;
             for (int kc = 0; kc < args.kc_per_tap; ++kc) {
-              mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* st = smem + stage * kG2StageBytes;
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
               const int kb = tap * args.kc_per_tap + kc;
@@ -629,12 +629,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
         for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
           const int buf = cc & 1;
           const uint32_t buf_phase = (cc >> 1) & 1;
-          mbar_wait_cluster(&tmem_empty[buf], buf_phase ^ 1);
+          mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kG2N;
           const int kb1 = min(num_kb, kb0 + args.chunk_kb);
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait_cluster(&full_bar[stage], phase);
+            mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * kG2StageBytes);
             const uint64_t a_hi = make_desc_kmajor_sw128(st);
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
       for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
         const int buf = cc & 1;
         const uint32_t buf_phase = (cc >> 1) & 1;
-        mbar_wait_cluster(&tmem_full[buf], buf_phase);
+        mbar_wait(&tmem_full[buf], buf_phase);
         tc_fence_after();
         const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kG2N + half * NC;
 #pragma unroll
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm2_kernel(const __gri
         __syncwarp();
         if (lane_id() == 0) {
           if (rank == 0) mbar_arrive(&tmem_empty[buf]);
-          else mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[buf]), 0));
+          else mbar_arrive_remote_cta(map_to_cta(smem_u32(&tmem_empty[buf]), 0));
         }
       }
       const size_t gm = static_cast<size_t>(m_tile) * kBlockM + row;

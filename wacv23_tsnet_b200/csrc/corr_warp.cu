@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
           const int trow = b * args.hw + (2 * mt + static_cast<int>(rank)) * kCorrM;
           const int srow = (i * args.B + b) * args.hw + ch * kCorrN + static_cast<int>(rank) * (kCorrN / 2);
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait_cluster(&tl.empty_bar[stage], phase ^ 1);
+            mbar_wait(&tl.empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * kCorr2StageBytes;
             if (rank == 0) mbar_arrive_expect_tx(&tl.full_bar[stage], stage_tx);
             tma_load_2d_2sm(st, &args.t_hi, &tl.full_bar[stage], kb * kCorrK, trow);
@@ -649,12 +649,12 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
           for (int kb0 = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++cc) {
             const int buf = cc & 1;
             const uint32_t buf_phase = (cc >> 1) & 1;
-            mbar_wait_cluster(&tl.tmem_empty[buf], buf_phase ^ 1);
+            mbar_wait(&tl.tmem_empty[buf], buf_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * kCorrN;
             const int kb1 = min(num_kb, kb0 + args.chunk_kb);
             for (int kb = kb0; kb < kb1; ++kb) {
-              mbar_wait_cluster(&tl.full_bar[stage], phase);
+              mbar_wait(&tl.full_bar[stage], phase);
               tc_fence_after();
               const uint32_t st = smem_u32(smem + stage * kCorr2StageBytes);
               const uint64_t a_hi = make_desc_kmajor_sw128(st);
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
       for (int kb0 = 0, p = 0; kb0 < num_kb; kb0 += args.chunk_kb, ++p, ++it) {
         const int buf = it & 1;
         const uint32_t buf_phase = (it >> 1) & 1;
-        mbar_wait_cluster(&tl.tmem_full[buf], buf_phase);
+        mbar_wait(&tl.tmem_full[buf], buf_phase);
         tc_fence_after();
         const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kCorrN + half * kCorrNC;
         if (p == 0) {
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tile2_kernel(const __gri
         __syncwarp();
         if (lane_id() == 0) {
           if (rank == 0) mbar_arrive(&tl.tmem_empty[buf]);
-          else mbar_arrive_remote(map_to_cta(smem_u32(&tl.tmem_empty[buf]), 0));
+          else mbar_arrive_remote_cta(map_to_cta(smem_u32(&tl.tmem_empty[buf]), 0));
         }
       }
 

@@ -98,6 +98,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive with the DEFAULT semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): for
+// barriers that only order TMA / tcgen05 traffic and TMEM reads between the CTAs of a pair (no generic-proxy data crosses
+// the CTAs).  The .release.cluster form above costs MEMBAR.ALL.GPU + CCTL.IVALL (an L1 invalidate) per arrive, and the
+// membar waits for every outstanding global store of the thread -- in the GEMM epilogue warps that is the 128 KB tile they
+// have just written (ncu: 20 % of all stall samples of the Winograd plane GEMM sat on that sequence).
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -364,8 +364,12 @@ TSNET_HD void wino_output_body(const WinoOutArgs& a, int block, int thread, int 
 //   B  v = (y - mean) * rstd ; ReLU ; + residual ; act_out  -> shared memory (in place) and optional fp32 output
 //   C  reflect pad + B^T d B + hi/lo split                  -> the 16 operand planes of the next plane GEMMs
 // ------------------------------------------------------------------------------------------------
-constexpr int kBridgeCS = kWinoMSlab;  // channels per CTA = one M slab: phase A streams 32 KB contiguous per plane
-constexpr int kBridgePS = 32;          // shared-memory pixel stride in floats (8 lanes per pixel cover all 32 banks)
+// Two variants (template parameters CS = channels per CTA, PS = shared-memory pixel stride in floats):
+//   <32, 32>  one M slab per CTA: phase A streams 32 KB contiguous per plane; 128 KB image buffer, 512 threads, 1 CTA / SM
+//   <16, 24>  half a slab per CTA (64-byte pieces): 96 KB image buffer (16 channels + 8 pad so that the 64-byte groups
+//             the lanes of a warp touch alternate bank halves), 256 threads, 2 CTAs / SM whose read-heavy (A) and
+//             write-heavy (C) phases overlap
+constexpr int kBridgeCSDefault = kWinoMSlab;
 
 struct WinoBridgeArgs {
   const float* m;         // fp32, slab-major (wino_m_index)
@@ -390,11 +394,13 @@ struct WinoBridgeArgs {
 };
 
 // shared-memory layout: float y[H * W * PS]; double part[nseg * CS * 2]; float mr[CS * 2]
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD size_t wino_bridge_smem_bytes(int H, int W, int nthreads) {
   return static_cast<size_t>(H) * W * kBridgePS * 4 + static_cast<size_t>(nthreads / kBridgeCS) * kBridgeCS * 2 * 8 +
          kBridgeCS * 2 * 4;
 }
 
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y) {
   const int slabs = a.C / kBridgeCS;
   const int b = block / slabs, slab = block - b * slabs;
@@ -437,6 +443,7 @@ TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread
   }
 }
 
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_s1(const WinoBridgeArgs& a, int thread, int nthreads, const float* s_y, double* s_part) {
   const int HW = a.H * a.W;
   const int nseg = nthreads / kBridgeCS;
@@ -454,6 +461,7 @@ TSNET_HD void wino_bridge_phase_s1(const WinoBridgeArgs& a, int thread, int nthr
   s_part[(seg * kBridgeCS + c) * 2 + 1] = q;
 }
 
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_s2(const WinoBridgeArgs& a, int block, int thread, int nthreads, const double* s_part,
                                    float* s_mr) {
   if (thread >= kBridgeCS) return;
@@ -484,6 +492,7 @@ TSNET_HD void wino_bridge_phase_s2(const WinoBridgeArgs& a, int block, int threa
   }
 }
 
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y,
                                   const float* s_mr) {
   const int slabs = a.C / kBridgeCS;
@@ -538,6 +547,7 @@ TSNET_HD void wino_bridge_phase_b(const WinoBridgeArgs& a, int block, int thread
 
 // phase N (after B; reads only): this slab's sum of squares of every pixel, channel order rotated by the pixel index so
 // that the lanes of a warp (consecutive pixels, 128 bytes apart) hit different banks
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_n(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y) {
   if (!a.corr_ssq) return;
   const int slabs = a.C / kBridgeCS;
@@ -553,6 +563,7 @@ TSNET_HD void wino_bridge_phase_n(const WinoBridgeArgs& a, int block, int thread
   }
 }
 
+template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y) {
   const int slabs = a.C / kBridgeCS;
   const int b = block / slabs, slab = block - b * slabs;

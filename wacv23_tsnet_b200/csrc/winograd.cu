@@ -19,22 +19,34 @@ __global__ void __launch_bounds__(256, 3) wino_output_kernel(const WinoOutArgs a
   wino_output_body(a, blockIdx.x, threadIdx.x, blockDim.x);
 }
 
-constexpr int kBridgeThreads = 512;
-__global__ void __launch_bounds__(kBridgeThreads, 1) wino_bridge_kernel(const WinoBridgeArgs a) {
+template <int CS, int PS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) wino_bridge_kernel(const WinoBridgeArgs a) {
   extern __shared__ __align__(16) uint8_t bridge_smem[];
   float* s_y = reinterpret_cast<float*>(bridge_smem);
-  double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * kBridgePS * 4);
-  float* s_mr = reinterpret_cast<float*>(s_part + (kBridgeThreads / kBridgeCS) * kBridgeCS * 2);
-  wino_bridge_phase_a(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
+  double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * PS * 4);
+  float* s_mr = reinterpret_cast<float*>(s_part + (THREADS / CS) * CS * 2);
+  wino_bridge_phase_a<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
   __syncthreads();
-  wino_bridge_phase_s1(a, threadIdx.x, kBridgeThreads, s_y, s_part);
+  wino_bridge_phase_s1<CS, PS>(a, threadIdx.x, THREADS, s_y, s_part);
   __syncthreads();
-  wino_bridge_phase_s2(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_part, s_mr);
+  wino_bridge_phase_s2<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_part, s_mr);
   __syncthreads();
-  wino_bridge_phase_b(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y, s_mr);
+  wino_bridge_phase_b<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y, s_mr);
   __syncthreads();
-  wino_bridge_phase_n(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
-  wino_bridge_phase_c(a, blockIdx.x, threadIdx.x, kBridgeThreads, s_y);
+  wino_bridge_phase_n<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
+  wino_bridge_phase_c<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
+}
+
+template <int CS, int PS, int THREADS, int MINB>
+static int launch_wino_bridge(const WinoBridgeArgs& a, cudaStream_t stream) {
+  const size_t smem = wino_bridge_smem_bytes<CS, PS>(a.H, a.W, THREADS);
+  TSNET_ARG_CHECK(smem <= 227 * 1024, "wino_bridge: %d x %d image needs %zu B of shared memory", a.H, a.W, smem);
+  static int smem_attr[kMaxDevices] = {0};
+  TSNET_CUDA_CHECK(ensure_dyn_smem(wino_bridge_kernel<CS, PS, THREADS, MINB>, static_cast<int>(smem), smem_attr));
+  const unsigned blocks = static_cast<unsigned>(a.B) * (a.C / CS);
+  wino_bridge_kernel<CS, PS, THREADS, MINB><<<blocks, THREADS, smem, stream>>>(a);
+  TSNET_LAUNCH_CHECK();
+  return 0;
 }
 
 // called by tsnet_build_taps (elementwise.cu) for mode TSNET_TAPS_WINO
@@ -83,15 +95,14 @@ extern "C" int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m
                                  uint16_t* v_lo, void* stream) {
   TSNET_ARG_CHECK(d && m && v_hi && v_lo, "wino_bridge: null argument");
   TSNET_ARG_CHECK(d->H % 2 == 0 && d->W % 2 == 0 && d->H >= 4 && d->W >= 4, "wino_bridge: H, W must be even, >= 4");
-  TSNET_ARG_CHECK(d->C > 0 && d->C % kBridgeCS == 0, "wino_bridge: C %d must be a multiple of %d", d->C, kBridgeCS);
+  TSNET_ARG_CHECK(d->C > 0 && d->C % kWinoMSlab == 0, "wino_bridge: C %d must be a multiple of %d", d->C, kWinoMSlab);
+  TSNET_ARG_CHECK(d->variant == 0 || d->variant == 1, "wino_bridge: variant %d", d->variant);
   TSNET_ARG_CHECK(d->Cp_total % 64 == 0 && d->c_off % 4 == 0 && d->c_off + d->C <= d->Cp_total,
                   "wino_bridge: operand channel window does not fit (Cp_total must be a multiple of 64)");
   TSNET_ARG_CHECK(!addend || d->addend_rows > 0, "wino_bridge: addend needs addend_rows > 0");
   const int actC = d->act_C_total > 0 ? d->act_C_total : d->C;
   TSNET_ARG_CHECK(!act_out || (actC % 4 == 0 && d->act_c_off % 4 == 0 && d->act_c_off + d->C <= actC),
                   "wino_bridge: act_out channel window does not fit");
-  const size_t smem = wino_bridge_smem_bytes(d->H, d->W, kBridgeThreads);
-  TSNET_ARG_CHECK(smem <= 227 * 1024, "wino_bridge: %d x %d image needs %zu B of shared memory", d->H, d->W, smem);
   WinoBridgeArgs a;
   a.m = m; a.bias = bias; a.addend = addend; a.residual = residual; a.act_out = act_out;
   a.mean_rstd_out = mean_rstd_out; a.hi = v_hi; a.lo = v_lo;
@@ -104,10 +115,6 @@ extern "C" int tsnet_wino_bridge(const tsnet_wino_bridge_desc* d, const float* m
                   "wino_bridge: corr_hi / corr_lo / corr_rank / corr_ssq come together");
   a.corr_hi = d->corr_hi; a.corr_lo = d->corr_lo; a.corr_rank = d->corr_rank; a.corr_ssq = d->corr_ssq;
   a.corr_scale = d->corr_scale == 0.f ? 1.f : d->corr_scale;
-  static int smem_attr[kMaxDevices] = {0};
-  TSNET_CUDA_CHECK(ensure_dyn_smem(wino_bridge_kernel, static_cast<int>(smem), smem_attr));
-  const unsigned blocks = static_cast<unsigned>(d->B) * (d->C / kBridgeCS);
-  wino_bridge_kernel<<<blocks, kBridgeThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  TSNET_LAUNCH_CHECK();
-  return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d->variant == 1 ? launch_wino_bridge<16, 24, 256, 2>(a, st) : launch_wino_bridge<32, 32, 512, 1>(a, st);
 }

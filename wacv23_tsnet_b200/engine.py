@@ -46,6 +46,7 @@ class ForwardEngine:
         # mix.  The value is an int, or a dict {net name: chunk} with key "default".
         self.wino_chunk_kb = {"img_enc": 2, "default": 4}
         self.wino_flags = 0      # tsnet_wino_gemm_desc.flags (experiments: L.CONV_SMALL_FIRST)
+        self.bridge_variant = 0  # tsnet_wino_bridge_desc.variant: 0 = 32-channel slabs (1 CTA / SM), 1 = 16-channel (2 / SM)
         self._packs = {}
         self._coord = {}
         self._src_cache = None   # opt-in source-feature cache (see forward(src_key=...))
@@ -152,7 +153,8 @@ class ForwardEngine:
             pw = self._pack_wino(pc[0], pc[1], cin_range=pc[2] if len(pc) > 2 else None)
             mbuf = ops.wino_gemm(taps, pw, B, H, W, m, m.act_scale, chunk_kb=self._chunk(pc[0]), flags=self.wino_flags)
             t = ops.wino_bridge(mbuf, pw, B, H, W, m, relu=relu, addend=addend, residual=residual, act_out=act_out,
-                                act_c_off=act_c_off, taps=dest, c_off=c_off, corr=corr_out)
+                                act_c_off=act_c_off, taps=dest, c_off=c_off, corr=corr_out,
+                                variant=self.bridge_variant)
             return t, act_out
         if is3:
             y, mr = self._conv3(taps, pc[0], pc[1], B, H, W, addend=addend, cin_range=pc[2] if len(pc) > 2 else None)
@@ -265,8 +267,9 @@ class ForwardEngine:
         corr_out = None
         if self.bridge and self._tmode3(h, w, Cf, 2 * Cf) == L.TAPS_WINO:
             s_hi = torch.empty((n * B * hw, Cf), dtype=torch.int16, device=dev)
+            self._ssq_slabs = Cf // (16 if self.bridge_variant else 32)
             corr_out = dict(hi=s_hi, lo=torch.empty_like(s_hi), rank=plan.rank_s,
-                            ssq=torch.empty((n * B, Cf // 32, hw), dtype=torch.float32, device=dev), done=False)
+                            ssq=torch.empty((n * B, self._ssq_slabs, hw), dtype=torch.float32, device=dev), done=False)
         cache_sig = None
         if src_key is not None:
             cache_sig = (src_key, n, B, tuple(img_divs), m.name, self.winograd, self.bridge, str(self.wino_chunk_kb),
@@ -298,11 +301,13 @@ class ForwardEngine:
         tar_ops = ops.corr_operands(tar_fea.view(B, hw, Cf), m, rank=plan.rank_t)
         if corr_out is not None and corr_out["done"]:
             # the last img_enc bridge pass wrote the sources' operand rows + partial sums of squares
-            src_ops = (corr_out["hi"], corr_out["lo"], ops.corr_norms(corr_out["ssq"], n * B, hw, Cf // 32, plan.rank_s))
+            src_ops = (corr_out["hi"], corr_out["lo"],
+                       ops.corr_norms(corr_out["ssq"], n * B, hw, corr_out["ssq"].shape[1], plan.rank_s))
         else:
             src_ops = ops.corr_operands(src_fea.view(n * B, hw, Cf), m, rank=plan.rank_s)
             if cached_ssq is not None:   # cache hit after a bridge-emitting miss: same norms as the miss computed
-                src_ops = (src_ops[0], src_ops[1], ops.corr_norms(cached_ssq, n * B, hw, Cf // 32, plan.rank_s))
+                src_ops = (src_ops[0], src_ops[1],
+                           ops.corr_norms(cached_ssq, n * B, hw, cached_ssq.shape[1], plan.rank_s))
         src_fea_v = src_fea.view(n, B, hw, Cf)
         dec_hi = torch.empty((B, h, w, 2 * Cf), dtype=torch.int16, device=dev)
         dec_lo = torch.empty_like(dec_hi)

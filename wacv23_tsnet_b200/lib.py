@@ -58,7 +58,7 @@ class WinoBridgeDesc(C.Structure):
                 ("Cp_total", C.c_int), ("c_off", C.c_int), ("fmt", C.c_int), ("scale", C.c_float), ("eps", C.c_float),
                 ("act_C_total", C.c_int), ("act_c_off", C.c_int), ("addend_rows", C.c_longlong),
                 ("corr_hi", C.c_void_p), ("corr_lo", C.c_void_p), ("corr_rank", C.c_void_p), ("corr_ssq", C.c_void_p),
-                ("corr_scale", C.c_float)]
+                ("corr_scale", C.c_float), ("variant", C.c_int)]
 
 
 class StemConvDesc(C.Structure):

@@ -202,7 +202,7 @@ def wino_conv(taps, pw, B, H, W, mode, act_scale, want_stats=True, addend=None, 
 
 
 def wino_bridge(m_buf, pw, B, H, W, mode, relu=False, addend=None, residual=None, act_out=None, act_c_off=0, taps=None,
-                c_off=0, mean_rstd_out=None, act_scale=None, corr=None):
+                c_off=0, mean_rstd_out=None, act_scale=None, corr=None, variant=0):
     """Fused layer boundary between two Winograd convolutions (tsnet_wino_bridge): output transform + bias (+ addend) ->
     InstanceNorm -> [ReLU] -> [+ residual] -> [fp32 act_out] -> input transform.  Returns (hi, lo, (16, H/2, W/2)).
     corr = dict(hi, lo [B*H*W, C] int16, rank = device pointer of the [B, H*W] rank table, ssq fp32 [B, C/32, H*W]): the
@@ -224,13 +224,14 @@ def wino_bridge(m_buf, pw, B, H, W, mode, relu=False, addend=None, residual=None
         assert addend.shape[-1] == Cc and addend.is_contiguous() and addend.dtype == torch.float32
         rows = addend.numel() // Cc
     d.addend_rows = rows
+    d.variant = variant   # 0: 32-channel slabs, 1 CTA / SM; 1: 16-channel slabs, 2 CTAs / SM
     if act_out is not None:
         assert act_out.dtype == torch.float32 and act_out.is_contiguous() and act_out.shape[:3] == (B, H, W)
         d.act_C_total, d.act_c_off = act_out.shape[-1], act_c_off
     if residual is not None:
         assert _f32(residual).shape == (B, H, W, Cc)
     if corr is not None:
-        assert corr["hi"].shape == (B * H * W, Cc) and corr["ssq"].shape == (B, Cc // 32, H * W)
+        assert corr["hi"].shape == (B * H * W, Cc) and corr["ssq"].shape == (B, Cc // (16 if variant else 32), H * W)
         d.corr_hi, d.corr_lo = corr["hi"].data_ptr(), corr["lo"].data_ptr()
         d.corr_rank, d.corr_ssq, d.corr_scale = corr["rank"], corr["ssq"].data_ptr(), mode.act_scale
         corr["done"] = True
