@@ -203,7 +203,7 @@ class TSNet(nn.Module):
 
     def set_train_input(self, src_img_list, src_lbl_list, src_bbox_list, tar_img, tar_lbl, tar_bbox, use_prev=None):
         self._src_sig = None
-        self._src_img_raw = [self._img(x, keep_u8=False) for x in src_img_list]
+        self._src_img_raw = [self._img(x, keep_u8=False).contiguous() for x in src_img_list]
         self._src_img_div = [1.0 if (use_prev is not None and use_prev[i]) else 255.0
                              for i in range(len(self._src_img_raw))]
         self.src_lbl_list = [self._lbl(x) for x in src_lbl_list]
