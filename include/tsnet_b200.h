@@ -264,7 +264,9 @@ int tsnet_stem_conv_fwd(const tsnet_stem_conv_desc* d, const void* img_nchw, con
  *
  * Call order on one stream (SURVEY section 8b names this group `tsnet_corr_warp_fwd`):
  *   1. tsnet_corr_prepare     masks -> per-map class-sorted order, tile classes, work list, closed forms
- *   2. tsnet_l2norm_split x2  F.normalize of target / source features, rows written in the sorted order
+ *   2. operands, rows written in the sorted order: tsnet_corr_operands (un-normalised rows + reciprocal norms; the
+ *      default) for the target and -- unless the producing tsnet_wino_bridge already wrote them (corr_* fields +
+ *      tsnet_corr_norms) -- the sources; or tsnet_l2norm_split x2 (rows normalised up front, rnorm_* = NULL)
  *   3. tsnet_corr_warp_fwd    = tsnet_corr_tiles (tcgen05 similarity tiles -> partial softmax states)
  *                             + tsnet_corr_finish (merge -> warp grid -> grid_sample -> source mean)
  *

@@ -1,5 +1,5 @@
 """bench.py's workload (FaceForensics config: bs=32, n_source=3, n_blocks=4, fp16x3, inputs resident), N forwards and
-nothing else -- the target of the ncu captures in tools/profile.sh.  Prints `FORWARD_LAUNCHES <n>` = kernel launches of
+nothing else -- the target of the ncu captures in tools/gpu_r2.sh.  Prints `FORWARD_LAUNCHES <n>` = kernel launches of
 the last forward (counted by the library wrappers) so that the summariser can cut the launch list."""
 import argparse, contextlib, io, os, sys
 import torch

@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2-CTA variant of the BLOCK_N = 256 kernel (tcgen05.mma.cta_group::2; opt-in: TSNET_CONV_2CTA=1).
+// 2-CTA variant of the BLOCK_N = 256 kernel (tcgen05.mma.cta_group::2; the default whenever the pixel tiles pair up).
 // A CTA pair takes two adjacent pixel tiles (M = 256) of one 256-channel slab: each CTA TMA-loads its own A tile and only
 // HALF of the weight tile (128 of the 256 rows); the leader issues the MMAs of both SMs.  Operand delivery per SM drops
 // from 96 KB to 64 KB per K block (three 64 KB stages instead of two 96 KB ones) -- the same change took the

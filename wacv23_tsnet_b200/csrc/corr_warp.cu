@@ -12,7 +12,7 @@
 //     written here.  Everything else goes on the work list.  (sort = 0 keeps the raster order.)
 //  K1 corr_tile2_kernel    (persistent, 74 CTA PAIRS, default)  work item = (sample, 256 target rows, source, 256 source
 //     columns): tcgen05.mma.cta_group::2, M = 256 across the pair -- see the comment above the kernel.
-//     corr_tile_kernel     (persistent, <= 148 CTAs, TSNET_K1_2CTA=0)  work item = (sample, 128 target rows, source,
+//     corr_tile_kernel     (persistent, <= 148 CTAs, tsnet_corr_desc.one_cta)  work item = (sample, 128 target rows, source,
 //     256 source columns).  Common to both:
 //     S = T_hat[128 x C] . S_hat[256 x C]^T on tcgen05 (3-term hi/lo split, fp32 accumulate in TMEM, two 128 x 256
 //     accumulators so the tensor pipe runs on the next item while eight softmax warps read the finished one:
