@@ -1419,7 +1419,12 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   memset(&a, 0, sizeof(a));
   a.tiles_per_img = tiles / kBlockM;
   a.num_m_tiles = d->B * a.tiles_per_img;
-  const bool two_cta = (d->flags & TSNET_CONV_ONE_CTA) == 0 && a.num_m_tiles % 2 == 0;
+  // tile width: 256 (CTA pairs) whenever that gives every SM work; small batches (the demos' one frame per forward:
+  // 16 planes x 2 pixel tiles x Cout/256 slabs = 32 .. 64 items) fall back to 128- / 64-wide 1-CTA tiles.  The
+  // accumulation order per element does not depend on the tile width, so results are bit-identical.
+  int bn = kG2N;
+  while (bn > 64 && 16 * a.num_m_tiles * (d->Cout / bn) < num_sms()) bn >>= 1;
+  const bool two_cta = bn == kG2N && (d->flags & TSNET_CONV_ONE_CTA) == 0 && a.num_m_tiles % 2 == 0;
   {  // V, K-block-major: [B * 16][C / 64][TH][TW][64]
     const uint64_t dims[5] = {64, (uint64_t)d->TW, (uint64_t)d->TH, (uint64_t)d->C / 64, (uint64_t)d->B * 16};
     const uint64_t str[4] = {128, (uint64_t)d->TW * 128, (uint64_t)tiles * 128, (uint64_t)(d->C / 64) * tiles * 128};
@@ -1431,14 +1436,14 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   {
     const uint64_t dims[2] = {(uint64_t)d->C, (uint64_t)16 * d->Cout};
     const uint64_t str[1] = {(uint64_t)d->C * 2};
-    const uint32_t box[2] = {64, two_cta ? (uint32_t)(kG2N / 2) : (uint32_t)kG2N};
+    const uint32_t box[2] = {64, two_cta ? (uint32_t)(kG2N / 2) : (uint32_t)bn};
     int r = encode_tmap_u16_sw128(&a.b_hi, u_hi, 2, dims, str, box);
     if (r) return r;
     if (d->split && (r = encode_tmap_u16_sw128(&a.b_lo, u_lo, 2, dims, str, box))) return r;
   }
   a.y = m_out;
   a.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
-  a.num_n_tiles = d->Cout / kG2N;
+  a.num_n_tiles = d->Cout / bn;
   a.Wt = Wt;
   a.rows_per_tile = rows;
   a.wtiles_per_row = d->TW / Wt;
@@ -1456,7 +1461,8 @@ extern "C" int tsnet_wino_gemm_fwd(const tsnet_wino_gemm_desc* d, const uint16_t
   a.y_slab_tiles = tiles;
   a.small_first = (d->flags & TSNET_CONV_SMALL_FIRST) ? 1 : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return two_cta ? launch_conv_gemm2(a, s) : launch_conv_gemm<256>(a, s);
+  if (two_cta) return launch_conv_gemm2(a, s);
+  return bn == 256 ? launch_conv_gemm<256>(a, s) : (bn == 128 ? launch_conv_gemm<128>(a, s) : launch_conv_gemm<64>(a, s));
 }
 
 // ------------------------------------------------------------------------------------------------
