@@ -39,15 +39,17 @@ static void emul_bridge(const WinoBridgeArgs& a, int nthreads) {
   uint8_t* smem = new uint8_t[bytes + 16];
   float* s_y = reinterpret_cast<float*>(smem);
   double* s_part = reinterpret_cast<double*>(smem + static_cast<size_t>(a.H) * a.W * PS * 4);
-  float* s_mr = reinterpret_cast<float*>(s_part + (nthreads / CS) * CS * 2);
+  float* s_mr = reinterpret_cast<float*>(s_part + static_cast<size_t>(nthreads) * 8);
   const int blocks = a.B * (a.C / CS);
+  const bool fold = !a.residual && !a.act_out && !a.corr_hi;
   for (int blk = 0; blk < blocks; ++blk) {   // phases separated by block-wide barriers in the kernel
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_a<CS, PS>(a, blk, t, nthreads, s_y);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s1<CS, PS>(a, t, nthreads, s_y, s_part);
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_a<CS, PS>(a, blk, t, nthreads, s_y, s_part);
     for (int t = 0; t < nthreads; ++t) wino_bridge_phase_s2<CS, PS>(a, blk, t, nthreads, s_part, s_mr);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_b<CS, PS>(a, blk, t, nthreads, s_y, s_mr);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_n<CS, PS>(a, blk, t, nthreads, s_y);
-    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_c<CS, PS>(a, blk, t, nthreads, s_y);
+    if (!fold) {
+      for (int t = 0; t < nthreads; ++t) wino_bridge_phase_b<CS, PS>(a, blk, t, nthreads, s_y, s_mr);
+      for (int t = 0; t < nthreads; ++t) wino_bridge_phase_n<CS, PS>(a, blk, t, nthreads, s_y);
+    }
+    for (int t = 0; t < nthreads; ++t) wino_bridge_phase_c<CS, PS>(a, blk, t, nthreads, s_y, s_mr, fold);
   }
   delete[] smem;
 }

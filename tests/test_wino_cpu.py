@@ -216,6 +216,14 @@ def test_bridge_pass_equals_output_norm_input_chain(emul, H, W, Cc, relu, with_r
     assert float((rows - a_out.double().view(B, H * W, Cc) * 16.0).abs().max() / (a_out.abs().max() * 16.0)) < 2e-6
     ssq_ref = (a_out.double() ** 2).view(B, H * W, Cc // CS, CS).sum(-1).permute(0, 2, 1)
     assert float((ssq.double() - ssq_ref).abs().max() / ssq_ref.max()) < 1e-6
+    if not with_res:
+        # without residual / act_out / correlation outputs the in-place phase B is skipped and phase C normalises on read:
+        # the operands must be the same bits
+        hi2 = torch.zeros((B, 16, Cp // 64, H // 2, W // 2, 64), dtype=torch.int16)
+        lo2 = torch.zeros_like(hi2)
+        emul.wino_emul_bridge(_p(ms), _p(bias), _p(addend), H * W, None, None, None, _p(hi2), _p(lo2), B, H, W, Cc,
+                              int(relu), Cp, 32, 0, Cc, 0, 16.0, 1e-5, nthreads, None, None, None, None, 16.0, variant)
+        assert torch.equal(v_logical(hi2), hi) and torch.equal(v_logical(lo2), lo)
     M = m.double().view(4, 4, B, H // 2, W // 2, Cc)
     y = torch.einsum("ai,ijbxyc,ej->bxayec", AT, M, AT).reshape(B, H, W, Cc) + bias.double() + \
         addend.double().view(1, H, W, Cc)

@@ -393,20 +393,24 @@ struct WinoBridgeArgs {
   float corr_scale;
 };
 
-// shared-memory layout: float y[H * W * PS]; double part[nseg * CS * 2]; float mr[CS * 2]
+// shared-memory layout: float y[H * W * PS]; double part[nthreads][8] (sum, sum of squares of the thread's 4 channels);
+// float mr[CS * 2]
 template <int kBridgeCS, int kBridgePS>
 TSNET_HD size_t wino_bridge_smem_bytes(int H, int W, int nthreads) {
-  return static_cast<size_t>(H) * W * kBridgePS * 4 + static_cast<size_t>(nthreads / kBridgeCS) * kBridgeCS * 2 * 8 +
-         kBridgeCS * 2 * 4;
+  return static_cast<size_t>(H) * W * kBridgePS * 4 + static_cast<size_t>(nthreads) * 8 * 8 + kBridgeCS * 2 * 4;
 }
 
 template <int kBridgeCS, int kBridgePS>
-TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y) {
+TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread, int nthreads, float* s_y,
+                                  double* s_part) {
   const int slabs = a.C / kBridgeCS;
   const int b = block / slabs, slab = block - b * slabs;
   const int TH = a.H / 2, TW = a.W / 2, T = TH * TW;
   const size_t ptile = static_cast<size_t>(a.B) * T;
   constexpr int CQ = kBridgeCS / 4;
+  // statistics: nthreads is a multiple of CQ, so every unit of a thread has the same 4 channels (cq = thread % CQ); the
+  // thread's sum / sum of squares over its output pixels are kept in fp64 and merged in phase S in a fixed order
+  double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
   for (int u = thread; u < T * CQ; u += nthreads) {
     const int tile = u / CQ, cq = u - tile * CQ;
     const int ty = tile / TW, tx = tile - ty * TW;
@@ -439,37 +443,30 @@ TSNET_HD void wino_bridge_phase_a(const WinoBridgeArgs& a, int block, int thread
         o = f4_add(o, ld_f4(a.addend + (gp % static_cast<size_t>(a.addend_rows)) * a.C + c));
       }
       st_f4(s_y + static_cast<size_t>(pix) * kBridgePS + cq * 4, o);
+      const double ox = o.x, oy = o.y, oz = o.z, ow = o.w;
+      ds[0] += ox; dq[0] += ox * ox;
+      ds[1] += oy; dq[1] += oy * oy;
+      ds[2] += oz; dq[2] += oz * oz;
+      ds[3] += ow; dq[3] += ow * ow;
     }
   }
-}
-
-template <int kBridgeCS, int kBridgePS>
-TSNET_HD void wino_bridge_phase_s1(const WinoBridgeArgs& a, int thread, int nthreads, const float* s_y, double* s_part) {
-  const int HW = a.H * a.W;
-  const int nseg = nthreads / kBridgeCS;
-  const int c = thread % kBridgeCS, seg = thread / kBridgeCS;
-  if (seg >= nseg) return;
-  const int per = (HW + nseg - 1) / nseg;
-  const int p0 = seg * per, p1 = p0 + per < HW ? p0 + per : HW;
-  double s = 0.0, q = 0.0;
-  for (int p = p0; p < p1; ++p) {
-    const double v = static_cast<double>(s_y[static_cast<size_t>(p) * kBridgePS + c]);
-    s += v;
-    q += v * v;
+  double* sp = s_part + static_cast<size_t>(thread) * 8;
+  for (int k = 0; k < 4; ++k) {
+    sp[2 * k] = ds[k];
+    sp[2 * k + 1] = dq[k];
   }
-  s_part[(seg * kBridgeCS + c) * 2 + 0] = s;
-  s_part[(seg * kBridgeCS + c) * 2 + 1] = q;
 }
 
 template <int kBridgeCS, int kBridgePS>
 TSNET_HD void wino_bridge_phase_s2(const WinoBridgeArgs& a, int block, int thread, int nthreads, const double* s_part,
                                    float* s_mr) {
   if (thread >= kBridgeCS) return;
-  const int nseg = nthreads / kBridgeCS;
+  constexpr int CQ = kBridgeCS / 4;
+  const int cq = thread >> 2, comp = thread & 3;  // channel `thread` = component comp of the threads with t % CQ == cq
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < nseg; ++k) {
-    s += s_part[(k * kBridgeCS + thread) * 2 + 0];
-    q += s_part[(k * kBridgeCS + thread) * 2 + 1];
+  for (int t = cq; t < nthreads; t += CQ) {        // fixed order: deterministic
+    s += s_part[static_cast<size_t>(t) * 8 + 2 * comp];
+    q += s_part[static_cast<size_t>(t) * 8 + 2 * comp + 1];
   }
   const double n = static_cast<double>(a.H) * a.W;
   const double mean = s / n;
@@ -564,7 +561,9 @@ TSNET_HD void wino_bridge_phase_n(const WinoBridgeArgs& a, int block, int thread
 }
 
 template <int kBridgeCS, int kBridgePS>
-TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y) {
+// `fold` = phase B was skipped (no residual, act_out or correlation outputs): normalisation (+ ReLU) happens here, on read
+TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread, int nthreads, const float* s_y,
+                                  const float* s_mr, bool fold) {
   const int slabs = a.C / kBridgeCS;
   const int b = block / slabs, slab = block - b * slabs;
   const int TH = a.H / 2, TW = a.W / 2, T = TH * TW;
@@ -575,16 +574,35 @@ TSNET_HD void wino_bridge_phase_c(const WinoBridgeArgs& a, int block, int thread
     const int ty = tile / TW, tx = tile - ty * TW;
     const int ys[4] = {wino_reflect(2 * ty - 1, a.H), 2 * ty, 2 * ty + 1, wino_reflect(2 * ty + 2, a.H)};
     const int xs[4] = {wino_reflect(2 * tx - 1, a.W), 2 * tx, 2 * tx + 1, wino_reflect(2 * tx + 2, a.W)};
+    f4 mean = f4{0.f, 0.f, 0.f, 0.f}, rstd = f4{1.f, 1.f, 1.f, 1.f};
+    if (fold) {
+      const f4 m01 = ld_f4(s_mr + cq * 8), m23 = ld_f4(s_mr + cq * 8 + 4);
+      mean = f4{m01.x, m01.z, m23.x, m23.z};
+      rstd = f4{m01.y, m01.w, m23.y, m23.w};
+    }
     f4 t[4][4];  // t[s][i] = (B^T d)[i][s]
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int sx = 0; sx < 4; ++sx) {
       const float* col = s_y + static_cast<size_t>(xs[sx]) * kBridgePS + cq * 4;
-      const f4 d0 = ld_f4(col + static_cast<size_t>(ys[0]) * a.W * kBridgePS);
-      const f4 d1 = ld_f4(col + static_cast<size_t>(ys[1]) * a.W * kBridgePS);
-      const f4 d2 = ld_f4(col + static_cast<size_t>(ys[2]) * a.W * kBridgePS);
-      const f4 d3 = ld_f4(col + static_cast<size_t>(ys[3]) * a.W * kBridgePS);
+      f4 d[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int r = 0; r < 4; ++r) {
+        f4 v = ld_f4(col + static_cast<size_t>(ys[r]) * a.W * kBridgePS);
+        if (fold) {  // same expression as phase B
+          v.x = (v.x - mean.x) * rstd.x; v.y = (v.y - mean.y) * rstd.y;
+          v.z = (v.z - mean.z) * rstd.z; v.w = (v.w - mean.w) * rstd.w;
+          if (a.relu) {
+            v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+            v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+          }
+        }
+        d[r] = v;
+      }
+      const f4 d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
       t[sx][0] = f4_sub(d0, d2);
       t[sx][1] = f4_add(d1, d2);
       t[sx][2] = f4_sub(d2, d1);

@@ -24,17 +24,19 @@ __global__ void __launch_bounds__(THREADS, MINB) wino_bridge_kernel(const WinoBr
   extern __shared__ __align__(16) uint8_t bridge_smem[];
   float* s_y = reinterpret_cast<float*>(bridge_smem);
   double* s_part = reinterpret_cast<double*>(bridge_smem + static_cast<size_t>(a.H) * a.W * PS * 4);
-  float* s_mr = reinterpret_cast<float*>(s_part + (THREADS / CS) * CS * 2);
-  wino_bridge_phase_a<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
-  __syncthreads();
-  wino_bridge_phase_s1<CS, PS>(a, threadIdx.x, THREADS, s_y, s_part);
+  float* s_mr = reinterpret_cast<float*>(s_part + THREADS * 8);
+  wino_bridge_phase_a<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y, s_part);
   __syncthreads();
   wino_bridge_phase_s2<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_part, s_mr);
   __syncthreads();
-  wino_bridge_phase_b<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y, s_mr);
-  __syncthreads();
-  wino_bridge_phase_n<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
-  wino_bridge_phase_c<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
+  // a boundary without residual / act_out / correlation outputs needs no in-place pass: phase C normalises on read
+  const bool fold = !a.residual && !a.act_out && !a.corr_hi;
+  if (!fold) {
+    wino_bridge_phase_b<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y, s_mr);
+    __syncthreads();
+    wino_bridge_phase_n<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y);
+  }
+  wino_bridge_phase_c<CS, PS>(a, blockIdx.x, threadIdx.x, THREADS, s_y, s_mr, fold);
 }
 
 template <int CS, int PS, int THREADS, int MINB>
