@@ -21,10 +21,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=60)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cache-sources", action="store_true",
+                    help="opt-in: the three source frames are the same tensors for every driving frame, so their device "
+                         "copies and img_enc features are reused (enable_source_cache)")
     args = ap.parse_args()
     torch.manual_seed(1234)
     model = TSNet(is_train=False, label_nc=2, n_blocks=4, n_downsampling=3, n_source=3, cuda_graph=not args.no_graph)
     model.eval()
+    model.enable_source_cache(args.cache_sources)
     vid = synth.dataset_like_inputs(args.frames, 2, 3, seed=7)
     t = torch.from_numpy
     # demo style: sources are 5-D tensors [n, 1, C, H, W] iterated over dim 0 (demo_face.py:176-178)
@@ -48,7 +52,7 @@ def main():
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if not warm:
-                print(f"{args.frames} frames, bs=1, n_source=3, n_blocks=4, graph={not args.no_graph}: "
+                print(f"{args.frames} frames, bs=1, n_source=3, n_blocks=4, graph={not args.no_graph}, source cache={args.cache_sources}: "
                       f"{dt / args.frames * 1e3:.2f} ms/frame = {args.frames / dt:.1f} frames/s "
                       f"(uint8 RGB {tuple(frames[-1].shape)} on the host)")
 
